@@ -1,0 +1,25 @@
+"""4dcapture-fpv_b200 -- B200-native hot path of 4DCapture-FPV's global_optimization stage.
+
+The directory name is not a Python identifier; import it with
+    import importlib; fpv = importlib.import_module("4dcapture-fpv_b200")
+(tests/conftest.py and bench.py also alias it as `fpv_b200` in sys.modules).
+
+Public surface (each mirrors a reference signature, see the module docstrings):
+    distChamfer(a, b), chamferDist()                      chamfer.py
+    create(...), SMPLXB200                                body_model.py
+    verts_transform, body2world, contact_robust_loss,
+    second_diff_l1, first_diff_l1                         residuals.py
+    distChamferSharded, allreduce_grads, shard_range      sharded.py
+    FitProblem                                            fit.py
+Everything computes on an sm_100 GPU through libfpv_b200.so; there is no CPU or eager fallback.
+"""
+from . import _lib  # noqa: F401
+from .body_model import SMPLXB200, SMPLXOutput, create, load_smplx_npz  # noqa: F401
+from .chamfer import chamferDist, distChamfer, nn_search, pack_planes, unpack_keys  # noqa: F401
+from .fit import FitProblem, LOSS_WEIGHTS  # noqa: F401
+from .residuals import (body2world, contact_robust_loss, first_diff_l1, second_diff_l1,  # noqa: F401
+                        verts_transform)
+from .sharded import allreduce_grads, combine_keys, distChamferSharded, shard_range  # noqa: F401
+from . import synthetic  # noqa: F401
+
+__version__ = "0.1.0"

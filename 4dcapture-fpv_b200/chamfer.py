@@ -1,0 +1,177 @@
+"""Drop-in chamfer operators backed by the sm_100a nearest-neighbour kernels.
+
+Signatures kept:
+  distChamfer(a, b)            /root/reference/chamfer_python.py:18-28, imported at
+                               global_optimization.py:34
+  chamferDist()(xyz1, xyz2)    [3P] ChamferDistancePytorch @ 719b0f1c, called at
+                               global_optimization.py:292-294 and :349-353
+
+Differences from the literal reference, all supersets:
+  * N != M is accepted (chamfer_python.py:24-27 only works for N == M);
+  * `b` may be a single cloud shared by every batch -- [M,3], [1,M,3] or a stride-0 .expand() view --
+    so the T-fold scene copy of global_optimization.py:176 need not exist (a real [bs,M,3] works too);
+  * distances use the canonical direct-difference arithmetic (never negative).
+"""
+from __future__ import annotations
+
+import torch
+
+from . import _lib
+
+
+def _prep(a: torch.Tensor, b: torch.Tensor):
+    if a.dim() != 3 or a.shape[-1] != 3:
+        raise RuntimeError(f"distChamfer: expected a of shape [bs,N,3], got {tuple(a.shape)}")
+    if b.dim() == 2:
+        b = b.unsqueeze(0)
+    if b.dim() != 3 or b.shape[-1] != 3:
+        raise RuntimeError(f"distChamfer: expected b of shape [bs,M,3], got {tuple(b.shape)}")
+    if a.dtype != torch.float32 or b.dtype != torch.float32:
+        raise RuntimeError("distChamfer: float32 inputs required")
+    _lib.require_cuda(a, b)
+    if a.device != b.device:
+        raise RuntimeError("distChamfer: a and b are on different devices")
+    bs = a.shape[0]
+    shared = False
+    if b.shape[0] != bs:
+        if b.shape[0] != 1:
+            raise RuntimeError(f"distChamfer: batch mismatch {bs} vs {b.shape[0]}")
+        shared = True
+    elif bs > 1 and b.stride(0) == 0:
+        b = b[0:1]
+        shared = True
+    if a.shape[1] == 0 or b.shape[1] == 0 or bs == 0:
+        raise RuntimeError("distChamfer: empty cloud (torch.min over an empty dimension)")
+    return a, b, shared
+
+
+class _ChamferFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, a, b, shared: bool, idx_dtype):
+        a_c = a.contiguous()
+        b_c = b.contiguous()
+        bs, N, _ = a_c.shape
+        M = b_c.shape[1]
+        dev = a_c.device
+        L = _lib.lib()
+        d_b2a = torch.empty(bs, M, dtype=torch.float32, device=dev)
+        d_a2b = torch.empty(bs, N, dtype=torch.float32, device=dev)
+        i_b2a = torch.empty(bs, M, dtype=idx_dtype, device=dev)
+        i_a2b = torch.empty(bs, N, dtype=idx_dtype, device=dev)
+        idx_bytes = 8 if idx_dtype == torch.int64 else 4
+        with torch.cuda.device(dev):
+            nbytes = L.fpv_chamfer_fwd_workspace_bytes(bs, N, M, int(shared))
+            ws = _lib.workspace(nbytes, dev)
+            _lib.check(L.fpv_chamfer_fwd(_lib.ptr(a_c), _lib.ptr(b_c), bs, N, M, int(shared),
+                                         _lib.ptr(d_b2a), _lib.ptr(d_a2b), _lib.ptr(i_b2a), _lib.ptr(i_a2b),
+                                         idx_bytes, _lib.ptr(ws), ws.numel(), _lib.stream_ptr()),
+                       "fpv_chamfer_fwd")
+        ctx.save_for_backward(a_c, b_c, i_b2a, i_a2b)
+        ctx.shared = shared
+        ctx.idx_bytes = idx_bytes
+        ctx.mark_non_differentiable(i_b2a, i_a2b)
+        ctx.set_materialize_grads(False)
+        return d_b2a, d_a2b, i_b2a, i_a2b
+
+    @staticmethod
+    def backward(ctx, g_b2a, g_a2b, _g1, _g2):
+        a, b, i_b2a, i_a2b = ctx.saved_tensors  # never mutated: backward(retain_graph=True) is safe (:591)
+        need_a, need_b = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
+        if not (need_a or need_b) or (g_b2a is None and g_a2b is None):
+            return None, None, None, None
+        bs, N, _ = a.shape
+        M = b.shape[1]
+        dev = a.device
+        L = _lib.lib()
+        g1 = g_b2a.contiguous().float() if g_b2a is not None else None
+        g2 = g_a2b.contiguous().float() if g_a2b is not None else None
+        grad_a = torch.empty_like(a)
+        grad_b = torch.empty_like(b) if need_b else None
+        with torch.cuda.device(dev):
+            nbytes = L.fpv_chamfer_bwd_workspace_bytes(bs, N, M, int(ctx.shared), int(need_b))
+            ws = _lib.workspace(nbytes, dev)
+            _lib.check(L.fpv_chamfer_bwd(_lib.ptr(a), _lib.ptr(b), bs, N, M, int(ctx.shared),
+                                         _lib.ptr(g1), _lib.ptr(g2), _lib.ptr(i_b2a), _lib.ptr(i_a2b),
+                                         ctx.idx_bytes, _lib.ptr(grad_a), _lib.ptr(grad_b),
+                                         _lib.ptr(ws), ws.numel(), _lib.stream_ptr()),
+                       "fpv_chamfer_bwd")
+        return (grad_a if need_a else None), grad_b, None, None
+
+
+def distChamfer(a: torch.Tensor, b: torch.Tensor, idx_dtype: torch.dtype = torch.int64):
+    """chamfer_python.distChamfer: returns (d_b2a [bs,M], d_a2b [bs,N], i_b2a [bs,M], i_a2b [bs,N]).
+
+    Squared distances, both directions, lowest index on ties, differentiable w.r.t. a and b through
+    the argmin (chamfer_python.py:28).  Indices are int64 as torch.min returns them; pass
+    idx_dtype=torch.int32 to halve the index traffic.
+    """
+    if idx_dtype not in (torch.int64, torch.int32):
+        raise RuntimeError("distChamfer: idx_dtype must be torch.int64 or torch.int32")
+    a, b, shared = _prep(a, b)
+    return _ChamferFn.apply(a, b, shared, idx_dtype)
+
+
+class chamferDist(torch.nn.Module):
+    """[3P] dist_chamfer.chamferDist as used at global_optimization.py:292-294:
+    forward(xyz1 [bs,N,3], xyz2 [bs,M,3]) -> (dist1 [bs,N], dist2 [bs,M])."""
+
+    def forward(self, xyz1: torch.Tensor, xyz2: torch.Tensor):
+        d_2to1, d_1to2, _, _ = distChamfer(xyz1, xyz2, idx_dtype=torch.int32)
+        return d_1to2, d_2to1
+
+
+def nn_search(queries: torch.Tensor, planes: torch.Tensor, M: int, *, ref_batches: int = 1,
+              idx_base: int = 0, want_keys: bool = False, idx_dtype: torch.dtype = torch.int32):
+    """One-direction search against pre-packed candidate planes (see pack_planes).
+
+    queries [B,N,3] -> (dist [B,N], idx [B,N]) or, with want_keys, the packed uint64 combine keys
+    (returned as int64: the sign bit is never set because canonical distances are non-negative).
+    """
+    _lib.require_cuda(queries, planes)
+    q = queries.contiguous()
+    B, N, _ = q.shape
+    dev = q.device
+    L = _lib.lib()
+    with torch.cuda.device(dev):
+        ws = _lib.workspace(L.fpv_nn_search_workspace_bytes(B, N, M), dev)
+        if want_keys:
+            keys = torch.empty(B, N, dtype=torch.int64, device=dev)
+            _lib.check(L.fpv_nn_search(_lib.ptr(q), 0, B, N, _lib.ptr(planes), ref_batches, M, idx_base,
+                                       None, None, 0, _lib.ptr(keys), _lib.ptr(ws), ws.numel(),
+                                       _lib.stream_ptr()), "fpv_nn_search")
+            return keys
+        dist = torch.empty(B, N, dtype=torch.float32, device=dev)
+        idx = torch.empty(B, N, dtype=idx_dtype, device=dev)
+        _lib.check(L.fpv_nn_search(_lib.ptr(q), 0, B, N, _lib.ptr(planes), ref_batches, M, idx_base,
+                                   _lib.ptr(dist), _lib.ptr(idx), 8 if idx_dtype == torch.int64 else 4,
+                                   None, _lib.ptr(ws), ws.numel(), _lib.stream_ptr()), "fpv_nn_search")
+    return dist, idx
+
+
+def pack_planes(points: torch.Tensor) -> torch.Tensor:
+    """[B,M,3] (or [M,3]) -> the padded SoA candidate planes the search kernel streams."""
+    if points.dim() == 2:
+        points = points.unsqueeze(0)
+    _lib.require_cuda(points)
+    p = points.contiguous()
+    B, M, _ = p.shape
+    L = _lib.lib()
+    with torch.cuda.device(p.device):
+        planes = torch.empty(L.fpv_nn_planes_bytes(B, M) // 4, dtype=torch.float32, device=p.device)
+        _lib.check(L.fpv_nn_pack_planes(_lib.ptr(p), B, M, _lib.ptr(planes), _lib.stream_ptr()),
+                   "fpv_nn_pack_planes")
+    return planes
+
+
+def unpack_keys(keys: torch.Tensor, idx_dtype: torch.dtype = torch.int32):
+    """Packed combine keys -> (dist f32, idx)."""
+    _lib.require_cuda(keys)
+    k = keys.contiguous()
+    L = _lib.lib()
+    dist = torch.empty(k.shape, dtype=torch.float32, device=k.device)
+    idx = torch.empty(k.shape, dtype=idx_dtype, device=k.device)
+    with torch.cuda.device(k.device):
+        _lib.check(L.fpv_nn_unpack_keys(_lib.ptr(k), k.numel(), _lib.ptr(dist), _lib.ptr(idx),
+                                        8 if idx_dtype == torch.int64 else 4, _lib.stream_ptr()),
+                   "fpv_nn_unpack_keys")
+    return dist, idx

@@ -1,0 +1,637 @@
+// nn_search.cu -- exact brute-force nearest neighbour (fused min + argmin) and the chamfer
+// forward/backward built on it.  sm_100a only.
+//
+// Replaces: chamfer_python.py:18-28 (distChamfer: three bmm + four reductions over a dense
+// [bs,N,M] matrix) and the [3P] NmDistanceKernel behind ext.chamferDist()
+// (global_optimization.py:292-294).  Design:
+//   * candidates live in padded SoA planes; a producer warp streams 1024-point tiles of the three
+//     planes into a 4-stage shared-memory ring with cp.async.bulk (TMA engine) + mbarriers;
+//   * 8 consumer warps hold QPT queries per thread in registers and evaluate four candidates per
+//     step from three broadcast LDS.128, with packed FADD2/FMUL2/FFMA2 (two candidates per
+//     instruction) -- the canonical d = fma(dz,dz,fma(dy,dy,dx*dx)) bit for bit;
+//   * the running minimum is a FMNMX3 chain; the argmin is only resolved on the (rare) steps in
+//     which the minimum strictly improved, so ties keep the lowest index;
+//   * candidate ranges can be split across CTAs; partial winners merge through a 64-bit
+//     (distance bits << 32 | index) atomicMin -- the same key the multi-GPU combine uses.
+#include <math_constants.h>
+
+#include "common.cuh"
+
+namespace fpv {
+
+constexpr int NN_THREADS = 256;  // consumer threads (8 warps) + 1 producer warp
+constexpr int NN_TILE = 1024;    // candidates per pipeline stage
+constexpr int NN_STAGES = 4;
+constexpr int NN_PAD = 32;       // plane length granularity (points)
+constexpr size_t NN_SMEM = size_t(NN_STAGES) * 3 * NN_TILE * sizeof(float) + 2 * NN_STAGES * sizeof(uint64_t);
+
+static int g_tune_qpt = 0;      // 0 = heuristic
+static int g_tune_nsplit = 0;   // 0 = heuristic
+
+struct NNParams {
+    const float *q;
+    int64_t q_bstride;  // floats between query batches (0 = shared)
+    int64_t N;          // queries per batch
+    const float *planes;
+    int64_t plane_bstride;  // floats between candidate batches (0 = shared)
+    int64_t Mp;             // plane length
+    int64_t M8;             // candidates scanned (M rounded up to 8; the pad is +inf)
+    int64_t chunk;          // candidates per blockIdx.y slice (multiple of NN_TILE)
+    int64_t idx_base;
+    float *dist;
+    void *idx;
+    int idx_bytes;
+    unsigned long long *keys;
+    int keys_atomic;
+};
+
+__device__ __forceinline__ float d2_scalar(float x, float y, float z, float rx, float ry, float rz) {
+    const float dx = __fsub_rn(x, rx), dy = __fsub_rn(y, ry), dz = __fsub_rn(z, rz);
+    return __fmaf_rn(dz, dz, __fmaf_rn(dy, dy, __fmul_rn(dx, dx)));
+}
+
+// Four candidates (one float4 per plane) against QPT register-resident queries.
+template <int QPT>
+__device__ __forceinline__ void nn_step(const float4 rx, const float4 ry, const float4 rz, const int j,
+                                        const float2 (&qx)[QPT], const float2 (&qy)[QPT],
+                                        const float2 (&qz)[QPT], float (&best)[QPT], int (&bidx)[QPT]) {
+    float mnew[QPT];
+    bool any = false;
+    const float2 nx0 = make_float2(-rx.x, -rx.y), nx1 = make_float2(-rx.z, -rx.w);
+    const float2 ny0 = make_float2(-ry.x, -ry.y), ny1 = make_float2(-ry.z, -ry.w);
+    const float2 nz0 = make_float2(-rz.x, -rz.y), nz1 = make_float2(-rz.z, -rz.w);
+#pragma unroll
+    for (int q = 0; q < QPT; ++q) {
+        const float2 dx0 = __fadd2_rn(qx[q], nx0), dx1 = __fadd2_rn(qx[q], nx1);
+        const float2 dy0 = __fadd2_rn(qy[q], ny0), dy1 = __fadd2_rn(qy[q], ny1);
+        const float2 dz0 = __fadd2_rn(qz[q], nz0), dz1 = __fadd2_rn(qz[q], nz1);
+        float2 s0 = __fmul2_rn(dx0, dx0), s1 = __fmul2_rn(dx1, dx1);
+        s0 = __ffma2_rn(dy0, dy0, s0);
+        s1 = __ffma2_rn(dy1, dy1, s1);
+        s0 = __ffma2_rn(dz0, dz0, s0);
+        s1 = __ffma2_rn(dz1, dz1, s1);
+        float m = fmin3(best[q], s0.x, s0.y);
+        m = fmin3(m, s1.x, s1.y);
+        mnew[q] = m;
+        any |= (m < best[q]);
+    }
+    if (any) {  // rare after the first few tiles: resolve WHICH candidate, lowest index first
+#pragma unroll
+        for (int q = 0; q < QPT; ++q) {
+            if (mnew[q] < best[q]) {
+                const float x = qx[q].x, y = qy[q].x, z = qz[q].x, m = mnew[q];
+                const float e0 = d2_scalar(x, y, z, rx.x, ry.x, rz.x);
+                const float e1 = d2_scalar(x, y, z, rx.y, ry.y, rz.y);
+                const float e2 = d2_scalar(x, y, z, rx.z, ry.z, rz.z);
+                bidx[q] = j + ((e0 == m) ? 0 : (e1 == m) ? 1 : (e2 == m) ? 2 : 3);
+            }
+        }
+    }
+#pragma unroll
+    for (int q = 0; q < QPT; ++q) best[q] = mnew[q];
+}
+
+template <int QPT>
+__global__ void __launch_bounds__(NN_THREADS + 32, (QPT <= 4) ? 2 : 1) nn_search_kernel(const NNParams p) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    float *tiles = reinterpret_cast<float *>(smem_raw);  // [STAGES][3][TILE]
+    uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw + size_t(NN_STAGES) * 3 * NN_TILE * sizeof(float));
+    uint64_t *empty = full + NN_STAGES;
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int64_t b = blockIdx.z;
+    const int64_t r0 = int64_t(blockIdx.y) * p.chunk;
+    const int64_t r1 = (r0 + p.chunk < p.M8) ? (r0 + p.chunk) : p.M8;
+    const int ntiles = int((r1 - r0 + NN_TILE - 1) / NN_TILE);
+
+    if (tid == 0) {
+#pragma unroll
+        for (int s = 0; s < NN_STAGES; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], NN_THREADS / 32);
+        }
+        mbar_fence_init();
+    }
+    __syncthreads();
+
+    if (warp == NN_THREADS / 32) {  // ---- producer warp: one lane drives the TMA engine ----
+        if (lane == 0) {
+            const float *src = p.planes + b * p.plane_bstride + r0;
+            for (int k = 0; k < ntiles; ++k) {
+                const int s = k % NN_STAGES;
+                const uint32_t ph = (k / NN_STAGES) & 1;
+                mbar_wait(&empty[s], ph ^ 1);
+                const int64_t rem = r1 - r0 - int64_t(k) * NN_TILE;
+                const uint32_t bytes = uint32_t(rem < NN_TILE ? rem : NN_TILE) * 4u;
+                float *dst = tiles + size_t(s) * 3 * NN_TILE;
+                const float *g = src + int64_t(k) * NN_TILE;
+                mbar_arrive_expect_tx(&full[s], 3 * bytes);
+                bulk_g2s(dst, g, bytes, &full[s]);
+                bulk_g2s(dst + NN_TILE, g + p.Mp, bytes, &full[s]);
+                bulk_g2s(dst + 2 * NN_TILE, g + 2 * p.Mp, bytes, &full[s]);
+            }
+        }
+        return;
+    }
+
+    // ---- consumer warps ----
+    float2 qx[QPT], qy[QPT], qz[QPT];
+    float best[QPT];
+    int bidx[QPT];
+    const int64_t qbase = int64_t(blockIdx.x) * (NN_THREADS * QPT);
+    const float *qsrc = p.q + b * p.q_bstride;
+#pragma unroll
+    for (int k = 0; k < QPT; ++k) {
+        int64_t qi = qbase + int64_t(k) * NN_THREADS + tid;
+        if (qi > p.N - 1) qi = p.N - 1;
+        const float x = __ldg(qsrc + 3 * qi), y = __ldg(qsrc + 3 * qi + 1), z = __ldg(qsrc + 3 * qi + 2);
+        qx[k] = make_float2(x, x);
+        qy[k] = make_float2(y, y);
+        qz[k] = make_float2(z, z);
+        best[k] = CUDART_INF_F;
+        bidx[k] = 0;
+    }
+
+    for (int k = 0; k < ntiles; ++k) {
+        const int s = k % NN_STAGES;
+        const uint32_t ph = (k / NN_STAGES) & 1;
+        mbar_wait(&full[s], ph);
+        const float4 *X = reinterpret_cast<const float4 *>(tiles + size_t(s) * 3 * NN_TILE);
+        const float4 *Y = X + NN_TILE / 4;
+        const float4 *Z = Y + NN_TILE / 4;
+        const int64_t rem = r1 - r0 - int64_t(k) * NN_TILE;
+        const int cnt4 = int(rem < NN_TILE ? rem : NN_TILE) >> 2;  // even: M8 is a multiple of 8
+        const int jbase = int(r0) + k * NN_TILE;
+#pragma unroll 2
+        for (int j4 = 0; j4 < cnt4; ++j4) {
+            nn_step<QPT>(X[j4], Y[j4], Z[j4], jbase + 4 * j4, qx, qy, qz, best, bidx);
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty[s]);
+    }
+
+#pragma unroll
+    for (int k = 0; k < QPT; ++k) {
+        const int64_t qi = qbase + int64_t(k) * NN_THREADS + tid;
+        if (qi < p.N) {
+            const int64_t o = b * p.N + qi;
+            const int64_t gi = p.idx_base + bidx[k];
+            if (p.keys) {
+                const unsigned long long key =
+                    (static_cast<unsigned long long>(__float_as_uint(best[k])) << 32) |
+                    static_cast<unsigned long long>(static_cast<uint32_t>(gi));
+                if (p.keys_atomic)
+                    atomicMin(p.keys + o, key);
+                else
+                    p.keys[o] = key;
+            } else {
+                p.dist[o] = best[k];
+                if (p.idx_bytes == 8)
+                    static_cast<long long *>(p.idx)[o] = gi;
+                else if (p.idx_bytes == 4)
+                    static_cast<int *>(p.idx)[o] = int(gi);
+            }
+        }
+    }
+}
+
+__global__ void pack_planes_kernel(const float *__restrict__ pts, int64_t M, int64_t Mp, float *__restrict__ planes) {
+    const int64_t b = blockIdx.y;
+    const int64_t j = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (j >= Mp) return;
+    float x = CUDART_INF_F, y = CUDART_INF_F, z = CUDART_INF_F;
+    if (j < M) {
+        const float *s = pts + (b * M + j) * 3;
+        x = s[0];
+        y = s[1];
+        z = s[2];
+    }
+    float *d = planes + b * 3 * Mp;
+    d[j] = x;
+    d[Mp + j] = y;
+    d[2 * Mp + j] = z;
+}
+
+__global__ void unpack_keys_kernel(const unsigned long long *__restrict__ keys, int64_t n, float *dist, void *idx,
+                                   int idx_bytes) {
+    const int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const unsigned long long k = keys[i];
+    if (dist) dist[i] = __uint_as_float(static_cast<uint32_t>(k >> 32));
+    const uint32_t lo = static_cast<uint32_t>(k);
+    if (idx_bytes == 8)
+        static_cast<long long *>(idx)[i] = static_cast<long long>(lo);
+    else if (idx_bytes == 4)
+        static_cast<int *>(idx)[i] = static_cast<int>(lo);
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+static int64_t planes_len(int64_t M) { return ceil_div(M, NN_PAD) * NN_PAD; }
+
+struct NNPlan {
+    int qpt;
+    int64_t qblocks;
+    int nsplit;
+    int64_t chunk, M8;
+};
+
+static NNPlan nn_plan(int64_t batches, int64_t N, int64_t M) {
+    NNPlan pl;
+    const int sms = sm_count();
+    const int64_t total_q = batches * N;
+    pl.qpt = (total_q >= int64_t(sms) * NN_THREADS * 8 * 2) ? 8 : 4;
+    if (g_tune_qpt == 4 || g_tune_qpt == 8) pl.qpt = g_tune_qpt;
+    pl.qblocks = ceil_div(N, int64_t(NN_THREADS) * pl.qpt);
+    pl.M8 = ceil_div(M, 8) * 8;
+    const int64_t base = pl.qblocks * batches;
+    const int64_t target = int64_t(sms) * 16;  // >= 8 waves at 2 CTAs/SM: tail below ~6%
+    int64_t ns = ceil_div(target, base);
+    const int64_t max_ns = pl.M8 / (4 * NN_TILE) > 1 ? pl.M8 / (4 * NN_TILE) : 1;
+    if (ns > max_ns) ns = max_ns;
+    if (ns > 65535) ns = 65535;
+    if (g_tune_nsplit > 0) ns = g_tune_nsplit;
+    pl.chunk = ceil_div(ceil_div(pl.M8, ns), NN_TILE) * NN_TILE;
+    pl.nsplit = int(ceil_div(pl.M8, pl.chunk));
+    return pl;
+}
+
+template <int QPT>
+static cudaError_t nn_launch(const NNParams &p, dim3 grid, cudaStream_t st) {
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(nn_search_kernel<QPT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             int(NN_SMEM));
+        if (e != cudaSuccess) return e;
+        configured = true;
+    }
+    nn_search_kernel<QPT><<<grid, NN_THREADS + 32, NN_SMEM, st>>>(p);
+    return cudaGetLastError();
+}
+
+// One direction.  Flattens the batch axis when one candidate set serves every batch.
+static int nn_search_impl(const float *queries, int q_shared, int64_t batches, int64_t N, const float *ref_planes,
+                          int64_t ref_batches, int64_t M, int64_t idx_base, float *dist, void *idx, int idx_bytes,
+                          uint64_t *keys, void *workspace, size_t workspace_bytes, cudaStream_t st) {
+    FPV_CHECK_ARG(batches > 0 && N > 0 && M > 0, "nn_search: empty input (batches=%lld N=%lld M=%lld)",
+                  (long long)batches, (long long)N, (long long)M);
+    FPV_CHECK_ARG(ref_batches == 1 || ref_batches == batches, "nn_search: ref_batches must be 1 or batches");
+    FPV_CHECK_ARG(idx_bytes == 0 || idx_bytes == 4 || idx_bytes == 8, "nn_search: idx_bytes must be 0, 4 or 8");
+    FPV_CHECK_ARG(M + idx_base <= 0xffffffffll && idx_base >= 0, "nn_search: index range exceeds 32 bits");
+    FPV_CHECK_ARG(keys || (dist && (idx || idx_bytes == 0)), "nn_search: no output requested");
+    const int64_t Mp = planes_len(M);
+    int64_t eb = batches, eN = N;
+    int64_t q_bstride = q_shared ? 0 : N * 3;
+    int64_t plane_bstride = (ref_batches == 1) ? 0 : 3 * Mp;
+    if (ref_batches == 1 && !q_shared) {  // every query meets the same candidates: one flat batch
+        eN = batches * N;
+        eb = 1;
+        q_bstride = 0;
+    }
+    FPV_CHECK_ARG(eb <= 65535, "nn_search: more than 65535 candidate batches");
+    const NNPlan pl = nn_plan(eb, eN, M);
+    NNParams p;
+    p.q = queries;
+    p.q_bstride = q_bstride;
+    p.N = eN;
+    p.planes = ref_planes;
+    p.plane_bstride = plane_bstride;
+    p.Mp = Mp;
+    p.M8 = pl.M8;
+    p.chunk = pl.chunk;
+    p.idx_base = idx_base;
+    p.dist = dist;
+    p.idx = idx;
+    p.idx_bytes = idx_bytes;
+    p.keys = reinterpret_cast<unsigned long long *>(keys);
+    p.keys_atomic = 0;
+    const int64_t total = eb * eN;
+    unsigned long long *scratch_keys = nullptr;
+    if (pl.nsplit > 1) {
+        if (!keys) {
+            Arena ar(workspace, workspace_bytes);
+            scratch_keys = ar.take<unsigned long long>(size_t(total));
+            if (!scratch_keys) {
+                set_error("nn_search: workspace too small (%zu bytes, need %zu)", workspace_bytes,
+                          align_up(size_t(total) * 8, 256));
+                return FPV_ERR_WORKSPACE;
+            }
+            p.keys = scratch_keys;
+        }
+        p.keys_atomic = 1;
+        FPV_CUDA(cudaMemsetAsync(p.keys, 0xff, size_t(total) * 8, st));
+    }
+    dim3 grid((unsigned)pl.qblocks, (unsigned)pl.nsplit, (unsigned)eb);
+    if (profile_on()) {
+        // algorithmic bytes: every distinct query point and candidate once, outputs once
+        const double qpts = double(q_shared ? N : batches * N), out_b = keys && !dist ? 8.0 : 4.0 + idx_bytes;
+        char nm[48];
+        snprintf(nm, sizeof(nm), "nn_search<%d> Q=%lld M=%lld", pl.qpt, (long long)total, (long long)M);
+        profile_begin(nm, st, 12.0 * qpts + 12.0 * double(M) * double(ref_batches) + out_b * double(total),
+                      double(total) * double(M));
+    }
+    cudaError_t e = (pl.qpt == 8) ? nn_launch<8>(p, grid, st) : nn_launch<4>(p, grid, st);
+    profile_end(st);
+    count_launch();
+    if (e != cudaSuccess) {
+        set_error("nn_search_kernel launch failed: %s", cudaGetErrorString(e));
+        return FPV_ERR_CUDA;
+    }
+    if (scratch_keys || (keys && dist)) {  // split merge, or caller wants keys AND plain outputs
+        const unsigned long long *src = scratch_keys ? scratch_keys : p.keys;
+        unpack_keys_kernel<<<(unsigned)ceil_div(total, 256), 256, 0, st>>>(src, total, dist, idx, idx_bytes);
+        FPV_LAUNCH_CHECK("unpack_keys_kernel");
+    }
+    return FPV_OK;
+}
+
+static size_t nn_search_ws(int64_t batches, int64_t N, int64_t M, int ref_shared) {
+    int64_t eb = batches, eN = N;
+    if (ref_shared) {
+        eN = batches * N;
+        eb = 1;
+    }
+    const NNPlan pl = nn_plan(eb, eN, M);
+    return pl.nsplit > 1 ? align_up(size_t(eb * eN) * 8, 256) : 0;
+}
+
+static int pack_planes_impl(const float *pts, int64_t batches, int64_t M, float *planes, cudaStream_t st) {
+    FPV_CHECK_ARG(batches > 0 && M > 0, "pack_planes: empty input");
+    FPV_CHECK_ARG(batches <= 65535, "pack_planes: more than 65535 batches");
+    const int64_t Mp = planes_len(M);
+    dim3 grid((unsigned)ceil_div(Mp, 256), (unsigned)batches);
+    pack_planes_kernel<<<grid, 256, 0, st>>>(pts, M, Mp, planes);
+    FPV_LAUNCH_CHECK("pack_planes_kernel");
+    return FPV_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// chamfer backward: gather for the direct term, fixed-point integer scatter for the argmin term
+// ---------------------------------------------------------------------------------------------
+template <typename IdxT>
+__global__ void bwd_cmax_kernel(const float *__restrict__ x, int64_t x_bstride, int64_t N, const float *__restrict__ y,
+                                int64_t y_bstride, const float *__restrict__ g, const IdxT *__restrict__ idx,
+                                unsigned *cmax_bits) {
+    const int64_t b = blockIdx.y;
+    const int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    float c = 0.f;
+    if (i < N) {
+        const int64_t j = static_cast<int64_t>(idx[b * N + i]);
+        const float *xi = x + b * x_bstride + 3 * i, *yj = y + b * y_bstride + 3 * j;
+        const float g2 = fabsf(__fmul_rn(2.f, g[b * N + i]));
+        const float m = fmaxf(fabsf(__fsub_rn(xi[0], yj[0])),
+                              fmaxf(fabsf(__fsub_rn(xi[1], yj[1])), fabsf(__fsub_rn(xi[2], yj[2]))));
+        c = __fmul_rn(g2, m);
+        if (!(c == c)) c = CUDART_INF_F;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) c = fmaxf(c, __shfl_xor_sync(0xffffffffu, c, o));
+    if ((threadIdx.x & 31) == 0 && c > 0.f) atomicMax(cmax_bits, __float_as_uint(c));
+}
+
+// power-of-two fixed-point exponent: |c| <= cmax < 2^e, at most 2^nb addends => sum < 2^(e+nb+k) <= 2^62
+__device__ __forceinline__ int fix_exponent(unsigned cmax_bits, int nb_bits) {
+    const float cm = __uint_as_float(cmax_bits);
+    if (!(cm > 0.f)) return 0;
+    int e;
+    frexpf(cm, &e);
+    int k = 62 - nb_bits - e;
+    return k < -120 ? -120 : (k > 120 ? 120 : k);
+}
+
+// For every (b,i): j = idx[b,i]; c = 2 g (x_i - y_j).  to_y: acc[b*acc_bstride + 3j..] -= c ; else
+// acc[b*acc_bstride + 3i..] += c (used when the target cloud is shared across batches).
+template <typename IdxT>
+__global__ void bwd_accum_kernel(const float *__restrict__ x, int64_t x_bstride, int64_t N, const float *__restrict__ y,
+                                 int64_t y_bstride, const float *__restrict__ g, const IdxT *__restrict__ idx,
+                                 const unsigned *__restrict__ cmax_bits, int nb_bits, int to_y, long long *acc,
+                                 int64_t acc_bstride) {
+    const int64_t b = blockIdx.y;
+    const int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    const float scale = ldexpf(1.f, fix_exponent(*cmax_bits, nb_bits));
+    const int64_t j = static_cast<int64_t>(idx[b * N + i]);
+    const float *xi = x + b * x_bstride + 3 * i, *yj = y + b * y_bstride + 3 * j;
+    const float g2 = __fmul_rn(2.f, g[b * N + i]);
+    unsigned long long *dst =
+        reinterpret_cast<unsigned long long *>(acc + b * acc_bstride + 3 * (to_y ? j : i));
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        float c = __fmul_rn(g2, __fsub_rn(xi[k], yj[k]));
+        if (to_y) c = -c;
+        const long long f = __float2ll_rn(__fmul_rn(c, scale));
+        if (f != 0) atomicAdd(dst + k, static_cast<unsigned long long>(f));
+    }
+}
+
+// grad[b,i,:] = (direct ? 2 g (x_i - y_idx) : 0) + acc * 2^-k
+template <typename IdxT>
+__global__ void bwd_finish_kernel(const float *__restrict__ x, int64_t N, const float *__restrict__ y,
+                                  int64_t y_bstride, const float *__restrict__ g, const IdxT *__restrict__ idx,
+                                  const unsigned *__restrict__ cmax_bits, int nb_bits, const long long *__restrict__ acc,
+                                  float *__restrict__ grad) {
+    const int64_t b = blockIdx.y;
+    const int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    float d[3] = {0.f, 0.f, 0.f};
+    if (g) {
+        const int64_t j = static_cast<int64_t>(idx[b * N + i]);
+        const float *xi = x + (b * N + i) * 3, *yj = y + b * y_bstride + 3 * j;
+        const float g2 = __fmul_rn(2.f, g[b * N + i]);
+#pragma unroll
+        for (int k = 0; k < 3; ++k) d[k] = __fmul_rn(g2, __fsub_rn(xi[k], yj[k]));
+    }
+    if (acc) {
+        const double inv = ldexp(1.0, -fix_exponent(*cmax_bits, nb_bits));
+#pragma unroll
+        for (int k = 0; k < 3; ++k) d[k] = __fadd_rn(d[k], float(double(acc[(b * N + i) * 3 + k]) * inv));
+    }
+#pragma unroll
+    for (int k = 0; k < 3; ++k) grad[(b * N + i) * 3 + k] = d[k];
+}
+
+static int ilog2_ceil(int64_t n) {
+    int b = 0;
+    while ((int64_t(1) << b) < n) ++b;
+    return b;
+}
+
+template <typename IdxT>
+static int chamfer_bwd_impl(const float *a, const float *b, int64_t bs, int64_t N, int64_t M, int b_shared,
+                            const float *g_b2a, const float *g_a2b, const IdxT *i_b2a, const IdxT *i_a2b,
+                            float *grad_a, float *grad_b, void *workspace, size_t workspace_bytes, cudaStream_t st) {
+    Arena ar(workspace, workspace_bytes);
+    unsigned *cmax = ar.take<unsigned>(2);
+    long long *acc_a = g_b2a ? ar.take<long long>(size_t(bs * N * 3)) : nullptr;
+    const int64_t gb_batches = b_shared ? 1 : bs;
+    const bool need_acc_b = grad_b && (g_a2b || (b_shared && g_b2a));
+    long long *acc_b = need_acc_b ? ar.take<long long>(size_t(gb_batches * M * 3)) : nullptr;
+    if (!cmax || (g_b2a && !acc_a) || (need_acc_b && !acc_b)) {
+        set_error("chamfer_bwd: workspace too small (%zu bytes)", workspace_bytes);
+        return FPV_ERR_WORKSPACE;
+    }
+    const int64_t b_bstride = b_shared ? 0 : M * 3;
+    FPV_CUDA(cudaMemsetAsync(cmax, 0, 2 * sizeof(unsigned), st));
+    dim3 gridN((unsigned)ceil_div(N, 256), (unsigned)bs), gridM((unsigned)ceil_div(M, 256), (unsigned)bs);
+
+    // ---- grad_a = 2 g_a2b (a_i - b_idx)  +  sum_{j: i_b2a[j]==i} 2 g_b2a[j] (a_i - b_j)
+    const int nb_a = ilog2_ceil(M) + 1;
+    if (g_b2a) {
+        FPV_CUDA(cudaMemsetAsync(acc_a, 0, size_t(bs * N * 3) * sizeof(long long), st));
+        bwd_cmax_kernel<IdxT><<<gridM, 256, 0, st>>>(b, b_bstride, M, a, N * 3, g_b2a, i_b2a, cmax);
+        FPV_LAUNCH_CHECK("bwd_cmax_kernel");
+        bwd_accum_kernel<IdxT><<<gridM, 256, 0, st>>>(b, b_bstride, M, a, N * 3, g_b2a, i_b2a, cmax, nb_a, 1, acc_a,
+                                                      N * 3);
+        FPV_LAUNCH_CHECK("bwd_accum_kernel");
+    }
+    bwd_finish_kernel<IdxT><<<gridN, 256, 0, st>>>(a, N, b, b_bstride, g_a2b, i_a2b, cmax, nb_a, acc_a, grad_a);
+    FPV_LAUNCH_CHECK("bwd_finish_kernel");
+
+    // ---- grad_b = 2 g_b2a (b_j - a_idx)  +  sum_{i: i_a2b[i]==j} 2 g_a2b[i] (b_j - a_i)
+    if (grad_b) {
+        const int nb_b = ilog2_ceil(b_shared ? bs * (N + 1) : N) + 1;
+        if (acc_b) FPV_CUDA(cudaMemsetAsync(acc_b, 0, size_t(gb_batches * M * 3) * sizeof(long long), st));
+        if (g_a2b) {
+            bwd_cmax_kernel<IdxT><<<gridN, 256, 0, st>>>(a, N * 3, N, b, b_bstride, g_a2b, i_a2b, cmax + 1);
+            FPV_LAUNCH_CHECK("bwd_cmax_kernel");
+        }
+        if (b_shared && g_b2a) {
+            bwd_cmax_kernel<IdxT><<<gridM, 256, 0, st>>>(b, 0, M, a, N * 3, g_b2a, i_b2a, cmax + 1);
+            FPV_LAUNCH_CHECK("bwd_cmax_kernel");
+        }
+        if (g_a2b) {
+            bwd_accum_kernel<IdxT><<<gridN, 256, 0, st>>>(a, N * 3, N, b, b_bstride, g_a2b, i_a2b, cmax + 1, nb_b, 1,
+                                                          acc_b, b_shared ? 0 : M * 3);
+            FPV_LAUNCH_CHECK("bwd_accum_kernel");
+        }
+        if (b_shared) {
+            if (g_b2a) {
+                bwd_accum_kernel<IdxT><<<gridM, 256, 0, st>>>(b, 0, M, a, N * 3, g_b2a, i_b2a, cmax + 1, nb_b, 0,
+                                                              acc_b, 0);
+                FPV_LAUNCH_CHECK("bwd_accum_kernel");
+            }
+            dim3 grid1((unsigned)ceil_div(M, 256), 1);
+            bwd_finish_kernel<IdxT><<<grid1, 256, 0, st>>>(b, M, a, 0, nullptr, i_b2a, cmax + 1, nb_b, acc_b, grad_b);
+            FPV_LAUNCH_CHECK("bwd_finish_kernel");
+        } else {
+            bwd_finish_kernel<IdxT><<<gridM, 256, 0, st>>>(b, M, a, N * 3, g_b2a, i_b2a, cmax + 1, nb_b, acc_b, grad_b);
+            FPV_LAUNCH_CHECK("bwd_finish_kernel");
+        }
+    }
+    return FPV_OK;
+}
+
+}  // namespace fpv
+
+// ---------------------------------------------------------------------------------------------
+// C ABI
+// ---------------------------------------------------------------------------------------------
+using namespace fpv;
+
+extern "C" {
+
+size_t fpv_nn_planes_bytes(int64_t batches, int64_t M) {
+    if (batches <= 0 || M <= 0) return 0;
+    return align_up(size_t(batches) * 3 * size_t(planes_len(M)) * sizeof(float), 256);
+}
+
+int fpv_nn_pack_planes(const float *pts, int64_t batches, int64_t M, float *planes, fpv_stream_t stream) {
+    FPV_CHECK_ARG(pts && planes, "fpv_nn_pack_planes: null pointer");
+    return pack_planes_impl(pts, batches, M, planes, static_cast<cudaStream_t>(stream));
+}
+
+size_t fpv_nn_search_workspace_bytes(int64_t batches, int64_t N, int64_t M) {
+    if (batches <= 0 || N <= 0 || M <= 0) return 0;
+    const size_t a = nn_search_ws(batches, N, M, 0), b = nn_search_ws(batches, N, M, 1);
+    return (a > b ? a : b) + 256;
+}
+
+int fpv_nn_search(const float *queries, int q_shared, int64_t batches, int64_t N, const float *ref_planes,
+                  int64_t ref_batches, int64_t M, int64_t idx_base, float *dist, void *idx, int idx_bytes,
+                  uint64_t *keys, void *workspace, size_t workspace_bytes, fpv_stream_t stream) {
+    FPV_CHECK_ARG(queries && ref_planes, "fpv_nn_search: null input pointer");
+    return nn_search_impl(queries, q_shared, batches, N, ref_planes, ref_batches, M, idx_base, dist, idx, idx_bytes,
+                          keys, workspace, workspace_bytes, static_cast<cudaStream_t>(stream));
+}
+
+int fpv_nn_unpack_keys(const uint64_t *keys, int64_t n, float *dist, void *idx, int idx_bytes, fpv_stream_t stream) {
+    FPV_CHECK_ARG(keys && n > 0, "fpv_nn_unpack_keys: empty input");
+    FPV_CHECK_ARG((idx_bytes == 4 || idx_bytes == 8) && idx, "fpv_nn_unpack_keys: idx_bytes must be 4 or 8");
+    unpack_keys_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        reinterpret_cast<const unsigned long long *>(keys), n, dist, idx, idx_bytes);
+    FPV_LAUNCH_CHECK("unpack_keys_kernel");
+    return FPV_OK;
+}
+
+// Debug/tuning hook (bench sweeps): force queries-per-thread (4|8) and the candidate split; 0 = heuristic.
+int fpv_nn_set_tuning(int qpt, int nsplit) {
+    g_tune_qpt = qpt;
+    g_tune_nsplit = nsplit;
+    return FPV_OK;
+}
+
+size_t fpv_chamfer_fwd_workspace_bytes(int64_t bs, int64_t N, int64_t M, int b_shared) {
+    if (bs <= 0 || N <= 0 || M <= 0) return 0;
+    size_t s = fpv_nn_planes_bytes(bs, N) + fpv_nn_planes_bytes(b_shared ? 1 : bs, M);
+    const size_t w1 = nn_search_ws(bs, N, M, b_shared ? 1 : 0), w2 = nn_search_ws(bs, M, N, 0);
+    return s + (w1 > w2 ? w1 : w2) + 512;
+}
+
+int fpv_chamfer_fwd(const float *a, const float *b, int64_t bs, int64_t N, int64_t M, int b_shared, float *d_b2a,
+                    float *d_a2b, void *i_b2a, void *i_a2b, int idx_bytes, void *workspace, size_t workspace_bytes,
+                    fpv_stream_t stream) {
+    FPV_CHECK_ARG(a && b && d_b2a && d_a2b && i_b2a && i_a2b, "fpv_chamfer_fwd: null pointer");
+    FPV_CHECK_ARG(bs > 0 && N > 0 && M > 0, "fpv_chamfer_fwd: empty cloud (bs=%lld N=%lld M=%lld)", (long long)bs,
+                  (long long)N, (long long)M);
+    FPV_CHECK_ARG(idx_bytes == 4 || idx_bytes == 8, "fpv_chamfer_fwd: idx_bytes must be 4 or 8");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    Arena ar(workspace, workspace_bytes);
+    const int64_t nb = b_shared ? 1 : bs;
+    float *pa = ar.take<float>(size_t(bs) * 3 * planes_len(N));
+    float *pb = ar.take<float>(size_t(nb) * 3 * planes_len(M));
+    if (!pa || !pb) {
+        set_error("fpv_chamfer_fwd: workspace too small (%zu bytes, need %zu)", workspace_bytes,
+                  fpv_chamfer_fwd_workspace_bytes(bs, N, M, b_shared));
+        return FPV_ERR_WORKSPACE;
+    }
+    int rc;
+    if ((rc = pack_planes_impl(a, bs, N, pa, st))) return rc;
+    if ((rc = pack_planes_impl(b, nb, M, pb, st))) return rc;
+    void *rest = ar.base + ar.off;
+    const size_t rest_bytes = ar.cap - ar.off;
+    // a -> b : every a_i finds its nearest b_j
+    if ((rc = nn_search_impl(a, 0, bs, N, pb, nb, M, 0, d_a2b, i_a2b, idx_bytes, nullptr, rest, rest_bytes, st)))
+        return rc;
+    // b -> a : every b_j finds its nearest a_i (per frame)
+    if ((rc = nn_search_impl(b, b_shared ? 1 : 0, bs, M, pa, bs, N, 0, d_b2a, i_b2a, idx_bytes, nullptr, rest,
+                             rest_bytes, st)))
+        return rc;
+    return FPV_OK;
+}
+
+size_t fpv_chamfer_bwd_workspace_bytes(int64_t bs, int64_t N, int64_t M, int b_shared, int want_grad_b) {
+    if (bs <= 0 || N <= 0 || M <= 0) return 0;
+    size_t s = 256 + align_up(size_t(bs * N * 3) * 8, 256);
+    if (want_grad_b) s += align_up(size_t((b_shared ? 1 : bs) * M * 3) * 8, 256);
+    return s + 256;
+}
+
+int fpv_chamfer_bwd(const float *a, const float *b, int64_t bs, int64_t N, int64_t M, int b_shared, const float *g_b2a,
+                    const float *g_a2b, const void *i_b2a, const void *i_a2b, int idx_bytes, float *grad_a,
+                    float *grad_b, void *workspace, size_t workspace_bytes, fpv_stream_t stream) {
+    FPV_CHECK_ARG(a && b && i_b2a && i_a2b && grad_a, "fpv_chamfer_bwd: null pointer");
+    FPV_CHECK_ARG(bs > 0 && N > 0 && M > 0, "fpv_chamfer_bwd: empty cloud");
+    FPV_CHECK_ARG(bs <= 65535, "fpv_chamfer_bwd: more than 65535 batches");
+    FPV_CHECK_ARG(idx_bytes == 4 || idx_bytes == 8, "fpv_chamfer_bwd: idx_bytes must be 4 or 8");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (idx_bytes == 8)
+        return chamfer_bwd_impl<long long>(a, b, bs, N, M, b_shared, g_b2a, g_a2b,
+                                           static_cast<const long long *>(i_b2a),
+                                           static_cast<const long long *>(i_a2b), grad_a, grad_b, workspace,
+                                           workspace_bytes, st);
+    return chamfer_bwd_impl<int>(a, b, bs, N, M, b_shared, g_b2a, g_a2b, static_cast<const int *>(i_b2a),
+                                 static_cast<const int *>(i_a2b), grad_a, grad_b, workspace, workspace_bytes, st);
+}
+
+}  // extern "C"

@@ -1,0 +1,178 @@
+/*
+ * fpv_b200.h -- C ABI of the B200-native hot path of 4DCapture-FPV's global_optimization stage.
+ *
+ * The reference has no FFI layer: its boundary is Python call signatures on torch tensors
+ * (SURVEY.md section 8b).  This header is what a host in any language binds instead; the Python
+ * mirror of the reference signatures (4dcapture-fpv_b200/*.py) is a ctypes client of exactly
+ * these symbols.  Conventions:
+ *   - every pointer is a DEVICE pointer unless the parameter name ends in _host;
+ *   - nothing allocates: callers size scratch with the *_bytes() queries and pass it in;
+ *   - `stream` is a cudaStream_t; all work is enqueued on it, no host synchronisation inside;
+ *   - return value 0 = ok, non-zero = error, text via fpv_last_error() (thread-local);
+ *   - fp32 data, int32 or int64 indices (idx_bytes = 4 | 8; the reference returns int64).
+ * Reference citations are relative to /root/reference/.
+ */
+#ifndef FPV_B200_H
+#define FPV_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FPV_ABI_VERSION 1
+#define FPV_OK 0
+#define FPV_ERR_INVALID 1
+#define FPV_ERR_CUDA 2
+#define FPV_ERR_WORKSPACE 3
+
+typedef void *fpv_stream_t; /* cudaStream_t */
+
+const char *fpv_last_error(void);
+int fpv_abi_version(void);
+/* sm_count / compute capability of `device`; fails loudly when no sm_100 GPU is present. */
+int fpv_device_query(int device, int *sm_count, int *cc_major, int *cc_minor);
+
+/* Measurement hooks (bench.py): kernel launches issued by this library since load; per-kernel CUDA-event
+ * timing of the instrumented launches with their algorithmic bytes / work items; an FP32 issue-rate probe
+ * (fused multiply-add lane operations per second) that gives the SIMT roofline denominator. */
+unsigned long long fpv_launch_count(void);
+int fpv_profile_enable(int on);
+int fpv_profile_count(void);
+int fpv_profile_get(int i, char *name48, float *ms, double *algo_bytes, double *work_items);
+int fpv_fp32_probe(double *lane_fma_per_s, fpv_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Chamfer nearest neighbour  (replaces chamfer_python.py:18-28 distChamfer and the [3P] CUDA op
+ * ext.chamferDist() called at global_optimization.py:292-294, :349-353).
+ * Canonical arithmetic: d = fma(dz,dz, fma(dy,dy, dx*dx)), dx = q - r in fp32; winner = the
+ * lexicographic minimum of (d, index) -- lowest index on ties, like torch.min / strict '<'.
+ * ------------------------------------------------------------------------------------------ */
+
+/* Candidate clouds are searched from padded structure-of-arrays planes [batches][3][Mp]. */
+size_t fpv_nn_planes_bytes(int64_t batches, int64_t M);
+int fpv_nn_pack_planes(const float *pts /*[batches,M,3]*/, int64_t batches, int64_t M,
+                       float *planes, fpv_stream_t stream);
+
+/* One direction: for every query the nearest candidate.
+ *   queries [q_batches,N,3] (q_shared != 0: one [N,3] set reused by every batch);
+ *   ref_planes from fpv_nn_pack_planes with ref_batches == batches, or 1 (shared by all batches);
+ *   idx_base is added to every index (scene shards keep global indices);
+ *   dist [batches,N] / idx [batches,N] may be NULL when only keys are wanted;
+ *   keys [batches,N] (optional) receives (float_bits(d) << 32) | idx, the multi-GPU combine key. */
+size_t fpv_nn_search_workspace_bytes(int64_t batches, int64_t N, int64_t M);
+int fpv_nn_search(const float *queries, int q_shared, int64_t batches, int64_t N,
+                  const float *ref_planes, int64_t ref_batches, int64_t M, int64_t idx_base,
+                  float *dist, void *idx, int idx_bytes, uint64_t *keys, void *workspace,
+                  size_t workspace_bytes, fpv_stream_t stream);
+int fpv_nn_unpack_keys(const uint64_t *keys, int64_t n, float *dist, void *idx, int idx_bytes,
+                       fpv_stream_t stream);
+/* Tuning hook for bench sweeps: force queries-per-thread (4 | 8) and the candidate split; 0 = heuristic.
+ * Results never depend on it. */
+int fpv_nn_set_tuning(int qpt, int nsplit);
+
+/* distChamfer(a, b) forward, reference output order (chamfer_python.py:28):
+ *   d_b2a [bs,M], d_a2b [bs,N], i_b2a [bs,M] (index into a), i_a2b [bs,N] (index into b).
+ * b_shared != 0: b is ONE [M,3] cloud for all bs frames (the reference materialises T copies at
+ * global_optimization.py:176; pass the copy-free form here). */
+size_t fpv_chamfer_fwd_workspace_bytes(int64_t bs, int64_t N, int64_t M, int b_shared);
+int fpv_chamfer_fwd(const float *a, const float *b, int64_t bs, int64_t N, int64_t M, int b_shared,
+                    float *d_b2a, float *d_a2b, void *i_b2a, void *i_a2b, int idx_bytes,
+                    void *workspace, size_t workspace_bytes, fpv_stream_t stream);
+
+/* distChamfer backward: gradient of sum(g_b2a*d_b2a) + sum(g_a2b*d_a2b) (either g may be NULL).
+ *   grad_a [bs,N,3] is overwritten; grad_b ([bs,M,3], or [M,3] when b_shared) may be NULL.
+ * The scatter through the argmin indices is a deterministic segmented reduction: contributions are
+ * converted to 64-bit fixed point against a device-computed bound and summed with integer adds,
+ * so the result does not depend on the order in which threads arrive. */
+size_t fpv_chamfer_bwd_workspace_bytes(int64_t bs, int64_t N, int64_t M, int b_shared, int want_grad_b);
+int fpv_chamfer_bwd(const float *a, const float *b, int64_t bs, int64_t N, int64_t M, int b_shared,
+                    const float *g_b2a, const float *g_a2b, const void *i_b2a, const void *i_a2b,
+                    int idx_bytes, float *grad_a, float *grad_b, void *workspace,
+                    size_t workspace_bytes, fpv_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Loss algebra around the chamfer term (global_optimization.py).
+ * ------------------------------------------------------------------------------------------ */
+
+/* :295  out[0] = mean( s/(s+1) ), s = sqrt(d+eps)  (the caller applies weight_contact). */
+size_t fpv_reduce_workspace_bytes(int64_t n);
+int fpv_robust_mean_fwd(const float *d, int64_t n, float eps, float *out, void *workspace,
+                        size_t workspace_bytes, fpv_stream_t stream);
+int fpv_robust_mean_bwd(const float *d, int64_t n, float eps, const float *g_out /*[1]*/,
+                        float *grad_d, fpv_stream_t stream);
+
+/* Temporal finite-difference L1 means over x [T,F] (F = features per frame):
+ *   order 2: mean |(x_t - x_{t+1}) - (x_{t+1} - x_{t+2})|   :266-267, :381-382, :404-405
+ *   order 1: mean |x_t - x_{t+1}|                             :304
+ *   order 1 with frame_w [T]: mean |(x_t - x_{t+1}) * w_{t+1}|  :415-429
+ * out[0] = the mean; *_bwd writes grad_x = g_out[0] * d(mean)/dx. */
+int fpv_tdiff_l1_fwd(const float *x, int64_t T, int64_t F, int order, const float *frame_w,
+                     float *out, void *workspace, size_t workspace_bytes, fpv_stream_t stream);
+int fpv_tdiff_l1_bwd(const float *x, int64_t T, int64_t F, int order, const float *frame_w,
+                     const float *g_out, float *grad_x, fpv_stream_t stream);
+
+/* :119-127 verts_transform: out[t,p] = M_t[:3,:3] * v[t,p] + M_t[:3,3]   (M [T,4,4] row-major). */
+int fpv_transform_fwd(const float *verts, const float *mats, int64_t T, int64_t P, float *out,
+                      fpv_stream_t stream);
+size_t fpv_transform_bwd_workspace_bytes(int64_t T, int64_t P);
+int fpv_transform_bwd(const float *verts, const float *mats, const float *g_out, int64_t T,
+                      int64_t P, float *g_verts, float *g_mats /*[T,4,4], may be NULL*/,
+                      void *workspace, size_t workspace_bytes, fpv_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * SMPL-X body model forward / backward  (replaces the [3P] smplx forward called at
+ * global_optimization.py:280-283, :333-335, :396-398; construction :154-168).
+ * ------------------------------------------------------------------------------------------ */
+
+#define FPV_SMPLX_JOINTS 55
+#define FPV_SMPLX_POSE_FEAT 486
+#define FPV_SMPLX_SHAPE 20
+#define FPV_SMPLX_KPAD 512  /* 486 pose features + 20 shape/expression + 1 (template) + 5 zero */
+#define FPV_SMPLX_THETA 122 /* per-frame parameter row, see below */
+
+/* Per-frame parameter row theta[t] (122 floats), the arguments of SMPLX.forward concatenated:
+ *   [0:3) global_orient  [3:66) body_pose  [66:69) jaw  [69:72) leye  [72:75) reye
+ *   [75:87) left_hand PCA  [87:99) right_hand PCA  [99:109) betas  [109:119) expression
+ *   [119:122) transl */
+
+/* Device-resident constants, prepared once by the host mirror (body_model.py). */
+typedef struct fpv_smplx_model {
+    int32_t num_verts;      /* V */
+    int32_t num_extra;      /* E: vertex-picked extra joints appended after the 55 */
+    int32_t ell_width;      /* W: max skinning influences per vertex */
+    int32_t reserved;
+    const float *basis_kn;  /* [512][3V]  rows: posedirs(486) | shapedirs^T(20) | v_template | 0 */
+    const float *basis_nk_hi, *basis_nk_lo; /* [3V][512] tf32 split of basis_kn^T (tensor-core fwd) */
+    const float *basis_kn_hi, *basis_kn_lo; /* [512][3V] tf32 split (tensor-core bwd) */
+    const float *j_template;   /* [55,3]    J_regressor @ v_template */
+    const float *j_shapedirs;  /* [55,3,20] J_regressor @ shapedirs */
+    const int32_t *parents;    /* [55] */
+    const float *hand_comps;   /* [2,12,45] left | right PCA components */
+    const float *pose_mean;    /* [165] */
+    const int32_t *ell_joint;  /* [W][V] joint index per influence (-1 = none) */
+    const float *ell_weight;   /* [W][V] */
+    const int32_t *csr_ptr;    /* [56] per-joint influence lists (the transpose of ell) */
+    const int32_t *csr_vert;   /* [nnz] */
+    const float *csr_weight;   /* [nnz] */
+    const int32_t *extra_vertex_ids; /* [E] */
+} fpv_smplx_model_t;
+
+/* Bytes of the per-call state kept between forward and backward, and of scratch. */
+size_t fpv_smplx_saved_bytes(const fpv_smplx_model_t *model_host, int64_t T);
+size_t fpv_smplx_workspace_bytes(const fpv_smplx_model_t *model_host, int64_t T);
+/* vertices [T,V,3], joints [T,55+E,3] (both include transl, as SMPLX.forward returns them). */
+int fpv_smplx_fwd(const fpv_smplx_model_t *model_host, int64_t T, const float *theta,
+                  float *vertices, float *joints, void *saved, void *workspace,
+                  size_t workspace_bytes, fpv_stream_t stream);
+/* g_vertices / g_joints may be NULL (= zeros); g_theta [T,122] is overwritten. */
+int fpv_smplx_bwd(const fpv_smplx_model_t *model_host, int64_t T, const float *theta,
+                  const void *saved, const float *g_vertices, const float *g_joints,
+                  float *g_theta, void *workspace, size_t workspace_bytes, fpv_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FPV_B200_H */

@@ -1,0 +1,57 @@
+"""GPU: one whole optimisation step (fit.FitProblem) vs the same step assembled from the CPU oracles."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import chamfer_oracle as co
+from oracle import residuals_oracle as ro
+from oracle import smplx_oracle as so
+
+pytestmark = pytest.mark.gpu
+
+
+def _oracle_step(fpv, prob):
+    from importlib import import_module
+    fit = import_module("4dcapture-fpv_b200.fit")
+    W = fit.LOSS_WEIGHTS
+    p = prob.params.detach().cpu().double().requires_grad_(True)
+    scale = prob.scale.detach().cpu().double().requires_grad_(True)
+    cam = prob.camera_ext.detach().cpu().double().requires_grad_(True)
+    data = prob.data.cpu().double()
+    sl = lambda r: p[:, r[0]:r[1]]
+    b2w = ro.body2world(sl(fit.P_CAM), scale, cam)
+    v, j = so.smplx_forward(prob.constants, betas=sl(fit.P_BETAS), global_orient=sl(fit.P_ORIENT),
+                            body_pose=sl(fit.P_POSE), transl=sl(fit.P_TRANSL), left_hand_pose=sl(fit.P_LH),
+                            right_hand_pose=sl(fit.P_RH), dtype=torch.float64)
+    verts = ro.verts_transform(v * scale, b2w)
+    joints = ro.verts_transform(j[:, 0:23] * scale, b2w)
+    scene = prob.host_scene.double()
+    # indices from the canonical fp32 oracle on the fp32 vertices the GPU path sees; distances re-derived in
+    # float64 through those indices so autograd flows exactly as torch.min would route it
+    v32 = verts.detach().float().numpy()
+    _, _, i_b2a, i_a2b = co.dist_chamfer(v32, prob.host_scene.numpy())
+    i_b2a, i_a2b = torch.tensor(i_b2a), torch.tensor(i_a2b)
+    d_a2b = ((verts - scene[i_a2b]) ** 2).sum(-1)
+    d_b2a = ((scene.unsqueeze(0) - torch.gather(verts, 1, i_b2a.unsqueeze(-1).expand(-1, -1, 3))) ** 2).sum(-1)
+    cid = prob.contact_ids.cpu()
+    losses = dict(rec=torch.mean(torch.abs(data - p)), smoothing=ro.second_diff_l1(p),
+                  contact=ro.contact_robust_loss(d_a2b[:, cid]), scene2body=d_b2a.mean(),
+                  world_smoothing=ro.first_diff_l1(joints), vert_smoothing=ro.second_diff_l1(verts))
+    total = sum(W[k] * x for k, x in losses.items())
+    total.backward()
+    return total.item(), p.grad, scale.grad, cam.grad
+
+
+def test_fit_step_matches_oracle(fpv, cuda_dev):
+    prob = fpv.FitProblem(T=6, M=20000, device=cuda_dev, seed=1235)
+    loss = prob.step()
+    ref_loss, gp, gs, gc = _oracle_step(fpv, prob)
+    assert loss.item() == pytest.approx(ref_loss, rel=2e-5)
+    for got, ref, name in [(prob.params.grad, gp, "params"), (prob.scale.grad, gs, "scale"), (prob.camera_ext.grad, gc, "camera_ext")]:
+        err = (got.cpu().double() - ref).abs().max().item()
+        tol = 5e-5 * ref.abs().max().item() + 1e-8
+        assert err <= tol, (name, err, tol)
+    l2 = prob.step()
+    assert l2.item() == loss.item()                                   # same inputs -> bitwise same loss
+    host = prob.step_e2e()
+    assert host[0].item() == pytest.approx(ref_loss, rel=2e-5) and host[1].shape == (6, 106)
