@@ -27,6 +27,7 @@ constexpr size_t NN_SMEM = size_t(NN_STAGES) * 3 * NN_TILE * sizeof(float) + 2 *
 
 static int g_tune_qpt = 0;      // 0 = heuristic
 static int g_tune_nsplit = 0;   // 0 = heuristic
+static int g_tune_packed = -1;  // -1 = default; else number of packed queries per thread
 
 struct NNParams {
     const float *q;
@@ -51,10 +52,14 @@ __device__ __forceinline__ float d2_scalar(float x, float y, float z, float rx, 
 }
 
 // Four candidates (one float4 per plane) against QPT register-resident queries.
-template <int QPT>
+// The first NP queries use packed FADD2/FMUL2/FFMA2 (3 issue slots per pair, but the packed forms only
+// sustain ~103 of the 128 lane-ops/SM/clk, profiles/r01_fp32_pipe_probe.txt); the rest use scalar
+// FADD/FMUL/FFMA (full pipe rate, 6 issue slots per pair).  Mixing the two balances the issue port
+// against the FP32 pipe.  Both evaluate the canonical expression, bit for bit.
+template <int QPT, int NP>
 __device__ __forceinline__ void nn_step(const float4 rx, const float4 ry, const float4 rz, const int j,
-                                        const float2 (&qx)[QPT], const float2 (&qy)[QPT],
-                                        const float2 (&qz)[QPT], float (&best)[QPT], int (&bidx)[QPT]) {
+                                        const float (&qx)[QPT], const float (&qy)[QPT],
+                                        const float (&qz)[QPT], float (&best)[QPT], int (&bidx)[QPT]) {
     float mnew[QPT];
     bool any = false;
     const float2 nx0 = make_float2(-rx.x, -rx.y), nx1 = make_float2(-rx.z, -rx.w);
@@ -62,16 +67,27 @@ __device__ __forceinline__ void nn_step(const float4 rx, const float4 ry, const 
     const float2 nz0 = make_float2(-rz.x, -rz.y), nz1 = make_float2(-rz.z, -rz.w);
 #pragma unroll
     for (int q = 0; q < QPT; ++q) {
-        const float2 dx0 = __fadd2_rn(qx[q], nx0), dx1 = __fadd2_rn(qx[q], nx1);
-        const float2 dy0 = __fadd2_rn(qy[q], ny0), dy1 = __fadd2_rn(qy[q], ny1);
-        const float2 dz0 = __fadd2_rn(qz[q], nz0), dz1 = __fadd2_rn(qz[q], nz1);
-        float2 s0 = __fmul2_rn(dx0, dx0), s1 = __fmul2_rn(dx1, dx1);
-        s0 = __ffma2_rn(dy0, dy0, s0);
-        s1 = __ffma2_rn(dy1, dy1, s1);
-        s0 = __ffma2_rn(dz0, dz0, s0);
-        s1 = __ffma2_rn(dz1, dz1, s1);
-        float m = fmin3(best[q], s0.x, s0.y);
-        m = fmin3(m, s1.x, s1.y);
+        float m;
+        if (q < NP) {
+            const float2 bx = make_float2(qx[q], qx[q]), by = make_float2(qy[q], qy[q]), bz = make_float2(qz[q], qz[q]);
+            const float2 dx0 = __fadd2_rn(bx, nx0), dx1 = __fadd2_rn(bx, nx1);
+            const float2 dy0 = __fadd2_rn(by, ny0), dy1 = __fadd2_rn(by, ny1);
+            const float2 dz0 = __fadd2_rn(bz, nz0), dz1 = __fadd2_rn(bz, nz1);
+            float2 s0 = __fmul2_rn(dx0, dx0), s1 = __fmul2_rn(dx1, dx1);
+            s0 = __ffma2_rn(dy0, dy0, s0);
+            s1 = __ffma2_rn(dy1, dy1, s1);
+            s0 = __ffma2_rn(dz0, dz0, s0);
+            s1 = __ffma2_rn(dz1, dz1, s1);
+            m = fmin3(best[q], s0.x, s0.y);
+            m = fmin3(m, s1.x, s1.y);
+        } else {
+            const float e0 = d2_scalar(qx[q], qy[q], qz[q], rx.x, ry.x, rz.x);
+            const float e1 = d2_scalar(qx[q], qy[q], qz[q], rx.y, ry.y, rz.y);
+            const float e2 = d2_scalar(qx[q], qy[q], qz[q], rx.z, ry.z, rz.z);
+            const float e3 = d2_scalar(qx[q], qy[q], qz[q], rx.w, ry.w, rz.w);
+            m = fmin3(best[q], e0, e1);
+            m = fmin3(m, e2, e3);
+        }
         mnew[q] = m;
         any |= (m < best[q]);
     }
@@ -79,7 +95,7 @@ __device__ __forceinline__ void nn_step(const float4 rx, const float4 ry, const 
 #pragma unroll
         for (int q = 0; q < QPT; ++q) {
             if (mnew[q] < best[q]) {
-                const float x = qx[q].x, y = qy[q].x, z = qz[q].x, m = mnew[q];
+                const float x = qx[q], y = qy[q], z = qz[q], m = mnew[q];
                 const float e0 = d2_scalar(x, y, z, rx.x, ry.x, rz.x);
                 const float e1 = d2_scalar(x, y, z, rx.y, ry.y, rz.y);
                 const float e2 = d2_scalar(x, y, z, rx.z, ry.z, rz.z);
@@ -91,7 +107,7 @@ __device__ __forceinline__ void nn_step(const float4 rx, const float4 ry, const 
     for (int q = 0; q < QPT; ++q) best[q] = mnew[q];
 }
 
-template <int QPT>
+template <int QPT, int NP>
 __global__ void __launch_bounds__(NN_THREADS + 32, (QPT <= 4) ? 2 : 1) nn_search_kernel(const NNParams p) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     float *tiles = reinterpret_cast<float *>(smem_raw);  // [STAGES][3][TILE]
@@ -135,7 +151,7 @@ __global__ void __launch_bounds__(NN_THREADS + 32, (QPT <= 4) ? 2 : 1) nn_search
     }
 
     // ---- consumer warps ----
-    float2 qx[QPT], qy[QPT], qz[QPT];
+    float qx[QPT], qy[QPT], qz[QPT];
     float best[QPT];
     int bidx[QPT];
     const int64_t qbase = int64_t(blockIdx.x) * (NN_THREADS * QPT);
@@ -145,9 +161,9 @@ __global__ void __launch_bounds__(NN_THREADS + 32, (QPT <= 4) ? 2 : 1) nn_search
         int64_t qi = qbase + int64_t(k) * NN_THREADS + tid;
         if (qi > p.N - 1) qi = p.N - 1;
         const float x = __ldg(qsrc + 3 * qi), y = __ldg(qsrc + 3 * qi + 1), z = __ldg(qsrc + 3 * qi + 2);
-        qx[k] = make_float2(x, x);
-        qy[k] = make_float2(y, y);
-        qz[k] = make_float2(z, z);
+        qx[k] = x;
+        qy[k] = y;
+        qz[k] = z;
         best[k] = CUDART_INF_F;
         bidx[k] = 0;
     }
@@ -164,7 +180,7 @@ __global__ void __launch_bounds__(NN_THREADS + 32, (QPT <= 4) ? 2 : 1) nn_search
         const int jbase = int(r0) + k * NN_TILE;
 #pragma unroll 2
         for (int j4 = 0; j4 < cnt4; ++j4) {
-            nn_step<QPT>(X[j4], Y[j4], Z[j4], jbase + 4 * j4, qx, qy, qz, best, bidx);
+            nn_step<QPT, NP>(X[j4], Y[j4], Z[j4], jbase + 4 * j4, qx, qy, qz, best, bidx);
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(&empty[s]);
@@ -241,7 +257,8 @@ static NNPlan nn_plan(int64_t batches, int64_t N, int64_t M) {
     NNPlan pl;
     const int sms = sm_count();
     const int64_t total_q = batches * N;
-    pl.qpt = (total_q >= int64_t(sms) * NN_THREADS * 8 * 2) ? 8 : 4;
+    (void)total_q;
+    pl.qpt = 4;  // measured: 4 queries/thread, 2 CTAs/SM beats 8 queries/thread, 1 CTA/SM on every shape (profiles/r01_nn_tune2.txt)
     if (g_tune_qpt == 4 || g_tune_qpt == 8) pl.qpt = g_tune_qpt;
     pl.qblocks = ceil_div(N, int64_t(NN_THREADS) * pl.qpt);
     pl.M8 = ceil_div(M, 8) * 8;
@@ -257,17 +274,39 @@ static NNPlan nn_plan(int64_t batches, int64_t N, int64_t M) {
     return pl;
 }
 
-template <int QPT>
+template <int QPT, int NP>
 static cudaError_t nn_launch(const NNParams &p, dim3 grid, cudaStream_t st) {
     static bool configured = false;
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(nn_search_kernel<QPT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        cudaError_t e = cudaFuncSetAttribute(nn_search_kernel<QPT, NP>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              int(NN_SMEM));
         if (e != cudaSuccess) return e;
         configured = true;
     }
-    nn_search_kernel<QPT><<<grid, NN_THREADS + 32, NN_SMEM, st>>>(p);
+    nn_search_kernel<QPT, NP><<<grid, NN_THREADS + 32, NN_SMEM, st>>>(p);
     return cudaGetLastError();
+}
+
+constexpr int NN_DEFAULT_NP4 = 4, NN_DEFAULT_NP8 = 8;
+
+static cudaError_t nn_dispatch(int qpt, const NNParams &p, dim3 grid, cudaStream_t st) {
+    const int np = g_tune_packed >= 0 ? g_tune_packed : (qpt == 8 ? NN_DEFAULT_NP8 : NN_DEFAULT_NP4);
+    if (qpt == 8) {
+        switch (np) {
+            case 0: return nn_launch<8, 0>(p, grid, st);
+            case 2: return nn_launch<8, 2>(p, grid, st);
+            case 4: return nn_launch<8, 4>(p, grid, st);
+            case 6: return nn_launch<8, 6>(p, grid, st);
+            default: return nn_launch<8, 8>(p, grid, st);
+        }
+    }
+    switch (np) {
+        case 0: return nn_launch<4, 0>(p, grid, st);
+        case 1: return nn_launch<4, 1>(p, grid, st);
+        case 2: return nn_launch<4, 2>(p, grid, st);
+        case 3: return nn_launch<4, 3>(p, grid, st);
+        default: return nn_launch<4, 4>(p, grid, st);
+    }
 }
 
 // One direction.  Flattens the batch axis when one candidate set serves every batch.
@@ -331,7 +370,7 @@ static int nn_search_impl(const float *queries, int q_shared, int64_t batches, i
         profile_begin(nm, st, 12.0 * qpts + 12.0 * double(M) * double(ref_batches) + out_b * double(total),
                       double(total) * double(M));
     }
-    cudaError_t e = (pl.qpt == 8) ? nn_launch<8>(p, grid, st) : nn_launch<4>(p, grid, st);
+    cudaError_t e = nn_dispatch(pl.qpt, p, grid, st);
     profile_end(st);
     count_launch();
     if (e != cudaSuccess) {
@@ -564,10 +603,12 @@ int fpv_nn_unpack_keys(const uint64_t *keys, int64_t n, float *dist, void *idx, 
     return FPV_OK;
 }
 
-// Debug/tuning hook (bench sweeps): force queries-per-thread (4|8) and the candidate split; 0 = heuristic.
-int fpv_nn_set_tuning(int qpt, int nsplit) {
+// Debug/tuning hook (bench sweeps): force queries-per-thread (4|8), the candidate split (0 = heuristic)
+// and how many of a thread's queries use packed FP32x2 math (-1 = default).
+int fpv_nn_set_tuning(int qpt, int nsplit, int packed) {
     g_tune_qpt = qpt;
     g_tune_nsplit = nsplit;
+    g_tune_packed = packed;
     return FPV_OK;
 }
 

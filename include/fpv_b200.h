@@ -69,9 +69,10 @@ int fpv_nn_search(const float *queries, int q_shared, int64_t batches, int64_t N
                   size_t workspace_bytes, fpv_stream_t stream);
 int fpv_nn_unpack_keys(const uint64_t *keys, int64_t n, float *dist, void *idx, int idx_bytes,
                        fpv_stream_t stream);
-/* Tuning hook for bench sweeps: force queries-per-thread (4 | 8) and the candidate split; 0 = heuristic.
+/* Tuning hook for bench sweeps: force queries-per-thread (4 | 8; 0 = heuristic), the candidate split
+ * (0 = heuristic) and how many queries per thread use packed FP32x2 math (-1 = default).
  * Results never depend on it. */
-int fpv_nn_set_tuning(int qpt, int nsplit);
+int fpv_nn_set_tuning(int qpt, int nsplit, int packed);
 
 /* distChamfer(a, b) forward, reference output order (chamfer_python.py:28):
  *   d_b2a [bs,M], d_a2b [bs,N], i_b2a [bs,M] (index into a), i_a2b [bs,N] (index into b).

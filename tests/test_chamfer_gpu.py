@@ -80,11 +80,11 @@ def test_split_candidate_path_and_int32(fpv, cuda_dev):
     _assert_exact(got, co.dist_chamfer(a, b))
     L = fpv._lib.lib()
     try:
-        for qpt, ns in [(4, 1), (8, 1), (4, 7), (8, 13)]:
-            L.fpv_nn_set_tuning(qpt, ns)
+        for qpt, ns, packed in [(4, 1, 0), (8, 1, 8), (4, 7, 1), (8, 13, 2), (4, 3, 4), (8, 2, 0), (4, 0, 3), (8, 0, 6)]:
+            L.fpv_nn_set_tuning(qpt, ns, packed)
             _assert_exact(_run(fpv, a, b, cuda_dev), co.dist_chamfer(a, b))
     finally:
-        L.fpv_nn_set_tuning(0, 0)
+        L.fpv_nn_set_tuning(0, 0, -1)
 
 
 def test_far_from_origin_and_special_values(fpv, cuda_dev):

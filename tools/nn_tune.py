@@ -18,12 +18,12 @@ def timeit(fn, reps=3):
     return best
 
 def bench(label, queries, planes, M, ref_batches, pairs):
-    for qpt in (4, 8):
-        for ns in (0, 1):
-            L.fpv_nn_set_tuning(qpt, ns)
+    for qpt, nps in ((4, (0, 1, 2, 3, 4)), (8, (0, 2, 4, 6, 8))):
+        for npk in nps:
+            L.fpv_nn_set_tuning(qpt, 0, npk)
             ms = timeit(lambda: fpv.nn_search(queries, planes, M, ref_batches=ref_batches))
-            print(f"{label:28s} qpt={qpt} nsplit={'auto' if ns == 0 else ns}: {ms:9.3f} ms  {pairs / ms / 1e9:7.3f} Tpair/s", flush=True)
-    L.fpv_nn_set_tuning(0, 0)
+            print(f"{label:28s} qpt={qpt} packed={npk}: {ms:9.3f} ms  {pairs / ms / 1e9:7.3f} Tpair/s", flush=True)
+    L.fpv_nn_set_tuning(0, 0, -1)
 
 T = int(sys.argv[1]) if len(sys.argv) > 1 else 60
 M = 1_000_000
