@@ -60,6 +60,10 @@ SIGNATURES = {
     "fpv_transform_bwd_workspace_bytes": (c_size_t, [c_int64, c_int64]),
     "fpv_transform_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_void_p,
                                   c_void_p, c_size_t, c_void_p]),
+    "fpv_split_tf32": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p]),
+    "fpv_tc_gemm_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
+    "fpv_tc_gemm_3xtf32": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_int, c_int, c_int,
+                                   c_void_p, c_int64, c_int, c_void_p, c_size_t, c_void_p]),
     "fpv_smplx_saved_bytes": (c_size_t, [POINTER(SmplxModelStruct), c_int64]),
     "fpv_smplx_workspace_bytes": (c_size_t, [POINTER(SmplxModelStruct), c_int64]),
     "fpv_smplx_fwd": (c_int, [POINTER(SmplxModelStruct), c_int64, c_void_p, c_void_p, c_void_p, c_void_p,

@@ -53,6 +53,15 @@ def load_smplx_npz(path: str, num_betas: int = 10, num_expression_coeffs: int = 
                 pose_mean=f32(pose_mean), extra_vertex_ids=torch.zeros(0, dtype=torch.int64))
 
 
+def split_tf32(x: torch.Tensor):
+    """x -> (hi, lo), each exactly representable in TF32 (10 explicit mantissa bits), hi + lo = x to 2^-22.
+    Same bit recipe as the device code (round-half-up on the magnitude, csrc/tc_gemm.cu::tf32_round)."""
+    def rn(t):
+        return ((t.contiguous().view(torch.int32) + 0x1000) & -0x2000).view(torch.float32)
+    hi = rn(x)
+    return hi, rn(x - hi)
+
+
 class _SMPLXFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, theta, module):
@@ -145,7 +154,20 @@ class SMPLXB200(nn.Module):
         extra = c.get("extra_vertex_ids", torch.zeros(0, dtype=torch.int64))
         self.num_extra = int(extra.numel())
         f32 = lambda t: t.to(torch.float32).contiguous()
-        self.register_buffer("basis_kn", f32(basis))
+        # TF32 hi/lo splits of the basis in both tensor-core operand orientations (K contiguous):
+        #   forward  v_posed = coef x basis_nk^T : basis_nk [3V, 512]
+        #   backward gC = g_vposed x basis_kn^T  : basis_kn [512, P], P = 3V rounded up to 4 (TMA row pitch)
+        b32 = f32(basis)
+        P = (3 * V + 3) // 4 * 4
+        kn = torch.zeros(KP, P, dtype=torch.float32)
+        kn[:, :3 * V] = b32
+        kn_hi, kn_lo = split_tf32(kn)
+        nk_hi, nk_lo = split_tf32(b32.t().contiguous())
+        self.register_buffer("basis_kn", b32, persistent=False)
+        self.register_buffer("basis_kn_hi", kn_hi, persistent=False)
+        self.register_buffer("basis_kn_lo", kn_lo, persistent=False)
+        self.register_buffer("basis_nk_hi", nk_hi, persistent=False)
+        self.register_buffer("basis_nk_lo", nk_lo, persistent=False)
         self.register_buffer("j_template", f32(j_template))
         self.register_buffer("j_shapedirs", f32(j_shapedirs))
         self.register_buffer("parents", c["parents"].to(torch.int32).contiguous())
@@ -188,7 +210,8 @@ class SMPLXB200(nn.Module):
             s.num_verts, s.num_extra, s.ell_width, s.reserved = self.num_verts, self.num_extra, self.ell_width, 0
             p = lambda t: t.data_ptr() if t.numel() else None
             s.basis_kn = p(self.basis_kn)
-            s.basis_nk_hi = s.basis_nk_lo = s.basis_kn_hi = s.basis_kn_lo = None
+            s.basis_nk_hi, s.basis_nk_lo = p(self.basis_nk_hi), p(self.basis_nk_lo)
+            s.basis_kn_hi, s.basis_kn_lo = p(self.basis_kn_hi), p(self.basis_kn_lo)
             s.j_template, s.j_shapedirs, s.parents = p(self.j_template), p(self.j_shapedirs), p(self.parents)
             s.hand_comps, s.pose_mean = p(self.hand_comps), p(self.pose_mean)
             s.ell_joint, s.ell_weight = p(self.ell_joint), p(self.ell_weight)

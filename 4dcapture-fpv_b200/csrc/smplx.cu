@@ -25,8 +25,15 @@ constexpr int NSH = FPV_SMPLX_SHAPE;
 constexpr int NTH = FPV_SMPLX_THETA;
 constexpr int TH_LH = 75, TH_RH = 87, TH_BETA = 99, TH_TRANSL = 119;
 
+int tc_gemm_3xtf32(const float *a_hi, const float *a_lo, int64_t lda, const float *b_hi, const float *b_lo,
+                   int64_t ldb, int M, int N, int K, float *C, int64_t ldc, int ksplit, float *partial,
+                   cudaStream_t st);  // tc_gemm.cu
+
+// row pitch (floats) of every [*, 3V] operand of the tensor-core GEMMs: TMA needs 16-byte multiples
+static inline int64_t pitch3v(int64_t V) { return (3 * V + 3) / 4 * 4; }
+
 struct SavedLayout {
-    size_t R, G, J, A, coef, vposed, total;  // float offsets
+    size_t R, G, J, A, coef_hi, coef_lo, vposed, total;  // float offsets
 };
 static SavedLayout saved_layout(int64_t T, int64_t V) {
     SavedLayout L;
@@ -40,10 +47,15 @@ static SavedLayout saved_layout(int64_t T, int64_t V) {
     L.G = take(size_t(T) * NJ * 12);
     L.J = take(size_t(T) * NJ * 3);
     L.A = take(size_t(T) * NJ * 12);
-    L.coef = take(size_t(T) * KP);
-    L.vposed = take(size_t(T) * V * 3);
+    L.coef_hi = take(size_t(T) * KP);
+    L.coef_lo = take(size_t(T) * KP);
+    L.vposed = take(size_t(T) * pitch3v(V));
     L.total = o;
     return L;
+}
+
+__device__ __forceinline__ float tf32_rn(float x) {
+    return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -70,8 +82,8 @@ __device__ __forceinline__ void rodrigues(const float *r, float *R) {
 __global__ void __launch_bounds__(64) pose_fwd_kernel(const fpv_smplx_model_t m, const float *__restrict__ theta,
                                                       float *__restrict__ sR, float *__restrict__ sG,
                                                       float *__restrict__ sJ, float *__restrict__ sA,
-                                                      float *__restrict__ coef, float *__restrict__ joints,
-                                                      int joints_stride) {
+                                                      float *__restrict__ coef_hi, float *__restrict__ coef_lo,
+                                                      float *__restrict__ joints, int joints_stride) {
     __shared__ float th[NTH];
     __shared__ float fp[165];
     __shared__ float R[NJ][9];
@@ -169,91 +181,10 @@ __global__ void __launch_bounds__(64) pose_fwd_kernel(const fpv_smplx_model_t m,
         } else if (k == NPF + NSH) {
             v = 1.f;
         }
-        coef[t * KP + k] = v;
+        const float h = tf32_rn(v);  // TF32 hi/lo split feeding the 3xTF32 tensor-core contraction
+        coef_hi[t * KP + k] = h;
+        coef_lo[t * KP + k] = tf32_rn(v - h);
     }
-}
-
-// ---------------------------------------------------------------------------------------------
-// 2. blend GEMM (fp32 SIMT).  C[M,N] (+split-K partials) = A[M,K] * op(B)
-//    TRANS_B = false: B is [K,N] row-major.   TRANS_B = true: B is [N,K] row-major.
-//    64x64 tile, BK = 16, 256 threads x (4x4) outputs.  gridDim.z slices K; slice z writes
-//    C + z*M*N (the caller reduces slices in fixed order).
-// ---------------------------------------------------------------------------------------------
-template <bool TRANS_B>
-__global__ void __launch_bounds__(256) sgemm_kernel(const float *__restrict__ A, const float *__restrict__ B,
-                                                    float *__restrict__ C, int M, int N, int K, int kchunk) {
-    __shared__ float As[16][64 + 4];
-    __shared__ float Bs[16][64 + 4];
-    const int tid = threadIdx.x;
-    const int tx = tid & 15, ty = tid >> 4;
-    const int m0 = blockIdx.y * 64, n0 = blockIdx.x * 64;
-    const int kbeg = blockIdx.z * kchunk;
-    const int kend = (kbeg + kchunk < K) ? kbeg + kchunk : K;
-    float acc[4][4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
-    for (int k0 = kbeg; k0 < kend; k0 += 16) {
-        // A tile: 64 rows x 16 k  (4 elements per thread, k fastest)
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            const int e = tid + u * 256;
-            const int r = e >> 4, kk = e & 15;
-            const int gm = m0 + r, gk = k0 + kk;
-            As[kk][r] = (gm < M && gk < kend) ? A[size_t(gm) * K + gk] : 0.f;
-        }
-        if (TRANS_B) {
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const int e = tid + u * 256;
-                const int r = e >> 4, kk = e & 15;
-                const int gn = n0 + r, gk = k0 + kk;
-                Bs[kk][r] = (gn < N && gk < kend) ? B[size_t(gn) * K + gk] : 0.f;
-            }
-        } else {
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const int e = tid + u * 256;
-                const int kk = e >> 6, c = e & 63;
-                const int gn = n0 + c, gk = k0 + kk;
-                Bs[kk][c] = (gn < N && gk < kend) ? B[size_t(gk) * N + gn] : 0.f;
-            }
-        }
-        __syncthreads();
-#pragma unroll
-        for (int kk = 0; kk < 16; ++kk) {
-            float a[4], b[4];
-#pragma unroll
-            for (int i = 0; i < 4; ++i) a[i] = As[kk][ty * 4 + i];
-#pragma unroll
-            for (int j = 0; j < 4; ++j) b[j] = Bs[kk][tx * 4 + j];
-#pragma unroll
-            for (int i = 0; i < 4; ++i)
-#pragma unroll
-                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
-        }
-        __syncthreads();
-    }
-    float *Cz = C + size_t(blockIdx.z) * M * N;
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const int gm = m0 + ty * 4 + i;
-        if (gm >= M) continue;
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const int gn = n0 + tx * 4 + j;
-            if (gn < N) Cz[size_t(gm) * N + gn] = acc[i][j];
-        }
-    }
-}
-
-__global__ void splitk_reduce_kernel(const float *__restrict__ part, int64_t mn, int nz, float *__restrict__ out) {
-    const int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
-    if (i >= mn) return;
-    float s = 0.f;
-    for (int z = 0; z < nz; ++z) s += part[size_t(z) * mn + i];
-    out[i] = s;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -278,7 +209,7 @@ __device__ __forceinline__ void blend_transform(const float (*A)[12], const int3
 __global__ void __launch_bounds__(SKIN_THREADS) skin_fwd_kernel(const fpv_smplx_model_t m,
                                                                 const float *__restrict__ theta,
                                                                 const float *__restrict__ sA,
-                                                                const float *__restrict__ vposed,
+                                                                const float *__restrict__ vposed, int64_t ldp,
                                                                 float *__restrict__ verts) {
     __shared__ float A[NJ][12];
     __shared__ float tr[3];
@@ -291,7 +222,7 @@ __global__ void __launch_bounds__(SKIN_THREADS) skin_fwd_kernel(const fpv_smplx_
     if (v >= V) return;
     float Tm[12];
     blend_transform(A, m.ell_joint, m.ell_weight, m.ell_width, V, v, Tm);
-    const float *vp = vposed + (t * V + v) * 3;
+    const float *vp = vposed + t * ldp + 3 * v;
     const float x = vp[0], y = vp[1], z = vp[2];
     float *o = verts + (t * V + v) * 3;
 #pragma unroll
@@ -334,7 +265,8 @@ __global__ void __launch_bounds__(SKIN_THREADS) skin_bwd_kernel(const fpv_smplx_
                                                                 const float *__restrict__ sA,
                                                                 const float *__restrict__ g_verts,
                                                                 const float *__restrict__ g_joints, int joints_stride,
-                                                                float *__restrict__ g_vposed) {
+                                                                int64_t ldp, float *__restrict__ g_vposed_hi,
+                                                                float *__restrict__ g_vposed_lo) {
     __shared__ float A[NJ][12];
     __shared__ int ex_id[MAX_EXTRA];
     __shared__ float ex_g[MAX_EXTRA][3];
@@ -353,15 +285,19 @@ __global__ void __launch_bounds__(SKIN_THREADS) skin_bwd_kernel(const fpv_smplx_
     eff_grad(g_verts, t, V, v, E, ex_id, ex_g, g);
     float Tm[12];
     blend_transform(A, m.ell_joint, m.ell_weight, m.ell_width, V, v, Tm);
-    float *o = g_vposed + (t * V + v) * 3;
 #pragma unroll
-    for (int c = 0; c < 3; ++c) o[c] = Tm[c] * g[0] + Tm[4 + c] * g[1] + Tm[8 + c] * g[2];
+    for (int c = 0; c < 3; ++c) {
+        const float gv = Tm[c] * g[0] + Tm[4 + c] * g[1] + Tm[8 + c] * g[2];
+        const float h = tf32_rn(gv);
+        g_vposed_hi[t * ldp + 3 * v + c] = h;
+        g_vposed_lo[t * ldp + 3 * v + c] = tf32_rn(gv - h);
+    }
 }
 
 // grid (56, T): blocks 0..54 reduce the influence list of one joint to gA[t][j][12] = sum w * g (x) [vp,1];
 // block 55 reduces sum_v g -> gT[t][3].  Strided accumulation + fixed tree: deterministic.
 __global__ void __launch_bounds__(128) jointgrad_kernel(const fpv_smplx_model_t m, const float *__restrict__ vposed,
-                                                        const float *__restrict__ g_verts,
+                                                        int64_t ldp, const float *__restrict__ g_verts,
                                                         const float *__restrict__ g_joints, int joints_stride,
                                                         float *__restrict__ gA, float *__restrict__ gT) {
     __shared__ int ex_id[MAX_EXTRA];
@@ -386,7 +322,7 @@ __global__ void __launch_bounds__(128) jointgrad_kernel(const fpv_smplx_model_t 
             const float w = m.csr_weight[e];
             float g[3];
             eff_grad(g_verts, t, V, v, E, ex_id, ex_g, g);
-            const float *vp = vposed + (t * V + v) * 3;
+            const float *vp = vposed + t * ldp + 3 * v;
             const float x = vp[0], y = vp[1], z = vp[2];
 #pragma unroll
             for (int r = 0; r < 3; ++r) {
@@ -572,10 +508,10 @@ __global__ void __launch_bounds__(64) pose_bwd_kernel(const fpv_smplx_model_t m,
     }
 }
 
-constexpr int BWD_KCHUNK = 1024;
+constexpr int BWD_KSPLIT = 12;  // 3 x 4 output tiles x 12 k-slices = 144 CTAs ~ one wave of 148 SMs
 
 struct BwdLayout {
-    size_t gvp, gA, gT, gC, part, total;  // float offsets
+    size_t gvp_hi, gvp_lo, gA, gT, gC, part, total;  // float offsets
     int nz;
 };
 static BwdLayout bwd_layout(int64_t T, int64_t V) {
@@ -586,8 +522,9 @@ static BwdLayout bwd_layout(int64_t T, int64_t V) {
         o += align_up(n, 64);
         return r;
     };
-    L.nz = int(ceil_div(3 * V, BWD_KCHUNK));
-    L.gvp = take(size_t(T) * V * 3);
+    L.nz = BWD_KSPLIT;
+    L.gvp_hi = take(size_t(T) * pitch3v(V));
+    L.gvp_lo = take(size_t(T) * pitch3v(V));
     L.gA = take(size_t(T) * NJ * 12);
     L.gT = take(size_t(T) * 3);
     L.gC = take(size_t(T) * KP);
@@ -616,7 +553,9 @@ static int check_model(const fpv_smplx_model_t *m) {
     FPV_CHECK_ARG(m, "smplx: null model");
     FPV_CHECK_ARG(m->num_verts > 0 && m->ell_width > 0 && m->num_extra >= 0 && m->num_extra <= MAX_EXTRA,
                   "smplx: bad model sizes (V=%d W=%d E=%d)", m->num_verts, m->ell_width, m->num_extra);
-    FPV_CHECK_ARG(m->basis_kn && m->j_template && m->j_shapedirs && m->parents && m->hand_comps && m->pose_mean &&
+    FPV_CHECK_ARG(m->basis_nk_hi && m->basis_nk_lo && m->basis_kn_hi && m->basis_kn_lo,
+                  "smplx: model lacks the TF32-split basis (tensor-core operands)");
+    FPV_CHECK_ARG(m->j_template && m->j_shapedirs && m->parents && m->hand_comps && m->pose_mean &&
                       m->ell_joint && m->ell_weight && m->csr_ptr && m->csr_vert && m->csr_weight,
                   "smplx: model has null constant pointers");
     FPV_CHECK_ARG(m->num_extra == 0 || m->extra_vertex_ids, "smplx: extra_vertex_ids missing");
@@ -637,18 +576,17 @@ int fpv_smplx_fwd(const fpv_smplx_model_t *model, int64_t T, const float *theta,
     const SavedLayout L = saved_layout(T, V);
     float *S = static_cast<float *>(saved);
     const int jstride = NJ + m.num_extra;
-    pose_fwd_kernel<<<(unsigned)T, 64, 0, st>>>(m, theta, S + L.R, S + L.G, S + L.J, S + L.A, S + L.coef, joints,
-                                                jstride);
+    const int64_t ldp = pitch3v(V);
+    pose_fwd_kernel<<<(unsigned)T, 64, 0, st>>>(m, theta, S + L.R, S + L.G, S + L.J, S + L.A, S + L.coef_hi, S + L.coef_lo,
+                                                joints, jstride);
     FPV_LAUNCH_CHECK("pose_fwd_kernel");
-    {
-        const int N = 3 * V;
-        dim3 grid((unsigned)ceil_div(N, 64), (unsigned)ceil_div(T, 64), 1);
-        sgemm_kernel<false><<<grid, 256, 0, st>>>(S + L.coef, m.basis_kn, S + L.vposed, int(T), N, KP, KP);
-        FPV_LAUNCH_CHECK("sgemm_kernel<nn>");
-    }
+    // v_posed[T,3V] = coef[T,512] x basis^T  (template + shape + pose blend shapes, one tcgen05 contraction)
+    rc = tc_gemm_3xtf32(S + L.coef_hi, S + L.coef_lo, KP, m.basis_nk_hi, m.basis_nk_lo, KP, int(T), 3 * V, KP,
+                        S + L.vposed, ldp, 1, nullptr, st);
+    if (rc) return rc;
     {
         dim3 grid((unsigned)ceil_div(V, SKIN_THREADS), (unsigned)T);
-        skin_fwd_kernel<<<grid, SKIN_THREADS, 0, st>>>(m, theta, S + L.A, S + L.vposed, vertices);
+        skin_fwd_kernel<<<grid, SKIN_THREADS, 0, st>>>(m, theta, S + L.A, S + L.vposed, ldp, vertices);
         FPV_LAUNCH_CHECK("skin_fwd_kernel");
     }
     if (m.num_extra > 0) {
@@ -676,25 +614,22 @@ int fpv_smplx_bwd(const fpv_smplx_model_t *model, int64_t T, const float *theta,
     const float *S = static_cast<const float *>(saved);
     float *W = static_cast<float *>(workspace);
     const int jstride = NJ + m.num_extra;
+    const int64_t ldp = pitch3v(V);
     {
         dim3 grid((unsigned)ceil_div(V, SKIN_THREADS), (unsigned)T);
-        skin_bwd_kernel<<<grid, SKIN_THREADS, 0, st>>>(m, S + L.A, g_vertices, g_joints, jstride, W + B.gvp);
+        skin_bwd_kernel<<<grid, SKIN_THREADS, 0, st>>>(m, S + L.A, g_vertices, g_joints, jstride, ldp, W + B.gvp_hi,
+                                                       W + B.gvp_lo);
         FPV_LAUNCH_CHECK("skin_bwd_kernel");
     }
     {
         dim3 grid(NJ + 1, (unsigned)T);
-        jointgrad_kernel<<<grid, 128, 0, st>>>(m, S + L.vposed, g_vertices, g_joints, jstride, W + B.gA, W + B.gT);
+        jointgrad_kernel<<<grid, 128, 0, st>>>(m, S + L.vposed, ldp, g_vertices, g_joints, jstride, W + B.gA, W + B.gT);
         FPV_LAUNCH_CHECK("jointgrad_kernel");
     }
-    {
-        const int K = 3 * V;
-        dim3 grid((unsigned)ceil_div(KP, 64), (unsigned)ceil_div(T, 64), (unsigned)B.nz);
-        sgemm_kernel<true><<<grid, 256, 0, st>>>(W + B.gvp, m.basis_kn, W + B.part, int(T), KP, K, BWD_KCHUNK);
-        FPV_LAUNCH_CHECK("sgemm_kernel<nt>");
-        const int64_t mn = T * KP;
-        splitk_reduce_kernel<<<(unsigned)ceil_div(mn, 256), 256, 0, st>>>(W + B.part, mn, B.nz, W + B.gC);
-        FPV_LAUNCH_CHECK("splitk_reduce_kernel");
-    }
+    // gC[T,512] = g_vposed[T,3V] x basis  (split-K over 3V on the tensor cores, fixed-order slice reduction)
+    rc = tc_gemm_3xtf32(W + B.gvp_hi, W + B.gvp_lo, ldp, m.basis_kn_hi, m.basis_kn_lo, ldp, int(T), KP, 3 * V, W + B.gC,
+                        KP, B.nz, W + B.part, st);
+    if (rc) return rc;
     pose_bwd_kernel<<<(unsigned)T, 64, 0, st>>>(m, theta, S + L.R, S + L.G, S + L.J, W + B.gA, W + B.gT, W + B.gC,
                                                 g_joints, jstride, g_theta);
     FPV_LAUNCH_CHECK("pose_bwd_kernel");

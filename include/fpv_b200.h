@@ -145,9 +145,11 @@ typedef struct fpv_smplx_model {
     int32_t num_extra;      /* E: vertex-picked extra joints appended after the 55 */
     int32_t ell_width;      /* W: max skinning influences per vertex */
     int32_t reserved;
-    const float *basis_kn;  /* [512][3V]  rows: posedirs(486) | shapedirs^T(20) | v_template | 0 */
-    const float *basis_nk_hi, *basis_nk_lo; /* [3V][512] tf32 split of basis_kn^T (tensor-core fwd) */
-    const float *basis_kn_hi, *basis_kn_lo; /* [512][3V] tf32 split (tensor-core bwd) */
+    /* blend basis [512][3V]: rows posedirs(486) | shapedirs^T(20) | v_template | 0, stored as TF32 hi/lo
+     * splits in both operand orientations of the tcgen05 GEMMs.  P = 3V rounded up to a multiple of 4. */
+    const float *basis_kn;                  /* unused (reserved) */
+    const float *basis_nk_hi, *basis_nk_lo; /* [3V][512]  forward  B operand (K = 512 contiguous) */
+    const float *basis_kn_hi, *basis_kn_lo; /* [512][P]   backward B operand (K = 3V contiguous, pitch P) */
     const float *j_template;   /* [55,3]    J_regressor @ v_template */
     const float *j_shapedirs;  /* [55,3,20] J_regressor @ shapedirs */
     const int32_t *parents;    /* [55] */
@@ -172,6 +174,18 @@ int fpv_smplx_fwd(const fpv_smplx_model_t *model_host, int64_t T, const float *t
 int fpv_smplx_bwd(const fpv_smplx_model_t *model_host, int64_t T, const float *theta,
                   const void *saved, const float *g_vertices, const float *g_joints,
                   float *g_theta, void *workspace, size_t workspace_bytes, fpv_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Tensor-core GEMM with fp32-level accuracy (3xTF32 on tcgen05), the contraction engine of the SMPL-X
+ * blend shapes:  C[M,N] = sum_k A[m,k] * B[n,k], A and B row-major with K contiguous, given as TF32
+ * hi/lo splits (fpv_split_tf32).  Row pitches lda/ldb (floats) must be multiples of 4 and the bases 16-byte
+ * aligned (TMA).  ksplit > 1 slices K across CTAs; partials are reduced in fixed order (deterministic).
+ * ------------------------------------------------------------------------------------------ */
+int fpv_split_tf32(const float *src, int64_t n, float *hi, float *lo, fpv_stream_t stream);
+size_t fpv_tc_gemm_workspace_bytes(int M, int N, int ksplit);
+int fpv_tc_gemm_3xtf32(const float *a_hi, const float *a_lo, int64_t lda, const float *b_hi,
+                       const float *b_lo, int64_t ldb, int M, int N, int K, float *C, int64_t ldc,
+                       int ksplit, void *workspace, size_t workspace_bytes, fpv_stream_t stream);
 
 #ifdef __cplusplus
 }
