@@ -28,6 +28,23 @@ constexpr size_t NN_SMEM = size_t(NN_STAGES) * 3 * NN_TILE * sizeof(float) + 2 *
 static int g_tune_qpt = 0;      // 0 = heuristic
 static int g_tune_nsplit = 0;   // 0 = heuristic
 static int g_tune_packed = -1;  // -1 = default; else number of packed queries per thread
+static int g_engine = 0;        // 0 = auto, 1 = FP32 SIMT brute force, 2 = tensor-core filter + exact re-check
+
+// nn_tc.cu
+size_t nn_tc_workspace_bytes(int64_t cand_batches);
+void nn_tc_set_eshift(int e);
+void nn_tc_plan(int64_t eb, int64_t eN, int64_t M, int nsplit_hint, int *nsplit, int64_t *chunk);
+int nn_tc_launch(const float *queries, int64_t q_bstride, int64_t eb, int64_t eN, const float *planes,
+                 int64_t plane_bstride, int64_t cand_batches, int64_t Mp, int64_t M, int64_t idx_base, float *dist,
+                 void *idx, int idx_bytes, unsigned long long *keys, int keys_atomic, int nsplit, int64_t chunk,
+                 float *ymax_ws, cudaStream_t st);
+
+static bool use_tc(int64_t eb, int64_t eN, int64_t M) {
+    if (g_engine == 1) return false;
+    if (g_engine == 2) return true;
+    // the filter pays once there are enough rows to fill the MMA tiles and enough candidates to amortise setup
+    return eN >= 2048 && M >= 1024 && double(eb) * double(eN) * double(M) >= 2.0e9;
+}
 
 struct NNParams {
     const float *q;
@@ -329,57 +346,78 @@ static int nn_search_impl(const float *queries, int q_shared, int64_t batches, i
         q_bstride = 0;
     }
     FPV_CHECK_ARG(eb <= 65535, "nn_search: more than 65535 candidate batches");
-    const NNPlan pl = nn_plan(eb, eN, M);
-    NNParams p;
-    p.q = queries;
-    p.q_bstride = q_bstride;
-    p.N = eN;
-    p.planes = ref_planes;
-    p.plane_bstride = plane_bstride;
-    p.Mp = Mp;
-    p.M8 = pl.M8;
-    p.chunk = pl.chunk;
-    p.idx_base = idx_base;
-    p.dist = dist;
-    p.idx = idx;
-    p.idx_bytes = idx_bytes;
-    p.keys = reinterpret_cast<unsigned long long *>(keys);
-    p.keys_atomic = 0;
     const int64_t total = eb * eN;
+    const bool tc = use_tc(eb, eN, M);
+    NNPlan pl = nn_plan(eb, eN, M);
+    int tc_ns = 1;
+    int64_t tc_chunk = 0;
+    if (tc) nn_tc_plan(eb, eN, M, g_tune_nsplit, &tc_ns, &tc_chunk);
+    const int nsplit = tc ? tc_ns : pl.nsplit;
+    Arena ar(workspace, workspace_bytes);
+    float *ymax_ws = nullptr;
+    if (tc) {
+        ymax_ws = ar.take<float>(size_t(ref_batches));
+        if (!ymax_ws) {
+            set_error("nn_search: workspace too small (%zu bytes)", workspace_bytes);
+            return FPV_ERR_WORKSPACE;
+        }
+    }
+    unsigned long long *kout = reinterpret_cast<unsigned long long *>(keys);
     unsigned long long *scratch_keys = nullptr;
-    if (pl.nsplit > 1) {
-        if (!keys) {
-            Arena ar(workspace, workspace_bytes);
+    int keys_atomic = 0;
+    if (nsplit > 1) {
+        if (!kout) {
             scratch_keys = ar.take<unsigned long long>(size_t(total));
             if (!scratch_keys) {
                 set_error("nn_search: workspace too small (%zu bytes, need %zu)", workspace_bytes,
-                          align_up(size_t(total) * 8, 256));
+                          align_up(size_t(total) * 8, 256) + 512);
                 return FPV_ERR_WORKSPACE;
             }
-            p.keys = scratch_keys;
+            kout = scratch_keys;
         }
-        p.keys_atomic = 1;
-        FPV_CUDA(cudaMemsetAsync(p.keys, 0xff, size_t(total) * 8, st));
+        keys_atomic = 1;
+        FPV_CUDA(cudaMemsetAsync(kout, 0xff, size_t(total) * 8, st));
     }
-    dim3 grid((unsigned)pl.qblocks, (unsigned)pl.nsplit, (unsigned)eb);
     if (profile_on()) {
         // algorithmic bytes: every distinct query point and candidate once, outputs once
         const double qpts = double(q_shared ? N : batches * N), out_b = keys && !dist ? 8.0 : 4.0 + idx_bytes;
         char nm[48];
-        snprintf(nm, sizeof(nm), "nn_search<%d> Q=%lld M=%lld", pl.qpt, (long long)total, (long long)M);
+        snprintf(nm, sizeof(nm), "%s Q=%lld M=%lld", tc ? "nn_tc" : "nn_search<4>", (long long)total, (long long)M);
         profile_begin(nm, st, 12.0 * qpts + 12.0 * double(M) * double(ref_batches) + out_b * double(total),
                       double(total) * double(M));
     }
-    cudaError_t e = nn_dispatch(pl.qpt, p, grid, st);
-    profile_end(st);
-    count_launch();
-    if (e != cudaSuccess) {
-        set_error("nn_search_kernel launch failed: %s", cudaGetErrorString(e));
-        return FPV_ERR_CUDA;
+    if (tc) {
+        int rc = nn_tc_launch(queries, q_bstride, eb, eN, ref_planes, plane_bstride, ref_batches, Mp, M, idx_base, dist,
+                              idx, idx_bytes, kout, keys_atomic, tc_ns, tc_chunk, ymax_ws, st);
+        profile_end(st);
+        if (rc) return rc;
+    } else {
+        NNParams p;
+        p.q = queries;
+        p.q_bstride = q_bstride;
+        p.N = eN;
+        p.planes = ref_planes;
+        p.plane_bstride = plane_bstride;
+        p.Mp = Mp;
+        p.M8 = pl.M8;
+        p.chunk = pl.chunk;
+        p.idx_base = idx_base;
+        p.dist = dist;
+        p.idx = idx;
+        p.idx_bytes = idx_bytes;
+        p.keys = kout;
+        p.keys_atomic = keys_atomic;
+        dim3 grid((unsigned)pl.qblocks, (unsigned)pl.nsplit, (unsigned)eb);
+        cudaError_t e = nn_dispatch(pl.qpt, p, grid, st);
+        profile_end(st);
+        count_launch();
+        if (e != cudaSuccess) {
+            set_error("nn_search_kernel launch failed: %s", cudaGetErrorString(e));
+            return FPV_ERR_CUDA;
+        }
     }
     if (scratch_keys || (keys && dist)) {  // split merge, or caller wants keys AND plain outputs
-        const unsigned long long *src = scratch_keys ? scratch_keys : p.keys;
-        unpack_keys_kernel<<<(unsigned)ceil_div(total, 256), 256, 0, st>>>(src, total, dist, idx, idx_bytes);
+        unpack_keys_kernel<<<(unsigned)ceil_div(total, 256), 256, 0, st>>>(kout, total, dist, idx, idx_bytes);
         FPV_LAUNCH_CHECK("unpack_keys_kernel");
     }
     return FPV_OK;
@@ -391,8 +429,13 @@ static size_t nn_search_ws(int64_t batches, int64_t N, int64_t M, int ref_shared
         eN = batches * N;
         eb = 1;
     }
+    // worst case over both engines (the engine can be switched by the tuning hook after sizing)
     const NNPlan pl = nn_plan(eb, eN, M);
-    return pl.nsplit > 1 ? align_up(size_t(eb * eN) * 8, 256) : 0;
+    int tc_ns = 1;
+    int64_t tc_chunk = 0;
+    nn_tc_plan(eb, eN, M, g_tune_nsplit, &tc_ns, &tc_chunk);
+    const size_t keys = (pl.nsplit > 1 || tc_ns > 1) ? align_up(size_t(eb * eN) * 8, 256) : 0;
+    return keys + nn_tc_workspace_bytes(batches) + 256;
 }
 
 static int pack_planes_impl(const float *pts, int64_t batches, int64_t M, float *planes, cudaStream_t st) {
@@ -609,6 +652,14 @@ int fpv_nn_set_tuning(int qpt, int nsplit, int packed) {
     g_tune_qpt = qpt;
     g_tune_nsplit = nsplit;
     g_tune_packed = packed;
+    return FPV_OK;
+}
+
+// engine: 0 = auto, 1 = FP32 SIMT brute force, 2 = tensor-core filter + exact re-check.
+// tc_eshift: the filter's error bound is 2^-tc_eshift * max(|x|^2, max|y|^2) (0 = default 15).
+int fpv_nn_set_engine(int engine, int tc_eshift) {
+    g_engine = (engine >= 0 && engine <= 2) ? engine : 0;
+    nn_tc_set_eshift(tc_eshift > 0 ? tc_eshift : 15);
     return FPV_OK;
 }
 

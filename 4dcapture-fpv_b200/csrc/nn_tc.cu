@@ -1,0 +1,529 @@
+// nn_tc.cu -- exact nearest neighbour with a tensor-core FILTER (tcgen05 + TMEM) and an exact FP32 re-check.
+//
+// north_star item 1: "uses the tensor-core GEMM form (|x|^2+|y|^2-2x.y) only if ncu shows it beats the FP32
+// SIMT path, and then only with an exact FP32 re-check of the winning candidates".  This is that path.
+// Results are bit-identical to nn_search_kernel (nn_search.cu): the tensor cores only decide which
+// candidates are worth an exact evaluation.
+//
+//   approx  D~[i][j] = |x_i|^2 + |y_j|^2 - 2 x_i.y_j   as ONE K=16 TF32 contraction per pair:
+//           every coordinate is split x = xh + xl (TF32 pieces) and the three products xh*yh, xh*yl, xl*yh
+//           occupy three K slots; |x|^2 and |y|^2 are split in three TF32 pieces against constant 1s.
+//           |D~ - d_canonical| <= E_i := 2^-e * max(|x_i|^2, max_j |y_j|^2)   (e = 15 by default; the
+//           measured error is ~2^-19 of that scale, tests/test_nn_tc_gpu.py sweeps e to show the margin)
+//   exact   per query row, per group of 32 accumulator columns: a FMNMX3 chain gives the group's minimum;
+//           only when it is <= (best exact distance so far + E_i) are the columns re-read and the
+//           candidates below the threshold re-evaluated with the canonical fp32 expression.  Candidates
+//           are visited in increasing index order and updates use strict '<', so the lowest index wins.
+//           Proof sketch: the true winner j* has D~[j*] <= d(j*) + E <= best + E whenever it is met.
+//
+// CTA = 12 warps: 0 bulk-copy producer (candidate planes), 1-2 operand converters (fp32 planes -> TF32
+// split K=16 operand in the UMMA no-swizzle K-major layout), 3 TMEM allocator + MMA issuer
+// (tcgen05.mma.kind::tf32 128x256x8, two per tile), 4-11 epilogue (tcgen05.ld 32x32b.x32).
+// Each CTA keeps QT query tiles (128 rows each) resident as A operands and streams candidate tiles of 256.
+#include <math_constants.h>
+
+#include "common.cuh"
+
+namespace fpv {
+
+constexpr int TC_QT = 4;           // query tiles per CTA
+constexpr int TC_M = 128;          // rows per query tile (MMA M)
+constexpr int TC_N = 256;          // candidates per tile (MMA N)
+constexpr int TC_K = 16;           // TF32 slots per pair
+constexpr int TC_STAGES = 3;
+constexpr int TC_THREADS = 384;
+constexpr int TC_PLANE_BYTES = 3 * TC_N * 4;             // 3 KB   fp32 xyz planes of one candidate tile
+constexpr int TC_BOP_BYTES = TC_N * TC_K * 4;            // 16 KB  TF32 operand of one candidate tile
+constexpr int TC_AOP_BYTES = TC_M * TC_K * 4;            // 8 KB   TF32 operand of one query tile
+constexpr int TC_STAGE_BYTES = TC_PLANE_BYTES + TC_BOP_BYTES;
+constexpr int TC_STATE_WORDS = 6;  // per (tile, row, column-half): best d, best j, qx, qy, qz, error bound
+constexpr size_t TC_SMEM = size_t(TC_QT) * TC_AOP_BYTES + size_t(TC_STAGES) * TC_STAGE_BYTES +
+                           size_t(TC_QT) * TC_M * 2 * TC_STATE_WORDS * 4 + 256 /*barriers*/ + 128 /*align*/;
+
+static int g_tc_eshift = 15;
+
+struct NNTCParams {
+    const float *q;
+    int64_t q_bstride;
+    int64_t N;
+    const float *planes;
+    int64_t plane_bstride;
+    int64_t Mp, M;
+    int64_t chunk;  // candidates per blockIdx.y slice (multiple of TC_N)
+    int64_t idx_base;
+    const float *ymax;  // [candidate batches] max_j |y_j|^2 (finite part)
+    int64_t ymax_bstride;
+    float escale;  // 2^-e
+    float *dist;
+    void *idx;
+    int idx_bytes;
+    unsigned long long *keys;
+    int keys_atomic;
+};
+
+// ---- PTX wrappers (tcgen05) -------------------------------------------------------------------
+__device__ __forceinline__ void tcx_alloc(uint32_t *slot_smem, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot_smem)),
+                 "r"(ncols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tcx_dealloc(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tcx_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tcx_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tcx_commit(uint64_t *bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void tcx_mma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                             uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+        "}\n" ::"r"(tmem_d),
+        "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void tcx_ld32(uint32_t taddr, float (&v)[32]) {
+    uint32_t r[32];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// K-major operand without swizzle: 8-row x 16-byte core matrices; address(row r, 16B chunk c) =
+// (r % 8) * 16 + (r / 8) * SBO + c * LBO.  One MMA (K = 8 tf32 = 32 B) reads chunks c and c+1.
+__device__ __forceinline__ uint64_t umma_desc_plain(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    return uint64_t((smem_addr & 0x3FFFF) >> 4) | (uint64_t(lbo_bytes >> 4) << 16) | (uint64_t(sbo_bytes >> 4) << 32) |
+           (uint64_t(1) << 46);
+}
+__host__ __device__ constexpr uint32_t umma_idesc_tf32_mn(int M, int N) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | (uint32_t(N >> 3) << 17) | (uint32_t(M >> 4) << 24);
+}
+
+__device__ __forceinline__ float tf32r(float x) { return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u); }
+
+__device__ __forceinline__ float d2_canon(float x, float y, float z, float rx, float ry, float rz) {
+    const float dx = __fsub_rn(x, rx), dy = __fsub_rn(y, ry), dz = __fsub_rn(z, rz);
+    return __fmaf_rn(dz, dz, __fmaf_rn(dy, dy, __fmul_rn(dx, dx)));
+}
+
+// write one operand row (16 tf32 values) into the chunk-major no-swizzle layout: 4 chunks of 16 bytes,
+// chunk c of row r at  base + c * (rows*16) + (r/8)*128 + (r%8)*16
+__device__ __forceinline__ void store_row16(unsigned char *base, int rows, int r, const float (&k)[16]) {
+    unsigned char *p = base + (r >> 3) * 128 + (r & 7) * 16;
+#pragma unroll
+    for (int c = 0; c < 4; ++c)
+        *reinterpret_cast<float4 *>(p + size_t(c) * rows * 16) = make_float4(k[4 * c], k[4 * c + 1], k[4 * c + 2], k[4 * c + 3]);
+}
+
+__device__ __forceinline__ void split3(float v, float &h, float &m, float &l) {
+    h = tf32r(v);
+    const float r = v - h;
+    m = tf32r(r);
+    l = tf32r(r - m);
+}
+
+// Exact re-evaluation of one candidate column (canonical fp32 expression, strict '<': lowest index wins).
+__device__ __forceinline__ void tc_eval(const float *px, const float *py, const float *pz, int col, int jglob, int jmax,
+                                        float qx, float qy, float qz, float &bd, int &bj) {
+    if (jglob < jmax) {
+        const float d = d2_canon(qx, qy, qz, px[col], py[col], pz[col]);
+        if (d < bd) {
+            bd = d;
+            bj = jglob;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(TC_THREADS, 1) nn_tc_kernel(const NNTCParams p) {
+    extern __shared__ unsigned char smem_raw[];
+    const uint32_t base_u32 = smem_u32(smem_raw);
+    unsigned char *sm = smem_raw + (((base_u32 + 127u) & ~127u) - base_u32);
+    unsigned char *aop = sm;                                            // [QT][8 KB]
+    unsigned char *stages = aop + size_t(TC_QT) * TC_AOP_BYTES;         // [STAGES][planes 3 KB | bop 16 KB]
+    // per-thread search state, word-major so a warp's accesses are conflict-free: state[w][t][half][row]
+    float *state = reinterpret_cast<float *>(stages + size_t(TC_STAGES) * TC_STAGE_BYTES);
+    uint64_t *bars = reinterpret_cast<uint64_t *>(state + size_t(TC_QT) * TC_M * 2 * TC_STATE_WORDS);
+    uint64_t *pl_full = bars;                      // [STAGES] producer -> converters, epilogue
+    uint64_t *bop_full = pl_full + TC_STAGES;      // [STAGES] converters -> MMA
+    uint64_t *stage_empty = bop_full + TC_STAGES;  // [STAGES] epilogue -> producer
+    uint64_t *acc_full = stage_empty + TC_STAGES;  // [2] MMA -> epilogue
+    uint64_t *acc_empty = acc_full + 2;            // [2] epilogue -> MMA
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(acc_empty + 2);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int64_t b = blockIdx.z;
+    const int64_t r0 = int64_t(blockIdx.y) * p.chunk;
+    const int64_t r1 = (r0 + p.chunk < p.M) ? (r0 + p.chunk) : p.M;
+    const int ntiles = int((r1 - r0 + TC_N - 1) / TC_N);
+    const int64_t qbase = int64_t(blockIdx.x) * (TC_QT * TC_M);
+    const float *qsrc = p.q + b * p.q_bstride;
+
+    if (tid == 0) {
+        for (int s = 0; s < TC_STAGES; ++s) {
+            mbar_init(&pl_full[s], 1);
+            mbar_init(&bop_full[s], 2);
+            mbar_init(&stage_empty[s], 8);
+        }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&acc_full[i], 1);
+            mbar_init(&acc_empty[i], 8);
+        }
+        mbar_fence_init();
+    }
+    if (warp == 3) tcx_alloc(tmem_slot, 512);
+
+    // ---- epilogue threads own one query row per tile: load it, build the A operand (half 0 only) ----
+    const bool is_epi = warp >= 4;
+    const int ew = warp - 4;
+    const int quarter = warp & 3, half = ew >> 2;
+    const int row = quarter * 32 + lane;
+    constexpr int SW = TC_QT * 2 * TC_M;  // words per state plane
+    if (is_epi) {
+        const float ymax = p.ymax[b * p.ymax_bstride];
+        for (int t = 0; t < TC_QT; ++t) {
+            int64_t qi = qbase + int64_t(t) * TC_M + row;
+            if (qi > p.N - 1) qi = p.N - 1;
+            const float x = __ldg(qsrc + 3 * qi), y = __ldg(qsrc + 3 * qi + 1), z = __ldg(qsrc + 3 * qi + 2);
+            const float n = __fmaf_rn(z, z, __fmaf_rn(y, y, __fmul_rn(x, x)));
+            const float sc = fmaxf(n, ymax);
+            float *st = state + (t * 2 + half) * TC_M + row;
+            st[0 * SW] = CUDART_INF_F;
+            st[1 * SW] = __int_as_float(0);
+            st[2 * SW] = x;
+            st[3 * SW] = y;
+            st[4 * SW] = z;
+            // non-finite scale: the filter cannot be trusted for this row -> always re-check (bound = +inf)
+            st[5 * SW] = (tf32r(sc) < CUDART_INF_F) ? __fmul_rn(sc, p.escale) : CUDART_INF_F;
+            if (half == 0) {
+                float k[16];
+                float h, m, l;
+                k[0] = k[1] = tf32r(x);
+                k[2] = tf32r(x - k[0]);
+                k[3] = k[4] = tf32r(y);
+                k[5] = tf32r(y - k[3]);
+                k[6] = k[7] = tf32r(z);
+                k[8] = tf32r(z - k[6]);
+                split3(n, h, m, l);
+                k[9] = h;
+                k[10] = m;
+                k[11] = 1.f;
+                k[12] = 1.f;
+                k[13] = l;
+                k[14] = 1.f;
+                k[15] = 0.f;
+                if (!(h < CUDART_INF_F)) {  // keep inf/NaN out of the tensor cores; this row re-checks everything
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) k[i] = 0.f;
+                }
+                store_row16(aop + size_t(t) * TC_AOP_BYTES, TC_M, row, k);
+            }
+        }
+        fence_proxy_async();
+    }
+    tcx_fence_before();
+    __syncthreads();
+    tcx_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ---------------- producer: candidate planes -> smem ----------------
+        if (lane == 0) {
+            const float *src = p.planes + b * p.plane_bstride + r0;
+            for (int k = 0; k < ntiles; ++k) {
+                const int s = k % TC_STAGES;
+                const uint32_t ph = (k / TC_STAGES) & 1;
+                mbar_wait(&stage_empty[s], ph ^ 1);
+                int64_t cnt = p.Mp - (r0 + int64_t(k) * TC_N);  // planes are padded to Mp (multiple of 32) with +inf
+                if (cnt > TC_N) cnt = TC_N;
+                const uint32_t bytes = uint32_t(cnt) * 4u;
+                float *dst = reinterpret_cast<float *>(stages + size_t(s) * TC_STAGE_BYTES);
+                const float *g = src + int64_t(k) * TC_N;
+                mbar_arrive_expect_tx(&pl_full[s], 3 * bytes);
+                bulk_g2s(dst, g, bytes, &pl_full[s]);
+                bulk_g2s(dst + TC_N, g + p.Mp, bytes, &pl_full[s]);
+                bulk_g2s(dst + 2 * TC_N, g + 2 * p.Mp, bytes, &pl_full[s]);
+            }
+        }
+    } else if (warp == 1 || warp == 2) {
+        // ---------------- converters: fp32 planes -> TF32-split B operand ----------------
+        const int ct = (warp - 1) * 32 + lane;  // 0..63, four candidates each
+        for (int k = 0; k < ntiles; ++k) {
+            const int s = k % TC_STAGES;
+            const uint32_t ph = (k / TC_STAGES) & 1;
+            mbar_wait(&pl_full[s], ph);
+            unsigned char *st = stages + size_t(s) * TC_STAGE_BYTES;
+            const float *px = reinterpret_cast<const float *>(st), *py = px + TC_N, *pz = py + TC_N;
+            unsigned char *bop = st + TC_PLANE_BYTES;
+            const int64_t jt0 = r0 + int64_t(k) * TC_N;
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int c = ct + u * 64;
+                float x = 0.f, y = 0.f, z = 0.f, m = 1e30f;
+                if (jt0 + c < r1) {
+                    x = px[c];
+                    y = py[c];
+                    z = pz[c];
+                    m = __fmaf_rn(z, z, __fmaf_rn(y, y, __fmul_rn(x, x)));
+                    if (!(tf32r(m) < CUDART_INF_F)) {  // non-finite candidate: park it far away; the exact re-check decides
+                        x = y = z = 0.f;
+                        m = 1e30f;
+                    }
+                }
+                float k16[16];
+                float h, mm, l;
+                const float xh = tf32r(x), yh = tf32r(y), zh = tf32r(z);
+                k16[0] = -2.f * xh;
+                k16[1] = -2.f * tf32r(x - xh);
+                k16[2] = k16[0];
+                k16[3] = -2.f * yh;
+                k16[4] = -2.f * tf32r(y - yh);
+                k16[5] = k16[3];
+                k16[6] = -2.f * zh;
+                k16[7] = -2.f * tf32r(z - zh);
+                k16[8] = k16[6];
+                split3(m, h, mm, l);
+                k16[9] = 1.f;
+                k16[10] = 1.f;
+                k16[11] = h;
+                k16[12] = mm;
+                k16[13] = 1.f;
+                k16[14] = l;
+                k16[15] = 0.f;
+                store_row16(bop, TC_N, c, k16);
+            }
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bop_full[s]);
+        }
+    } else if (warp == 3) {
+        // ---------------- MMA issuer ----------------
+        if (lane == 0) {
+            constexpr uint32_t idesc = umma_idesc_tf32_mn(TC_M, TC_N);
+            const uint32_t aop_u32 = smem_u32(aop);
+            int seq = 0;
+            for (int k = 0; k < ntiles; ++k) {
+                const int s = k % TC_STAGES;
+                const uint32_t ph = (k / TC_STAGES) & 1;
+                mbar_wait(&bop_full[s], ph);
+                tcx_fence_after();
+                const uint32_t bop_u32 = smem_u32(stages + size_t(s) * TC_STAGE_BYTES + TC_PLANE_BYTES);
+                const uint64_t db0 = umma_desc_plain(bop_u32, TC_N * 16, 128);
+                const uint64_t db1 = umma_desc_plain(bop_u32 + 2 * TC_N * 16, TC_N * 16, 128);
+#pragma unroll 1
+                for (int t = 0; t < TC_QT; ++t, ++seq) {
+                    const int buf = seq & 1;
+                    mbar_wait(&acc_empty[buf], ((seq >> 1) & 1) ^ 1);
+                    tcx_fence_after();
+                    const uint32_t a_u32 = aop_u32 + uint32_t(t) * TC_AOP_BYTES;
+                    const uint64_t da0 = umma_desc_plain(a_u32, TC_M * 16, 128);
+                    const uint64_t da1 = umma_desc_plain(a_u32 + 2 * TC_M * 16, TC_M * 16, 128);
+                    const uint32_t d = tmem_base + uint32_t(buf * TC_N);
+                    tcx_mma_tf32(d, da0, db0, idesc, 0);
+                    tcx_mma_tf32(d, da1, db1, idesc, 1);
+                    tcx_commit(&acc_full[buf]);
+                }
+            }
+        }
+    } else {
+        // ---------------- epilogue: filter + exact re-check ----------------
+        int seq = 0;
+        const int jmax = int(r1);
+        for (int k = 0; k < ntiles; ++k) {
+            const int s = k % TC_STAGES;
+            const uint32_t ph = (k / TC_STAGES) & 1;
+            mbar_wait(&pl_full[s], ph);  // acquire the TMA-written planes for the exact re-check
+            const float *px = reinterpret_cast<const float *>(stages + size_t(s) * TC_STAGE_BYTES);
+            const float *py = px + TC_N, *pz = py + TC_N;
+            const int jt0 = int(r0) + k * TC_N;
+#pragma unroll 1
+            for (int t = 0; t < TC_QT; ++t, ++seq) {
+                float *st = state + (t * 2 + half) * TC_M + row;
+                float bd = st[0];
+                int bj = __float_as_int(st[SW]);
+                const float qx = st[2 * SW], qy = st[3 * SW], qz = st[4 * SW], qe = st[5 * SW];
+                const float bd_in = bd;
+                const int buf = seq & 1;
+                mbar_wait(&acc_full[buf], (seq >> 1) & 1);
+                tcx_fence_after();
+                const uint32_t taddr0 =
+                    tmem_base + (uint32_t(quarter * 32) << 16) + uint32_t(buf * TC_N + half * (TC_N / 2));
+#pragma unroll 1
+                for (int g = 0; g < TC_N / 2 / 32; ++g) {
+                    float v[32];
+                    tcx_ld32(taddr0 + uint32_t(g * 32), v);
+                    float pm[8];
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) pm[c] = fminf(fmin3(v[4 * c], v[4 * c + 1], v[4 * c + 2]), v[4 * c + 3]);
+                    float m = fmin3(pm[0], pm[1], pm[2]);
+                    m = fmin3(m, pm[3], pm[4]);
+                    m = fmin3(m, pm[5], pm[6]);
+                    m = fminf(m, pm[7]);
+                    float thresh = bd + qe;
+                    if (!(m > thresh)) {  // rare for long scans: some column may beat the best exact distance
+                        const int col0 = half * (TC_N / 2) + g * 32;
+#pragma unroll
+                        for (int c = 0; c < 8; ++c) {
+                            if (!(pm[c] > thresh)) {
+#pragma unroll
+                                for (int i = 0; i < 4; ++i) {
+                                    if (!(v[4 * c + i] > thresh)) {
+                                        tc_eval(px, py, pz, col0 + 4 * c + i, jt0 + col0 + 4 * c + i, jmax, qx, qy, qz, bd, bj);
+                                        thresh = bd + qe;
+                                    }
+                                }
+                            }
+                        }
+                    }
+                }
+                tcx_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&acc_empty[buf]);
+                if (bd < bd_in) {
+                    st[0] = bd;
+                    st[SW] = __int_as_float(bj);
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&stage_empty[s]);
+        }
+    }
+    tcx_fence_before();
+    __syncthreads();
+    if (warp == 3) {
+        tcx_fence_after();
+        tcx_dealloc(tmem_base, 512);
+    }
+    if (is_epi && half == 0) {
+        for (int t = 0; t < TC_QT; ++t) {
+            const int64_t qi = qbase + int64_t(t) * TC_M + row;
+            if (qi >= p.N) continue;
+            const float *s0 = state + (t * 2 + 0) * TC_M + row, *s1 = state + (t * 2 + 1) * TC_M + row;
+            float d = s0[0];
+            int j = __float_as_int(s0[SW]);
+            const float d1 = s1[0];
+            const int j1 = __float_as_int(s1[SW]);
+            if (d1 < d || (d1 == d && d1 < CUDART_INF_F && j1 < j)) {  // column halves: lexicographic (d, j)
+                d = d1;
+                j = j1;
+            }
+            const int64_t gi = p.idx_base + j;
+            const int64_t o = b * p.N + qi;
+            if (p.keys) {
+                const unsigned long long key = (static_cast<unsigned long long>(__float_as_uint(d)) << 32) |
+                                               static_cast<unsigned long long>(static_cast<uint32_t>(gi));
+                if (p.keys_atomic)
+                    atomicMin(p.keys + o, key);
+                else
+                    p.keys[o] = key;
+            } else {
+                p.dist[o] = d;
+                if (p.idx_bytes == 8)
+                    static_cast<long long *>(p.idx)[o] = gi;
+                else if (p.idx_bytes == 4)
+                    static_cast<int *>(p.idx)[o] = int(gi);
+            }
+        }
+    }
+}
+
+// max_j |y_j|^2 over the finite candidates of each batch (scale of the filter's error bound)
+__global__ void nn_tc_ymax_kernel(const float *__restrict__ planes, int64_t M, int64_t Mp, float *__restrict__ ymax) {
+    const int64_t b = blockIdx.y;
+    const float *X = planes + b * 3 * Mp, *Y = X + Mp, *Z = Y + Mp;
+    float m = 0.f;
+    for (int64_t j = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; j < M; j += int64_t(gridDim.x) * blockDim.x) {
+        const float n = __fmaf_rn(Z[j], Z[j], __fmaf_rn(Y[j], Y[j], __fmul_rn(X[j], X[j])));
+        if (n < CUDART_INF_F) m = fmaxf(m, n);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0 && m > 0.f) atomicMax(reinterpret_cast<unsigned *>(ymax + b), __float_as_uint(m));
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side (called from nn_search.cu)
+// ---------------------------------------------------------------------------------------------
+size_t nn_tc_workspace_bytes(int64_t cand_batches) { return align_up(size_t(cand_batches) * sizeof(float), 256); }
+
+void nn_tc_set_eshift(int e) { g_tc_eshift = (e >= 8 && e <= 30) ? e : 15; }
+
+void nn_tc_plan(int64_t eb, int64_t eN, int64_t M, int nsplit_hint, int *nsplit, int64_t *chunk) {
+    const int64_t qblocks = ceil_div(eN, int64_t(TC_QT) * TC_M);
+    const int64_t ntiles = ceil_div(M, TC_N);
+    int64_t ns = nsplit_hint > 0 ? nsplit_hint : 1;
+    if (nsplit_hint <= 0) {
+        const int64_t target = int64_t(sm_count()) * 8, base = qblocks * eb;
+        ns = ceil_div(target, base);
+        const int64_t max_ns = ntiles / 16 > 1 ? ntiles / 16 : 1;
+        if (ns > max_ns) ns = max_ns;
+    }
+    if (ns > 65535) ns = 65535;
+    if (ns > ntiles) ns = ntiles;
+    *chunk = ceil_div(ntiles, ns) * TC_N;
+    *nsplit = int(ceil_div(M, *chunk));
+}
+
+int nn_tc_launch(const float *queries, int64_t q_bstride, int64_t eb, int64_t eN, const float *planes,
+                 int64_t plane_bstride, int64_t cand_batches, int64_t Mp, int64_t M, int64_t idx_base, float *dist,
+                 void *idx, int idx_bytes, unsigned long long *keys, int keys_atomic, int nsplit, int64_t chunk,
+                 float *ymax_ws, cudaStream_t st) {
+    static bool configured = false;
+    if (!configured) {
+        FPV_CUDA(cudaFuncSetAttribute(nn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(TC_SMEM)));
+        configured = true;
+    }
+    FPV_CUDA(cudaMemsetAsync(ymax_ws, 0, size_t(cand_batches) * sizeof(float), st));
+    {
+        int nb = int(ceil_div(M, 256 * 8));
+        if (nb > 592) nb = 592;
+        dim3 grid((unsigned)nb, (unsigned)cand_batches);
+        nn_tc_ymax_kernel<<<grid, 256, 0, st>>>(planes, M, Mp, ymax_ws);
+        FPV_LAUNCH_CHECK("nn_tc_ymax_kernel");
+    }
+    NNTCParams p;
+    p.q = queries;
+    p.q_bstride = q_bstride;
+    p.N = eN;
+    p.planes = planes;
+    p.plane_bstride = plane_bstride;
+    p.Mp = Mp;
+    p.M = M;
+    p.chunk = chunk;
+    p.idx_base = idx_base;
+    p.ymax = ymax_ws;
+    p.ymax_bstride = (cand_batches > 1) ? 1 : 0;
+    p.escale = ldexpf(1.f, -g_tc_eshift);
+    p.dist = dist;
+    p.idx = idx;
+    p.idx_bytes = idx_bytes;
+    p.keys = keys;
+    p.keys_atomic = keys_atomic;
+    dim3 grid((unsigned)ceil_div(eN, int64_t(TC_QT) * TC_M), (unsigned)nsplit, (unsigned)eb);
+    nn_tc_kernel<<<grid, TC_THREADS, TC_SMEM, st>>>(p);
+    count_launch();
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) {
+        set_error("nn_tc_kernel launch failed: %s", cudaGetErrorString(e));
+        return FPV_ERR_CUDA;
+    }
+    return FPV_OK;
+}
+
+}  // namespace fpv

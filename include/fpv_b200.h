@@ -73,6 +73,10 @@ int fpv_nn_unpack_keys(const uint64_t *keys, int64_t n, float *dist, void *idx, 
  * (0 = heuristic) and how many queries per thread use packed FP32x2 math (-1 = default).
  * Results never depend on it. */
 int fpv_nn_set_tuning(int qpt, int nsplit, int packed);
+/* Search engine: 0 = auto, 1 = FP32 SIMT brute force (nn_search_kernel), 2 = tensor-core filter with exact
+ * FP32 re-check (nn_tc_kernel).  Both return bit-identical results.  tc_eshift > 0 overrides the filter's
+ * error-bound exponent (default 15); used by the tests to demonstrate the safety margin. */
+int fpv_nn_set_engine(int engine, int tc_eshift);
 
 /* distChamfer(a, b) forward, reference output order (chamfer_python.py:28):
  *   d_b2a [bs,M], d_a2b [bs,N], i_b2a [bs,M] (index into a), i_a2b [bs,N] (index into b).
