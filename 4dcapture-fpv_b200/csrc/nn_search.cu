@@ -33,6 +33,8 @@ static int g_engine = 0;        // 0 = auto, 1 = FP32 SIMT brute force, 2 = tens
 // nn_tc.cu
 size_t nn_tc_workspace_bytes(int64_t cand_batches);
 void nn_tc_set_eshift(int e);
+void nn_tc_set_subtile(int ns);
+void nn_tc_set_debug(long long *dbg);
 void nn_tc_plan(int64_t eb, int64_t eN, int64_t M, int nsplit_hint, int *nsplit, int64_t *chunk);
 int nn_tc_launch(const float *queries, int64_t q_bstride, int64_t eb, int64_t eN, const float *planes,
                  int64_t plane_bstride, int64_t cand_batches, int64_t Mp, int64_t M, int64_t idx_base, float *dist,
@@ -655,11 +657,18 @@ int fpv_nn_set_tuning(int qpt, int nsplit, int packed) {
     return FPV_OK;
 }
 
+// Debug: device buffer of 1024 int64 that receives a clock64 timeline of CTA 0 of nn_tc_kernel (NULL = off).
+int fpv_nn_tc_debug(long long *dbg) {
+    nn_tc_set_debug(dbg);
+    return FPV_OK;
+}
+
 // engine: 0 = auto, 1 = FP32 SIMT brute force, 2 = tensor-core filter + exact re-check.
 // tc_eshift: the filter's error bound is 2^-tc_eshift * max(|x|^2, max|y|^2) (0 = default 15).
 int fpv_nn_set_engine(int engine, int tc_eshift) {
     g_engine = (engine >= 0 && engine <= 2) ? engine : 0;
-    nn_tc_set_eshift(tc_eshift > 0 ? tc_eshift : 15);
+    nn_tc_set_eshift((tc_eshift & 0xff) > 0 ? (tc_eshift & 0xff) : 15);
+    nn_tc_set_subtile(tc_eshift >> 8);  // bits 8.. : accumulator sub-tile width (0 = default)
     return FPV_OK;
 }
 

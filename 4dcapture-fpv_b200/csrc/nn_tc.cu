@@ -36,11 +36,13 @@ constexpr int TC_PLANE_BYTES = 3 * TC_N * 4;             // 3 KB   fp32 xyz plan
 constexpr int TC_BOP_BYTES = TC_N * TC_K * 4;            // 16 KB  TF32 operand of one candidate tile
 constexpr int TC_AOP_BYTES = TC_M * TC_K * 4;            // 8 KB   TF32 operand of one query tile
 constexpr int TC_STAGE_BYTES = TC_PLANE_BYTES + TC_BOP_BYTES;
-constexpr int TC_STATE_WORDS = 6;  // per (tile, row, column-half): best d, best j, qx, qy, qz, error bound
+constexpr int TC_STATE_WORDS = 2;  // per (tile, row): best d, best j (final hand-off to the writer threads)
 constexpr size_t TC_SMEM = size_t(TC_QT) * TC_AOP_BYTES + size_t(TC_STAGES) * TC_STAGE_BYTES +
-                           size_t(TC_QT) * TC_M * 2 * TC_STATE_WORDS * 4 + 256 /*barriers*/ + 128 /*align*/;
+                           size_t(TC_QT) * TC_M * TC_STATE_WORDS * 4 + 256 /*barriers*/ + 128 /*align*/;
 
 static int g_tc_eshift = 15;
+static long long *g_tc_dbg = nullptr;
+static int g_tc_ns = 128;  // accumulator sub-tile width (64 | 128 | 256)
 
 struct NNTCParams {
     const float *q;
@@ -59,6 +61,7 @@ struct NNTCParams {
     int idx_bytes;
     unsigned long long *keys;
     int keys_atomic;
+    long long *dbg;  // optional timeline of CTA 0 (tools/nn_tc_timeline.py): [4][256] clock64 stamps
 };
 
 // ---- PTX wrappers (tcgen05) -------------------------------------------------------------------
@@ -88,8 +91,10 @@ __device__ __forceinline__ void tcx_mma_tf32(uint32_t tmem_d, uint64_t desc_a, u
         "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
         : "memory");
 }
-__device__ __forceinline__ void tcx_ld32(uint32_t taddr, float (&v)[32]) {
-    uint32_t r[32];
+// TMEM -> registers, 32 lanes x 32 consecutive columns (one accumulator row segment per thread).  The load is
+// asynchronous: tcx_ld32_issue starts it, tcx_ld32_wait makes the registers valid.  The wait takes the
+// registers as read-write operands so the compiler cannot hoist a use above it.
+__device__ __forceinline__ void tcx_ld32_issue(uint32_t taddr, uint32_t (&r)[32]) {
     asm volatile(
         "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
         "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
@@ -100,9 +105,28 @@ __device__ __forceinline__ void tcx_ld32(uint32_t taddr, float (&v)[32]) {
           "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
         : "r"(taddr)
         : "memory");
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tcx_ld32_wait(uint32_t (&r)[32]) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
+                   "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]),
+                   "+r"(r[16]), "+r"(r[17]), "+r"(r[18]), "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]),
+                   "+r"(r[23]), "+r"(r[24]), "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]), "+r"(r[29]),
+                   "+r"(r[30]), "+r"(r[31])
+                 :
+                 : "memory");
+}
+// one lane of a converged warp (CUTLASS elect_one_sync idiom)
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred = 0;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "elect.sync _|p, 0xffffffff;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(pred));
+    return pred != 0;
 }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
@@ -151,21 +175,56 @@ __device__ __forceinline__ void tc_eval(const float *px, const float *py, const 
     }
 }
 
+// One group of 32 accumulator columns of one query row: FMNMX3 tree, and -- only if the group's minimum
+// can beat the best exact distance -- the exact re-check of the columns under the threshold.
+__device__ __forceinline__ void tc_group(const uint32_t (&r)[32], const float *px, const float *py, const float *pz,
+                                         int col0, int jglob0, int jmax, float qx, float qy, float qz, float qe,
+                                         float &bd, int &bj) {
+    float pm[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c)
+        pm[c] = fminf(fmin3(__uint_as_float(r[4 * c]), __uint_as_float(r[4 * c + 1]), __uint_as_float(r[4 * c + 2])),
+                      __uint_as_float(r[4 * c + 3]));
+    float m = fmin3(pm[0], pm[1], pm[2]);
+    m = fmin3(m, pm[3], pm[4]);
+    m = fmin3(m, pm[5], pm[6]);
+    m = fminf(m, pm[7]);
+    float thresh = bd + qe;
+    if (!(m > thresh)) {  // rare on long scans; no warp-aligned instruction inside, so divergence is legal
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+            if (!(pm[c] > thresh)) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    if (!(__uint_as_float(r[4 * c + i]) > thresh)) {
+                        tc_eval(px, py, pz, col0 + 4 * c + i, jglob0 + 4 * c + i, jmax, qx, qy, qz, bd, bj);
+                        thresh = bd + qe;
+                    }
+                }
+            }
+        }
+    }
+}
+
+// NS = accumulator sub-tile width (columns per MMA): 512/NS TMEM buffers are in flight, which is what hides the
+// MMA -> commit -> epilogue -> release round trip (each sub-tile is only a K=16 contraction, ~NS/2 tensor cycles).
+template <int NS>
 __global__ void __launch_bounds__(TC_THREADS, 1) nn_tc_kernel(const NNTCParams p) {
+    constexpr int NBUF = 512 / NS;        // TMEM accumulator buffers
+    constexpr int NSUB = TC_N / NS;       // sub-tiles per 256-candidate stage
     extern __shared__ unsigned char smem_raw[];
     const uint32_t base_u32 = smem_u32(smem_raw);
     unsigned char *sm = smem_raw + (((base_u32 + 127u) & ~127u) - base_u32);
     unsigned char *aop = sm;                                            // [QT][8 KB]
     unsigned char *stages = aop + size_t(TC_QT) * TC_AOP_BYTES;         // [STAGES][planes 3 KB | bop 16 KB]
-    // per-thread search state, word-major so a warp's accesses are conflict-free: state[w][t][half][row]
-    float *state = reinterpret_cast<float *>(stages + size_t(TC_STAGES) * TC_STAGE_BYTES);
-    uint64_t *bars = reinterpret_cast<uint64_t *>(state + size_t(TC_QT) * TC_M * 2 * TC_STATE_WORDS);
+    float *state = reinterpret_cast<float *>(stages + size_t(TC_STAGES) * TC_STAGE_BYTES);  // [2][QT][128]
+    uint64_t *bars = reinterpret_cast<uint64_t *>(state + size_t(TC_QT) * TC_M * TC_STATE_WORDS);
     uint64_t *pl_full = bars;                      // [STAGES] producer -> converters, epilogue
     uint64_t *bop_full = pl_full + TC_STAGES;      // [STAGES] converters -> MMA
     uint64_t *stage_empty = bop_full + TC_STAGES;  // [STAGES] epilogue -> producer
-    uint64_t *acc_full = stage_empty + TC_STAGES;  // [2] MMA -> epilogue
-    uint64_t *acc_empty = acc_full + 2;            // [2] epilogue -> MMA
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(acc_empty + 2);
+    uint64_t *acc_full = stage_empty + TC_STAGES;  // [NBUF] MMA -> epilogue
+    uint64_t *acc_empty = acc_full + 8;            // [NBUF] epilogue -> MMA
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(acc_empty + 8);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int64_t b = blockIdx.z;
@@ -181,59 +240,62 @@ __global__ void __launch_bounds__(TC_THREADS, 1) nn_tc_kernel(const NNTCParams p
             mbar_init(&bop_full[s], 2);
             mbar_init(&stage_empty[s], 8);
         }
-        for (int i = 0; i < 2; ++i) {
+        for (int i = 0; i < NBUF; ++i) {
             mbar_init(&acc_full[i], 1);
-            mbar_init(&acc_empty[i], 8);
+            mbar_init(&acc_empty[i], 4);
         }
         mbar_fence_init();
     }
     if (warp == 3) tcx_alloc(tmem_slot, 512);
 
-    // ---- epilogue threads own one query row per tile: load it, build the A operand (half 0 only) ----
+    // ---- epilogue threads: set 0 (warps 4-7) owns query tiles 0,2,..; set 1 (warps 8-11) owns tiles 1,3,..
+    //      Each thread keeps the search state of its row in registers. ----
+    static_assert(TC_QT % 2 == 0 && NBUF % 2 == 0, "query tiles alternate between the two epilogue sets");
+    constexpr int TPS = TC_QT / 2;  // tiles per epilogue set
     const bool is_epi = warp >= 4;
-    const int ew = warp - 4;
-    const int quarter = warp & 3, half = ew >> 2;
+    const int eset = (warp - 4) >> 2;
+    const int quarter = warp & 3;
     const int row = quarter * 32 + lane;
-    constexpr int SW = TC_QT * 2 * TC_M;  // words per state plane
+    float qx[TPS], qy[TPS], qz[TPS], qe[TPS], bd[TPS];
+    int bj[TPS];
     if (is_epi) {
         const float ymax = p.ymax[b * p.ymax_bstride];
-        for (int t = 0; t < TC_QT; ++t) {
+#pragma unroll
+        for (int u = 0; u < TPS; ++u) {
+            const int t = 2 * u + eset;
             int64_t qi = qbase + int64_t(t) * TC_M + row;
             if (qi > p.N - 1) qi = p.N - 1;
             const float x = __ldg(qsrc + 3 * qi), y = __ldg(qsrc + 3 * qi + 1), z = __ldg(qsrc + 3 * qi + 2);
             const float n = __fmaf_rn(z, z, __fmaf_rn(y, y, __fmul_rn(x, x)));
             const float sc = fmaxf(n, ymax);
-            float *st = state + (t * 2 + half) * TC_M + row;
-            st[0 * SW] = CUDART_INF_F;
-            st[1 * SW] = __int_as_float(0);
-            st[2 * SW] = x;
-            st[3 * SW] = y;
-            st[4 * SW] = z;
+            qx[u] = x;
+            qy[u] = y;
+            qz[u] = z;
             // non-finite scale: the filter cannot be trusted for this row -> always re-check (bound = +inf)
-            st[5 * SW] = (tf32r(sc) < CUDART_INF_F) ? __fmul_rn(sc, p.escale) : CUDART_INF_F;
-            if (half == 0) {
-                float k[16];
-                float h, m, l;
-                k[0] = k[1] = tf32r(x);
-                k[2] = tf32r(x - k[0]);
-                k[3] = k[4] = tf32r(y);
-                k[5] = tf32r(y - k[3]);
-                k[6] = k[7] = tf32r(z);
-                k[8] = tf32r(z - k[6]);
-                split3(n, h, m, l);
-                k[9] = h;
-                k[10] = m;
-                k[11] = 1.f;
-                k[12] = 1.f;
-                k[13] = l;
-                k[14] = 1.f;
-                k[15] = 0.f;
-                if (!(h < CUDART_INF_F)) {  // keep inf/NaN out of the tensor cores; this row re-checks everything
+            qe[u] = (tf32r(sc) < CUDART_INF_F) ? __fmul_rn(sc, p.escale) : CUDART_INF_F;
+            bd[u] = CUDART_INF_F;
+            bj[u] = 0;
+            float k[16];
+            float h, m, l;
+            k[0] = k[1] = tf32r(x);
+            k[2] = tf32r(x - k[0]);
+            k[3] = k[4] = tf32r(y);
+            k[5] = tf32r(y - k[3]);
+            k[6] = k[7] = tf32r(z);
+            k[8] = tf32r(z - k[6]);
+            split3(n, h, m, l);
+            k[9] = h;
+            k[10] = m;
+            k[11] = 1.f;
+            k[12] = 1.f;
+            k[13] = l;
+            k[14] = 1.f;
+            k[15] = 0.f;
+            if (!(h < CUDART_INF_F)) {  // keep inf/NaN out of the tensor cores; this row re-checks everything
 #pragma unroll
-                    for (int i = 0; i < 16; ++i) k[i] = 0.f;
-                }
-                store_row16(aop + size_t(t) * TC_AOP_BYTES, TC_M, row, k);
+                for (int i = 0; i < 16; ++i) k[i] = 0.f;
             }
+            store_row16(aop + size_t(t) * TC_AOP_BYTES, TC_M, row, k);
         }
         fence_proxy_async();
     }
@@ -313,38 +375,49 @@ __global__ void __launch_bounds__(TC_THREADS, 1) nn_tc_kernel(const NNTCParams p
             if (lane == 0) mbar_arrive(&bop_full[s]);
         }
     } else if (warp == 3) {
-        // ---------------- MMA issuer ----------------
-        if (lane == 0) {
-            constexpr uint32_t idesc = umma_idesc_tf32_mn(TC_M, TC_N);
-            const uint32_t aop_u32 = smem_u32(aop);
-            int seq = 0;
-            for (int k = 0; k < ntiles; ++k) {
-                const int s = k % TC_STAGES;
-                const uint32_t ph = (k / TC_STAGES) & 1;
-                mbar_wait(&bop_full[s], ph);
-                tcx_fence_after();
-                const uint32_t bop_u32 = smem_u32(stages + size_t(s) * TC_STAGE_BYTES + TC_PLANE_BYTES);
-                const uint64_t db0 = umma_desc_plain(bop_u32, TC_N * 16, 128);
-                const uint64_t db1 = umma_desc_plain(bop_u32 + 2 * TC_N * 16, TC_N * 16, 128);
+        // ---------------- MMA issuer (whole warp converged; one elected lane issues) ----------------
+        constexpr uint32_t idesc = umma_idesc_tf32_mn(TC_M, NS);
+        const uint32_t aop_u32 = smem_u32(aop);
+        uint64_t da0[TC_QT], da1[TC_QT];
+#pragma unroll
+        for (int t = 0; t < TC_QT; ++t) {
+            da0[t] = umma_desc_plain(aop_u32 + uint32_t(t) * TC_AOP_BYTES, TC_M * 16, 128);
+            da1[t] = umma_desc_plain(aop_u32 + uint32_t(t) * TC_AOP_BYTES + 2 * TC_M * 16, TC_M * 16, 128);
+        }
+        uint32_t seq = 0;
+        for (int k = 0; k < ntiles; ++k) {
+            const int s = k % TC_STAGES;
+            const uint32_t ph = (k / TC_STAGES) & 1;
+            mbar_wait(&bop_full[s], ph);
+            tcx_fence_after();
+            const uint32_t bop_u32 = smem_u32(stages + size_t(s) * TC_STAGE_BYTES + TC_PLANE_BYTES);
 #pragma unroll 1
+            for (int sub = 0; sub < NSUB; ++sub) {
+                // rows [sub*NS, +NS) of the stage operand: NS/8 core-matrix groups of 128 bytes further on
+                const uint32_t b_u32 = bop_u32 + uint32_t(sub) * (NS / 8) * 128;
+                const uint64_t db0 = umma_desc_plain(b_u32, TC_N * 16, 128);
+                const uint64_t db1 = umma_desc_plain(b_u32 + 2 * TC_N * 16, TC_N * 16, 128);
+#pragma unroll
                 for (int t = 0; t < TC_QT; ++t, ++seq) {
-                    const int buf = seq & 1;
-                    mbar_wait(&acc_empty[buf], ((seq >> 1) & 1) ^ 1);
+                    const uint32_t buf = seq % NBUF;
+                    mbar_wait(&acc_empty[buf], ((seq / NBUF) & 1) ^ 1);
                     tcx_fence_after();
-                    const uint32_t a_u32 = aop_u32 + uint32_t(t) * TC_AOP_BYTES;
-                    const uint64_t da0 = umma_desc_plain(a_u32, TC_M * 16, 128);
-                    const uint64_t da1 = umma_desc_plain(a_u32 + 2 * TC_M * 16, TC_M * 16, 128);
-                    const uint32_t d = tmem_base + uint32_t(buf * TC_N);
-                    tcx_mma_tf32(d, da0, db0, idesc, 0);
-                    tcx_mma_tf32(d, da1, db1, idesc, 1);
-                    tcx_commit(&acc_full[buf]);
+                    if (p.dbg && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && seq < 256 && lane == 0)
+                        p.dbg[seq] = clock64();
+                    if (elect_one()) {
+                        const uint32_t d = tmem_base + buf * NS;
+                        tcx_mma_tf32(d, da0[t], db0, idesc, 0);
+                        tcx_mma_tf32(d, da1[t], db1, idesc, 1);
+                        tcx_commit(&acc_full[buf]);
+                    }
+                    __syncwarp();
                 }
             }
         }
     } else {
         // ---------------- epilogue: filter + exact re-check ----------------
-        int seq = 0;
         const int jmax = int(r1);
+        const uint32_t tlane = tmem_base + (uint32_t(quarter * 32) << 16);
         for (int k = 0; k < ntiles; ++k) {
             const int s = k % TC_STAGES;
             const uint32_t ph = (k / TC_STAGES) & 1;
@@ -353,55 +426,45 @@ __global__ void __launch_bounds__(TC_THREADS, 1) nn_tc_kernel(const NNTCParams p
             const float *py = px + TC_N, *pz = py + TC_N;
             const int jt0 = int(r0) + k * TC_N;
 #pragma unroll 1
-            for (int t = 0; t < TC_QT; ++t, ++seq) {
-                float *st = state + (t * 2 + half) * TC_M + row;
-                float bd = st[0];
-                int bj = __float_as_int(st[SW]);
-                const float qx = st[2 * SW], qy = st[3 * SW], qz = st[4 * SW], qe = st[5 * SW];
-                const float bd_in = bd;
-                const int buf = seq & 1;
-                mbar_wait(&acc_full[buf], (seq >> 1) & 1);
-                tcx_fence_after();
-                const uint32_t taddr0 =
-                    tmem_base + (uint32_t(quarter * 32) << 16) + uint32_t(buf * TC_N + half * (TC_N / 2));
+            for (int sub = 0; sub < NSUB; ++sub) {
+#pragma unroll
+                for (int u = 0; u < TPS; ++u) {
+                    const uint32_t seq = uint32_t((k * NSUB + sub) * TC_QT + 2 * u + eset);
+                    const uint32_t buf = seq % NBUF;
+                    const bool stamp = p.dbg && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && seq < 256 &&
+                                       quarter == 0 && lane == 0;
+                    if (stamp) p.dbg[256 + seq] = clock64();
+                    mbar_wait(&acc_full[buf], (seq / NBUF) & 1);
+                    if (stamp) p.dbg[512 + seq] = clock64();
+                    tcx_fence_after();
+                    const uint32_t taddr0 = tlane + buf * NS;
+                    const int c0 = sub * NS;
+                    uint32_t va[32], vb[32];
+                    tcx_ld32_issue(taddr0, va);
 #pragma unroll 1
-                for (int g = 0; g < TC_N / 2 / 32; ++g) {
-                    float v[32];
-                    tcx_ld32(taddr0 + uint32_t(g * 32), v);
-                    float pm[8];
-#pragma unroll
-                    for (int c = 0; c < 8; ++c) pm[c] = fminf(fmin3(v[4 * c], v[4 * c + 1], v[4 * c + 2]), v[4 * c + 3]);
-                    float m = fmin3(pm[0], pm[1], pm[2]);
-                    m = fmin3(m, pm[3], pm[4]);
-                    m = fmin3(m, pm[5], pm[6]);
-                    m = fminf(m, pm[7]);
-                    float thresh = bd + qe;
-                    if (!(m > thresh)) {  // rare for long scans: some column may beat the best exact distance
-                        const int col0 = half * (TC_N / 2) + g * 32;
-#pragma unroll
-                        for (int c = 0; c < 8; ++c) {
-                            if (!(pm[c] > thresh)) {
-#pragma unroll
-                                for (int i = 0; i < 4; ++i) {
-                                    if (!(v[4 * c + i] > thresh)) {
-                                        tc_eval(px, py, pz, col0 + 4 * c + i, jt0 + col0 + 4 * c + i, jmax, qx, qy, qz, bd, bj);
-                                        thresh = bd + qe;
-                                    }
-                                }
-                            }
-                        }
+                    for (int g = 0; g < NS / 32; g += 2) {  // software-pipelined: the next load flies during the min tree
+                        tcx_ld32_issue(taddr0 + uint32_t((g + 1) * 32), vb);
+                        tcx_ld32_wait(va);  // (waits for both outstanding loads; vb is fenced again below)
+                        tc_group(va, px, py, pz, c0 + g * 32, jt0 + c0 + g * 32, jmax, qx[u], qy[u], qz[u], qe[u], bd[u], bj[u]);
+                        tcx_ld32_wait(vb);
+                        if (g + 2 < NS / 32) tcx_ld32_issue(taddr0 + uint32_t((g + 2) * 32), va);
+                        tc_group(vb, px, py, pz, c0 + (g + 1) * 32, jt0 + c0 + (g + 1) * 32, jmax, qx[u], qy[u], qz[u], qe[u],
+                                 bd[u], bj[u]);
                     }
-                }
-                tcx_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&acc_empty[buf]);
-                if (bd < bd_in) {
-                    st[0] = bd;
-                    st[SW] = __int_as_float(bj);
+                    tcx_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&acc_empty[buf]);
+                    if (stamp) p.dbg[768 + seq] = clock64();
                 }
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(&stage_empty[s]);
+        }
+#pragma unroll
+        for (int u = 0; u < TPS; ++u) {
+            const int t = 2 * u + eset;
+            state[t * TC_M + row] = bd[u];
+            state[(TC_QT + t) * TC_M + row] = __int_as_float(bj[u]);
         }
     }
     tcx_fence_before();
@@ -410,19 +473,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) nn_tc_kernel(const NNTCParams p
         tcx_fence_after();
         tcx_dealloc(tmem_base, 512);
     }
-    if (is_epi && half == 0) {
+    if (is_epi && eset == 0) {
         for (int t = 0; t < TC_QT; ++t) {
             const int64_t qi = qbase + int64_t(t) * TC_M + row;
             if (qi >= p.N) continue;
-            const float *s0 = state + (t * 2 + 0) * TC_M + row, *s1 = state + (t * 2 + 1) * TC_M + row;
-            float d = s0[0];
-            int j = __float_as_int(s0[SW]);
-            const float d1 = s1[0];
-            const int j1 = __float_as_int(s1[SW]);
-            if (d1 < d || (d1 == d && d1 < CUDART_INF_F && j1 < j)) {  // column halves: lexicographic (d, j)
-                d = d1;
-                j = j1;
-            }
+            const float d = state[t * TC_M + row];
+            const int j = __float_as_int(state[(TC_QT + t) * TC_M + row]);
             const int64_t gi = p.idx_base + j;
             const int64_t o = b * p.N + qi;
             if (p.keys) {
@@ -462,7 +518,21 @@ __global__ void nn_tc_ymax_kernel(const float *__restrict__ planes, int64_t M, i
 // ---------------------------------------------------------------------------------------------
 size_t nn_tc_workspace_bytes(int64_t cand_batches) { return align_up(size_t(cand_batches) * sizeof(float), 256); }
 
+void nn_tc_set_debug(long long *dbg) { g_tc_dbg = dbg; }
 void nn_tc_set_eshift(int e) { g_tc_eshift = (e >= 8 && e <= 30) ? e : 15; }
+void nn_tc_set_subtile(int ns) { g_tc_ns = (ns == 64 || ns == 128 || ns == 256) ? ns : 128; }
+
+template <int NS>
+static cudaError_t nn_tc_dispatch(const NNTCParams &p, dim3 grid, cudaStream_t st) {
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(nn_tc_kernel<NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(TC_SMEM));
+        if (e != cudaSuccess) return e;
+        configured = true;
+    }
+    nn_tc_kernel<NS><<<grid, TC_THREADS, TC_SMEM, st>>>(p);
+    return cudaGetLastError();
+}
 
 void nn_tc_plan(int64_t eb, int64_t eN, int64_t M, int nsplit_hint, int *nsplit, int64_t *chunk) {
     const int64_t qblocks = ceil_div(eN, int64_t(TC_QT) * TC_M);
@@ -484,11 +554,6 @@ int nn_tc_launch(const float *queries, int64_t q_bstride, int64_t eb, int64_t eN
                  int64_t plane_bstride, int64_t cand_batches, int64_t Mp, int64_t M, int64_t idx_base, float *dist,
                  void *idx, int idx_bytes, unsigned long long *keys, int keys_atomic, int nsplit, int64_t chunk,
                  float *ymax_ws, cudaStream_t st) {
-    static bool configured = false;
-    if (!configured) {
-        FPV_CUDA(cudaFuncSetAttribute(nn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(TC_SMEM)));
-        configured = true;
-    }
     FPV_CUDA(cudaMemsetAsync(ymax_ws, 0, size_t(cand_batches) * sizeof(float), st));
     {
         int nb = int(ceil_div(M, 256 * 8));
@@ -515,10 +580,12 @@ int nn_tc_launch(const float *queries, int64_t q_bstride, int64_t eb, int64_t eN
     p.idx_bytes = idx_bytes;
     p.keys = keys;
     p.keys_atomic = keys_atomic;
+    p.dbg = g_tc_dbg;
     dim3 grid((unsigned)ceil_div(eN, int64_t(TC_QT) * TC_M), (unsigned)nsplit, (unsigned)eb);
-    nn_tc_kernel<<<grid, TC_THREADS, TC_SMEM, st>>>(p);
+    cudaError_t e = g_tc_ns == 256 ? nn_tc_dispatch<256>(p, grid, st)
+                    : g_tc_ns == 128 ? nn_tc_dispatch<128>(p, grid, st)
+                                     : nn_tc_dispatch<64>(p, grid, st);
     count_launch();
-    cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) {
         set_error("nn_tc_kernel launch failed: %s", cudaGetErrorString(e));
         return FPV_ERR_CUDA;

@@ -77,6 +77,8 @@ int fpv_nn_set_tuning(int qpt, int nsplit, int packed);
  * FP32 re-check (nn_tc_kernel).  Both return bit-identical results.  tc_eshift > 0 overrides the filter's
  * error-bound exponent (default 15); used by the tests to demonstrate the safety margin. */
 int fpv_nn_set_engine(int engine, int tc_eshift);
+/* Debug: device buffer of 1024 int64 receiving a clock64 pipeline timeline of CTA 0 of nn_tc_kernel (NULL = off). */
+int fpv_nn_tc_debug(long long *dbg);
 
 /* distChamfer(a, b) forward, reference output order (chamfer_python.py:28):
  *   d_b2a [bs,M], d_a2b [bs,N], i_b2a [bs,M] (index into a), i_a2b [bs,N] (index into b).

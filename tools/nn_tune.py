@@ -1,5 +1,5 @@
-"""Times the NN search kernel variants on the two config-2 directions (run on the GPU box)."""
-import importlib, sys, os, time
+"""Times the NN search engines on the two config-2 directions (run on the GPU box)."""
+import importlib, sys, os
 import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 fpv = importlib.import_module("4dcapture-fpv_b200")
@@ -18,12 +18,16 @@ def timeit(fn, reps=3):
     return best
 
 def bench(label, queries, planes, M, ref_batches, pairs):
-    for qpt, nps in ((4, (0, 1, 2, 3, 4)), (8, (0, 2, 4, 6, 8))):
-        for npk in nps:
-            L.fpv_nn_set_tuning(qpt, 0, npk)
-            ms = timeit(lambda: fpv.nn_search(queries, planes, M, ref_batches=ref_batches))
-            print(f"{label:28s} qpt={qpt} packed={npk}: {ms:9.3f} ms  {pairs / ms / 1e9:7.3f} Tpair/s", flush=True)
-    L.fpv_nn_set_tuning(0, 0, -1)
+    res = {}
+    for eng, name, arg in ((1, "simt", 0), (2, "tc64", 64 << 8), (2, "tc128", 128 << 8), (2, "tc256", 256 << 8)):
+        L.fpv_nn_set_engine(eng, arg)
+        out = fpv.nn_search(queries, planes, M, ref_batches=ref_batches)
+        res[name] = [o.clone() for o in out]
+        ms = timeit(lambda: fpv.nn_search(queries, planes, M, ref_batches=ref_batches))
+        print(f"{label:30s} engine={name:6s}: {ms:9.3f} ms  {pairs / ms / 1e9:7.3f} Tpair/s", flush=True)
+    same = all(torch.equal(a, b) for k in ("tc64", "tc128", "tc256") for a, b in zip(res["simt"], res[k]))
+    print(f"{label:30s} tc == simt bitwise: {same}", flush=True)
+    L.fpv_nn_set_engine(0, 0)
 
 T = int(sys.argv[1]) if len(sys.argv) > 1 else 60
 M = 1_000_000
@@ -34,7 +38,8 @@ pl_body = fpv.pack_planes(body)
 bench("body->scene (shared refs)", body, pl_scene, M, 1, T * V * M)
 qs = scene.unsqueeze(0).expand(T, -1, -1).contiguous()
 bench("scene->body (per-frame refs)", qs, pl_body, V, T, T * M * V)
-# sorted scene order (Morton-like: sort by x then y buckets) to see the slow-path sensitivity to candidate order
-order = torch.argsort(body[..., 2], dim=1)
-body_sorted = torch.gather(body, 1, order.unsqueeze(-1).expand(-1, -1, 3)).contiguous()
-bench("scene->body, z-sorted body", qs, fpv.pack_planes(body_sorted), V, T, T * M * V)
+# spatially sorted scene (x-major buckets): coherent query rows per warp -> fewer divergent re-checks
+key = (torch.floor((scene[:, 0] + 4) * 4) * 64 * 64 + torch.floor((scene[:, 1] + 4) * 4) * 64 + torch.floor(scene[:, 2] * 4)).long()
+ss = scene[torch.argsort(key)]
+qs2 = ss.unsqueeze(0).expand(T, -1, -1).contiguous()
+bench("scene->body, cell-sorted scene", qs2, pl_body, V, T, T * M * V)
