@@ -16,7 +16,50 @@ from __future__ import annotations
 
 import torch
 
-from . import _lib
+from . import _lib, spatial
+
+# Search strategy of distChamfer when `b` is one cloud shared by every batch (the scene):
+#   "auto"    spatially indexed exact search (nn_culled.cu) for scenes of >= SPATIAL_MIN_POINTS points,
+#             brute force (SIMT / tensor-core filter, chosen inside the library) otherwise
+#   "brute"   always the brute-force kernels          "spatial"  always the indexed search
+# Every strategy returns bit-identical results.
+ENGINE = "auto"
+SPATIAL_MIN_POINTS = 4096
+LAST_STATS = {}
+
+
+def _forward_spatial(a_c: torch.Tensor, b_c: torch.Tensor, idx_dtype):
+    """Both chamfer directions with the scene held in Morton order.  a_c [T,N,3], b_c [1,M,3].
+
+    a -> b (body vertex -> scene): the scene is static, so the box-culled tile search visits ~1 % of it.
+    b -> a (scene point -> body): far-field queries defeat box culling (SURVEY/DESIGN section 6), so this
+    direction stays brute force -- but its queries are issued in the scene's Morton order, which makes the rows of
+    a warp spatial neighbours: their running minima improve on the same candidate tiles and the tensor-core
+    filter's divergent exact re-checks collapse (profiles/r01_nn_tune6_tc_vs_simt.txt).
+    """
+    T, N, _ = a_c.shape
+    M = b_c.shape[1]
+    dev = a_c.device
+    L = _lib.lib()
+    scene = spatial.cached_scene(b_c)                                   # built once per scene tensor
+    body = spatial.SortedCloud(a_c, scene.lo, scene.inv_cell)           # per-step [T,N] Morton argsort
+    stats = torch.zeros(1, dtype=torch.int64, device=dev)
+    d_s, i_s = spatial.culled_search(body.sorted, False, T, scene, idx_dtype, stats=stats)
+    d_a2b = torch.empty_like(d_s).scatter_(1, body.perm, d_s)
+    i_a2b = torch.empty_like(i_s).scatter_(1, body.perm, i_s)
+    planes_a = pack_planes(a_c)                                         # candidates in ORIGINAL order: native tie-break
+    d_s2 = torch.empty(T, M, dtype=torch.float32, device=dev)
+    i_s2 = torch.empty(T, M, dtype=idx_dtype, device=dev)
+    with torch.cuda.device(dev):
+        ws = _lib.workspace(L.fpv_nn_search_workspace_bytes(T, M, N), dev)
+        _lib.check(L.fpv_nn_search(_lib.ptr(scene.sorted), 1, T, M, _lib.ptr(planes_a), T, N, 0, _lib.ptr(d_s2),
+                                   _lib.ptr(i_s2), 8 if idx_dtype == torch.int64 else 4, None, _lib.ptr(ws),
+                                   ws.numel(), _lib.stream_ptr()), "fpv_nn_search")
+    inv = scene.inv_perm[0]
+    d_b2a = d_s2.index_select(1, inv)
+    i_b2a = i_s2.index_select(1, inv)
+    LAST_STATS["tiles_searched"] = stats
+    return d_b2a, d_a2b, i_b2a, i_a2b
 
 
 def _prep(a: torch.Tensor, b: torch.Tensor):
@@ -59,13 +102,17 @@ class _ChamferFn(torch.autograd.Function):
         i_b2a = torch.empty(bs, M, dtype=idx_dtype, device=dev)
         i_a2b = torch.empty(bs, N, dtype=idx_dtype, device=dev)
         idx_bytes = 8 if idx_dtype == torch.int64 else 4
-        with torch.cuda.device(dev):
-            nbytes = L.fpv_chamfer_fwd_workspace_bytes(bs, N, M, int(shared))
-            ws = _lib.workspace(nbytes, dev)
-            _lib.check(L.fpv_chamfer_fwd(_lib.ptr(a_c), _lib.ptr(b_c), bs, N, M, int(shared),
-                                         _lib.ptr(d_b2a), _lib.ptr(d_a2b), _lib.ptr(i_b2a), _lib.ptr(i_a2b),
-                                         idx_bytes, _lib.ptr(ws), ws.numel(), _lib.stream_ptr()),
-                       "fpv_chamfer_fwd")
+        use_spatial = shared and (ENGINE == "spatial" or (ENGINE == "auto" and M >= SPATIAL_MIN_POINTS))
+        if use_spatial:
+            d_b2a, d_a2b, i_b2a, i_a2b = _forward_spatial(a_c, b_c, idx_dtype)
+        else:
+            with torch.cuda.device(dev):
+                nbytes = L.fpv_chamfer_fwd_workspace_bytes(bs, N, M, int(shared))
+                ws = _lib.workspace(nbytes, dev)
+                _lib.check(L.fpv_chamfer_fwd(_lib.ptr(a_c), _lib.ptr(b_c), bs, N, M, int(shared),
+                                             _lib.ptr(d_b2a), _lib.ptr(d_a2b), _lib.ptr(i_b2a), _lib.ptr(i_a2b),
+                                             idx_bytes, _lib.ptr(ws), ws.numel(), _lib.stream_ptr()),
+                           "fpv_chamfer_fwd")
         ctx.save_for_backward(a_c, b_c, i_b2a, i_a2b)
         ctx.shared = shared
         ctx.idx_bytes = idx_bytes

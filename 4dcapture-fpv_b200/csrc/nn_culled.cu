@@ -1,0 +1,383 @@
+// nn_culled.cu -- exact nearest neighbour over a spatially tiled candidate cloud with box culling.  sm_100a.
+//
+// SURVEY.md section 7 step 5 ("the exact uniform-grid/cell-sorted variant ... the only way to approach an
+// HBM-type roofline"): brute force evaluates Q*M pairs; here the candidate cloud is pre-sorted along a
+// Morton curve (the scene is static across all optimiser steps, global_optimization.py:175) and cut into
+// tiles of 64 consecutive points with their axis-aligned bounding boxes.  Queries arrive in compact groups
+// of 128 (also Morton-sorted by the caller).  One warp owns one group:
+//   1. it computes the group's bounding box and, 32 tiles at a time, the box-to-box lower bound of the
+//      squared distance to every tile; the tile with the smallest bound is searched first (seed);
+//   2. it sweeps all tiles again and searches only those whose lower bound does not exceed the group's
+//      current worst best-distance (re-evaluated after every searched tile).
+// Inside a tile the arithmetic is the canonical fp32 expression of nn_search.cu, bit for bit.  Because
+// tiles are visited out of index order, the winner is chosen by the full lexicographic rule
+// (distance, ORIGINAL index): ties still resolve to the lowest original index, and a culled tile can
+// never hold a winner because its lower bound (deflated by 2^-18 against fp32 rounding) exceeds every
+// best distance of the group -- the result is identical to brute force.
+#include <math_constants.h>
+
+#include "common.cuh"
+
+namespace fpv {
+
+constexpr int CU_TILE = 64;     // candidates per tile
+constexpr int CU_QPT = 4;       // queries per lane -> 128 queries per warp (group)
+constexpr int CU_GROUP = 32 * CU_QPT;
+constexpr int CU_WARPS = 4;     // groups per CTA
+
+struct CulledParams {
+    const float *q;       // [batches or 1][N][3] (grouped: 128 consecutive queries are spatially compact)
+    int64_t q_bstride;    // floats between batches (0 = shared)
+    int64_t N;
+    const float *planes;  // [cand batches][3][Mp] Morton-sorted candidates (pad = +inf)
+    int64_t plane_bstride, Mp, M;
+    const float *boxes;   // [cand batches][ntile + nsuper][6]  xmin ymin zmin xmax ymax zmax; a super box
+    int64_t box_bstride;  //   covers 32 consecutive tiles and follows the tile boxes
+    const int *oidx;      // [cand batches][M] original index of every sorted candidate
+    int64_t oidx_bstride;
+    int ntile, nsuper;
+    int64_t idx_base;
+    float *dist;
+    void *idx;
+    int idx_bytes;
+    unsigned long long *tiles_searched;  // optional statistics counter
+};
+
+__device__ __forceinline__ float cu_d2(float x, float y, float z, float rx, float ry, float rz) {
+    const float dx = __fsub_rn(x, rx), dy = __fsub_rn(y, ry), dz = __fsub_rn(z, rz);
+    return __fmaf_rn(dz, dz, __fmaf_rn(dy, dy, __fmul_rn(dx, dx)));
+}
+
+__device__ __forceinline__ float warp_min(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fminf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+// squared box-to-box gap, deflated so that fp32 rounding can never make it exceed a true pair distance
+__device__ __forceinline__ float box_lb(const float *__restrict__ b, const float (&gmin)[3], const float (&gmax)[3]) {
+    float s = 0.f;
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        const float g = fmaxf(0.f, fmaxf(b[a] - gmax[a], gmin[a] - b[3 + a]));
+        s = fmaf(g, g, s);
+    }
+    return s * (1.0f - 1.0f / 262144.0f);
+}
+
+// Search one tile (64 candidates staged in this warp's shared buffer) for the warp's 128 queries.
+__device__ __forceinline__ void cu_search_tile(const float *sx, const float *sy, const float *sz,
+                                               const int *__restrict__ oidx_tile, const float (&qx)[CU_QPT],
+                                               const float (&qy)[CU_QPT], const float (&qz)[CU_QPT],
+                                               float (&best)[CU_QPT], int (&bidx)[CU_QPT]) {
+    const float4 *X = reinterpret_cast<const float4 *>(sx);
+    const float4 *Y = reinterpret_cast<const float4 *>(sy);
+    const float4 *Z = reinterpret_cast<const float4 *>(sz);
+#pragma unroll 2
+    for (int j4 = 0; j4 < CU_TILE / 4; ++j4) {
+        const float4 rx = X[j4], ry = Y[j4], rz = Z[j4];
+        const float2 nx0 = make_float2(-rx.x, -rx.y), nx1 = make_float2(-rx.z, -rx.w);
+        const float2 ny0 = make_float2(-ry.x, -ry.y), ny1 = make_float2(-ry.z, -ry.w);
+        const float2 nz0 = make_float2(-rz.x, -rz.y), nz1 = make_float2(-rz.z, -rz.w);
+        float m4[CU_QPT];
+        bool any = false;
+#pragma unroll
+        for (int q = 0; q < CU_QPT; ++q) {
+            const float2 bx = make_float2(qx[q], qx[q]), by = make_float2(qy[q], qy[q]), bz = make_float2(qz[q], qz[q]);
+            const float2 dx0 = __fadd2_rn(bx, nx0), dx1 = __fadd2_rn(bx, nx1);
+            const float2 dy0 = __fadd2_rn(by, ny0), dy1 = __fadd2_rn(by, ny1);
+            const float2 dz0 = __fadd2_rn(bz, nz0), dz1 = __fadd2_rn(bz, nz1);
+            float2 s0 = __fmul2_rn(dx0, dx0), s1 = __fmul2_rn(dx1, dx1);
+            s0 = __ffma2_rn(dy0, dy0, s0);
+            s1 = __ffma2_rn(dy1, dy1, s1);
+            s0 = __ffma2_rn(dz0, dz0, s0);
+            s1 = __ffma2_rn(dz1, dz1, s1);
+            m4[q] = fminf(fmin3(s0.x, s0.y, s1.x), s1.y);
+            any |= (m4[q] <= best[q]);  // '<=': an equal distance with a lower original index must win
+        }
+        if (any) {
+#pragma unroll
+            for (int q = 0; q < CU_QPT; ++q) {
+                if (m4[q] <= best[q]) {
+                    const float e[4] = {cu_d2(qx[q], qy[q], qz[q], rx.x, ry.x, rz.x), cu_d2(qx[q], qy[q], qz[q], rx.y, ry.y, rz.y),
+                                        cu_d2(qx[q], qy[q], qz[q], rx.z, ry.z, rz.z), cu_d2(qx[q], qy[q], qz[q], rx.w, ry.w, rz.w)};
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+                        if (e[c] <= best[q]) {
+                            const int o = __ldg(oidx_tile + 4 * j4 + c);
+                            if (e[c] < best[q] || o < bidx[q]) {
+                                best[q] = e[c];
+                                bidx[q] = o;
+                            }
+                        }
+                    }
+                }
+            }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(CU_WARPS * 32) nn_culled_kernel(const CulledParams p) {
+    __shared__ __align__(16) float stile[CU_WARPS][3][CU_TILE];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t b = blockIdx.y;
+    const int64_t group = int64_t(blockIdx.x) * CU_WARPS + warp;
+    const int64_t q0 = group * CU_GROUP;
+    if (q0 >= p.N) return;  // whole warp leaves together
+    const float *qsrc = p.q + b * p.q_bstride;
+    const float *planes = p.planes + b * p.plane_bstride;
+    const float *boxes = p.boxes + b * p.box_bstride;
+    const int *oidx = p.oidx + b * p.oidx_bstride;
+    float *sx = stile[warp][0], *sy = stile[warp][1], *sz = stile[warp][2];
+
+    float qx[CU_QPT], qy[CU_QPT], qz[CU_QPT], best[CU_QPT];
+    int bidx[CU_QPT];
+    float gmin[3] = {CUDART_INF_F, CUDART_INF_F, CUDART_INF_F}, gmax[3] = {-CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F};
+#pragma unroll
+    for (int k = 0; k < CU_QPT; ++k) {
+        int64_t qi = q0 + k * 32 + lane;
+        if (qi > p.N - 1) qi = p.N - 1;
+        qx[k] = __ldg(qsrc + 3 * qi);
+        qy[k] = __ldg(qsrc + 3 * qi + 1);
+        qz[k] = __ldg(qsrc + 3 * qi + 2);
+        best[k] = CUDART_INF_F;
+        bidx[k] = 0;
+        gmin[0] = fminf(gmin[0], qx[k]); gmax[0] = fmaxf(gmax[0], qx[k]);
+        gmin[1] = fminf(gmin[1], qy[k]); gmax[1] = fmaxf(gmax[1], qy[k]);
+        gmin[2] = fminf(gmin[2], qz[k]); gmax[2] = fmaxf(gmax[2], qz[k]);
+    }
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        gmin[a] = warp_min(gmin[a]);
+        gmax[a] = warp_max(gmax[a]);
+    }
+    // a NaN query coordinate poisons the box: fminf/fmaxf drop NaNs, so the box only covers the finite
+    // queries; a NaN query never wins anything anyway (all its distances are NaN) -> result (+inf, 0).
+
+    auto stage_and_search = [&](int t) {
+        const int64_t j0 = int64_t(t) * CU_TILE;
+        __syncwarp();
+        sx[lane] = planes[j0 + lane];
+        sx[lane + 32] = planes[j0 + 32 + lane];
+        sy[lane] = planes[p.Mp + j0 + lane];
+        sy[lane + 32] = planes[p.Mp + j0 + 32 + lane];
+        sz[lane] = planes[2 * p.Mp + j0 + lane];
+        sz[lane + 32] = planes[2 * p.Mp + j0 + 32 + lane];
+        __syncwarp();
+        cu_search_tile(sx, sy, sz, oidx + j0, qx, qy, qz, best, bidx);
+    };
+    auto group_worst = [&]() {
+        float w = fmaxf(fmaxf(best[0], best[1]), fmaxf(best[2], best[3]));
+        return warp_max(w);
+    };
+
+    const float *sboxes = boxes + int64_t(p.ntile) * 6;
+    // ---- phase A: seed = the tile with the smallest lower bound inside the super-tile with the smallest ----
+    int seed;
+    {
+        float lmin = CUDART_INF_F;
+        int smin = 0;
+        for (int s0 = 0; s0 < p.nsuper; s0 += 32) {
+            const int sidx = s0 + lane;
+            if (sidx < p.nsuper) {
+                const float lb = box_lb(sboxes + int64_t(sidx) * 6, gmin, gmax);
+                if (lb < lmin) {
+                    lmin = lb;
+                    smin = sidx;
+                }
+            }
+        }
+        float wmin = warp_min(lmin);
+        unsigned m = __ballot_sync(0xffffffffu, lmin == wmin);
+        smin = __shfl_sync(0xffffffffu, smin, m ? __ffs(m) - 1 : 0);
+        const int t = smin * 32 + lane;
+        const float lb = (t < p.ntile) ? box_lb(boxes + int64_t(t) * 6, gmin, gmax) : CUDART_INF_F;
+        wmin = warp_min(lb);
+        m = __ballot_sync(0xffffffffu, lb == wmin);
+        seed = smin * 32 + (m ? __ffs(m) - 1 : 0);
+        if (seed >= p.ntile) seed = 0;
+    }
+    stage_and_search(seed);
+    float worst = group_worst();
+    unsigned long long searched = 1;
+
+    // ---- phase B: two-level sweep, searching only tiles that can still hold a winner ----
+    for (int s0 = 0; s0 < p.nsuper; s0 += 32) {
+        const int sidx = s0 + lane;
+        float slb = CUDART_INF_F;
+        if (sidx < p.nsuper) slb = box_lb(sboxes + int64_t(sidx) * 6, gmin, gmax);
+        unsigned smask = __ballot_sync(0xffffffffu, slb <= worst);
+        while (smask) {
+            const int sl = __ffs(smask) - 1;
+            smask &= smask - 1;
+            if (!(__shfl_sync(0xffffffffu, slb, sl) <= worst)) continue;
+            const int t0 = (s0 + sl) * 32;
+            const int t = t0 + lane;
+            float lb = CUDART_INF_F;
+            if (t < p.ntile && t != seed) lb = box_lb(boxes + int64_t(t) * 6, gmin, gmax);
+            unsigned mask = __ballot_sync(0xffffffffu, lb <= worst);
+            while (mask) {
+                const int l = __ffs(mask) - 1;
+                mask &= mask - 1;
+                if (__shfl_sync(0xffffffffu, lb, l) <= worst) {  // the group's worst distance may have shrunk
+                    stage_and_search(t0 + l);
+                    worst = group_worst();
+                    ++searched;
+                }
+            }
+        }
+    }
+    if (p.tiles_searched && lane == 0) atomicAdd(p.tiles_searched, searched);
+
+#pragma unroll
+    for (int k = 0; k < CU_QPT; ++k) {
+        const int64_t qi = q0 + k * 32 + lane;
+        if (qi < p.N) {
+            const int64_t o = b * p.N + qi;
+            const int64_t gi = p.idx_base + bidx[k];
+            p.dist[o] = best[k];
+            if (p.idx_bytes == 8)
+                static_cast<long long *>(p.idx)[o] = gi;
+            else
+                static_cast<int *>(p.idx)[o] = int(gi);
+        }
+    }
+}
+
+// Per-tile bounding boxes of Morton-sorted candidate planes (pad entries are +inf and are skipped).
+__global__ void tile_boxes_kernel(const float *__restrict__ planes, int64_t M, int64_t Mp, int ntile,
+                                  float *__restrict__ boxes) {
+    const int64_t b = blockIdx.y;
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= ntile) return;
+    const float *P = planes + b * 3 * Mp;
+    float lo[3] = {CUDART_INF_F, CUDART_INF_F, CUDART_INF_F}, hi[3] = {-CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F};
+    for (int c = 0; c < CU_TILE; ++c) {
+        const int64_t j = int64_t(t) * CU_TILE + c;
+        if (j >= M) break;
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            const float v = P[a * Mp + j];
+            lo[a] = fminf(lo[a], v);  // NaNs are dropped; a candidate with a NaN coordinate can never win
+            hi[a] = fmaxf(hi[a], v);
+        }
+    }
+    float *o = boxes + (b * int64_t(ntile + (ntile + 31) / 32) + t) * 6;
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        o[a] = lo[a];
+        o[3 + a] = hi[a];
+    }
+}
+
+__global__ void super_boxes_kernel(float *__restrict__ boxes, int ntile, int nsuper) {
+    const int64_t b = blockIdx.y;
+    const int sidx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (sidx >= nsuper) return;
+    float *B = boxes + b * int64_t(ntile + nsuper) * 6;
+    float lo[3] = {CUDART_INF_F, CUDART_INF_F, CUDART_INF_F}, hi[3] = {-CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F};
+    for (int t = sidx * 32; t < ntile && t < sidx * 32 + 32; ++t) {
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            lo[a] = fminf(lo[a], B[int64_t(t) * 6 + a]);
+            hi[a] = fmaxf(hi[a], B[int64_t(t) * 6 + 3 + a]);
+        }
+    }
+    float *o = B + int64_t(ntile + sidx) * 6;
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        o[a] = lo[a];
+        o[3 + a] = hi[a];
+    }
+}
+
+}  // namespace fpv
+
+using namespace fpv;
+
+extern "C" {
+
+int fpv_nn_culled_tile(void) { return CU_TILE; }
+
+/* Number of floats of the box array per candidate batch: 6 * (tiles + super-tiles of 32 tiles). */
+size_t fpv_nn_tile_boxes_floats(int64_t M) {
+    const int64_t ntile = ceil_div(M, CU_TILE);
+    return size_t(ntile + ceil_div(ntile, 32)) * 6;
+}
+
+/* planes: fpv_nn_pack_planes of the Morton-sorted candidates; boxes out: [batches][tiles + super-tiles][6]. */
+int fpv_nn_tile_boxes(const float *planes, int64_t batches, int64_t M, float *boxes, fpv_stream_t stream) {
+    FPV_CHECK_ARG(planes && boxes && batches > 0 && M > 0 && batches <= 65535, "fpv_nn_tile_boxes: bad arguments");
+    const int64_t Mp = ceil_div(M, 64) * 64;
+    const int ntile = int(ceil_div(M, CU_TILE));
+    const int nsuper = (ntile + 31) / 32;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    dim3 grid((unsigned)ceil_div(ntile, 128), (unsigned)batches);
+    tile_boxes_kernel<<<grid, 128, 0, st>>>(planes, M, Mp, ntile, boxes);
+    FPV_LAUNCH_CHECK("tile_boxes_kernel");
+    dim3 grid2((unsigned)ceil_div(nsuper, 128), (unsigned)batches);
+    super_boxes_kernel<<<grid2, 128, 0, st>>>(boxes, ntile, nsuper);
+    FPV_LAUNCH_CHECK("super_boxes_kernel");
+    return FPV_OK;
+}
+
+/* Exact NN with box culling.  queries: groups of 128 consecutive, spatially compact points
+ * ([batches][N][3], or one shared [N][3] set when q_shared); candidates: Morton-sorted planes, their boxes
+ * (fpv_nn_tile_boxes) and original indices [cand_batches][Mp] (Mp = M rounded up to 64, pad = INT32_MAX)
+ * with cand_batches == batches or 1.  Returns, per query, the canonical distance and the
+ * ORIGINAL index (+ idx_base) of the lexicographic (distance, original index) minimum -- identical to
+ * fpv_nn_search on the unsorted cloud.  tiles_searched (optional, device) accumulates statistics. */
+int fpv_nn_culled_search(const float *queries, int q_shared, int64_t batches, int64_t N, const float *planes,
+                         const float *boxes, const int32_t *orig_idx, int64_t cand_batches, int64_t M,
+                         int64_t idx_base, float *dist, void *idx, int idx_bytes,
+                         unsigned long long *tiles_searched, fpv_stream_t stream) {
+    FPV_CHECK_ARG(queries && planes && boxes && orig_idx && dist && idx, "fpv_nn_culled_search: null pointer");
+    FPV_CHECK_ARG(batches > 0 && N > 0 && M > 0 && batches <= 65535, "fpv_nn_culled_search: empty input");
+    FPV_CHECK_ARG(cand_batches == 1 || cand_batches == batches, "fpv_nn_culled_search: cand_batches must be 1 or batches");
+    FPV_CHECK_ARG(idx_bytes == 4 || idx_bytes == 8, "fpv_nn_culled_search: idx_bytes must be 4 or 8");
+    CulledParams p;
+    int64_t eb = batches, eN = N;
+    p.q_bstride = q_shared ? 0 : N * 3;
+    if (cand_batches == 1 && !q_shared) {  // one candidate set for every batch: one flat batch of queries
+        eN = batches * N;
+        eb = 1;
+        p.q_bstride = 0;
+    }
+    p.q = queries;
+    p.N = eN;
+    p.planes = planes;
+    p.Mp = ceil_div(M, 64) * 64;
+    p.M = M;
+    p.ntile = int(ceil_div(M, CU_TILE));
+    p.nsuper = (p.ntile + 31) / 32;
+    p.plane_bstride = cand_batches == 1 ? 0 : 3 * p.Mp;
+    p.boxes = boxes;
+    p.box_bstride = cand_batches == 1 ? 0 : int64_t(p.ntile + p.nsuper) * 6;
+    p.oidx = orig_idx;
+    p.oidx_bstride = cand_batches == 1 ? 0 : p.Mp;  // original indices are padded like the planes
+    p.idx_base = idx_base;
+    p.dist = dist;
+    p.idx = idx;
+    p.idx_bytes = idx_bytes;
+    p.tiles_searched = tiles_searched;
+    dim3 grid((unsigned)ceil_div(ceil_div(eN, CU_GROUP), CU_WARPS), (unsigned)eb);
+    if (profile_on()) {
+        char nm[48];
+        snprintf(nm, sizeof(nm), "nn_culled Q=%lld M=%lld", (long long)(eb * eN), (long long)M);
+        profile_begin(nm, static_cast<cudaStream_t>(stream),
+                      12.0 * double(q_shared ? N : batches * N) + 40.0 * double(M) * double(cand_batches) +
+                          (4.0 + idx_bytes) * double(eb * eN),
+                      double(eb * eN) * double(M));
+    }
+    nn_culled_kernel<<<grid, CU_WARPS * 32, 0, static_cast<cudaStream_t>(stream)>>>(p);
+    profile_end(static_cast<cudaStream_t>(stream));
+    FPV_LAUNCH_CHECK("nn_culled_kernel");
+    return FPV_OK;
+}
+
+}  // extern "C"

@@ -22,7 +22,7 @@ namespace fpv {
 constexpr int NN_THREADS = 256;  // consumer threads (8 warps) + 1 producer warp
 constexpr int NN_TILE = 1024;    // candidates per pipeline stage
 constexpr int NN_STAGES = 4;
-constexpr int NN_PAD = 32;       // plane length granularity (points)
+constexpr int NN_PAD = 64;       // plane length granularity (points; one culling tile of nn_culled.cu)
 constexpr size_t NN_SMEM = size_t(NN_STAGES) * 3 * NN_TILE * sizeof(float) + 2 * NN_STAGES * sizeof(uint64_t);
 
 static int g_tune_qpt = 0;      // 0 = heuristic

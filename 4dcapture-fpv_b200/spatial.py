@@ -1,0 +1,126 @@
+"""Spatial ordering helpers for the culled exact search (csrc/nn_culled.cu).
+
+A cloud is sorted along a 30-bit Morton curve, cut into tiles of 64 consecutive points with bounding boxes,
+and remembered together with the permutation that maps sorted positions back to ORIGINAL indices, so the
+search can return exactly what brute force returns on the unsorted cloud (lowest original index on ties).
+The scene cloud is constant across optimiser steps (global_optimization.py:175-176), so its sorted form is
+built once and cached; the body vertices are re-sorted every step (a [T,V] argsort).
+"""
+from __future__ import annotations
+
+from typing import Dict, Tuple
+
+import torch
+
+from . import _lib
+
+INT32_MAX = 2 ** 31 - 1
+
+
+def _spread10(v: torch.Tensor) -> torch.Tensor:
+    """Spread the low 10 bits of v so that there are two zero bits between consecutive bits."""
+    v = v & 0x3FF
+    v = (v | (v << 16)) & 0x030000FF
+    v = (v | (v << 8)) & 0x0300F00F
+    v = (v | (v << 4)) & 0x030C30C3
+    v = (v | (v << 2)) & 0x09249249
+    return v
+
+
+def morton_keys(points: torch.Tensor, lo: torch.Tensor, inv_cell: torch.Tensor) -> torch.Tensor:
+    """30-bit Morton code of every point of [..., 3] on the grid (lo, inv_cell); non-finite coordinates map to
+    the last cell (they never win a search, their position in the order is irrelevant)."""
+    q = torch.nan_to_num((points - lo) * inv_cell, nan=1023.0, posinf=1023.0, neginf=0.0).clamp_(0, 1023).to(torch.int64)
+    return _spread10(q[..., 0]) | (_spread10(q[..., 1]) << 1) | (_spread10(q[..., 2]) << 2)
+
+
+def grid_of(points: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+    flat = points.reshape(-1, 3)
+    finite = torch.nan_to_num(flat, nan=0.0, posinf=0.0, neginf=0.0)
+    lo = finite.amin(dim=0)
+    hi = finite.amax(dim=0)
+    ext = torch.clamp(hi - lo, min=1e-20)
+    return lo, 1023.999 / ext
+
+
+class SortedCloud:
+    """[B,M,3] cloud sorted per batch along the Morton curve + everything nn_culled_kernel needs."""
+
+    def __init__(self, points: torch.Tensor, lo: torch.Tensor = None, inv_cell: torch.Tensor = None):
+        if points.dim() == 2:
+            points = points.unsqueeze(0)
+        _lib.require_cuda(points)
+        L = _lib.lib()
+        B, M, _ = points.shape
+        self.B, self.M = B, M
+        if lo is None:
+            lo, inv_cell = grid_of(points)
+        self.lo, self.inv_cell = lo, inv_cell
+        keys = morton_keys(points, lo, inv_cell)
+        self.perm = torch.argsort(keys, dim=1)                                   # sorted position -> original index
+        self.sorted = torch.gather(points, 1, self.perm.unsqueeze(-1).expand(-1, -1, 3)).contiguous()
+        Mp = (M + 63) // 64 * 64
+        self.oidx = torch.full((B, Mp), INT32_MAX, dtype=torch.int32, device=points.device)
+        self.oidx[:, :M] = self.perm.to(torch.int32)
+        with torch.cuda.device(points.device):
+            self.planes = torch.empty(L.fpv_nn_planes_bytes(B, M) // 4, dtype=torch.float32, device=points.device)
+            _lib.check(L.fpv_nn_pack_planes(_lib.ptr(self.sorted), B, M, _lib.ptr(self.planes), _lib.stream_ptr()),
+                       "fpv_nn_pack_planes")
+            self.boxes = torch.empty(B * L.fpv_nn_tile_boxes_floats(M), dtype=torch.float32, device=points.device)
+            _lib.check(L.fpv_nn_tile_boxes(_lib.ptr(self.planes), B, M, _lib.ptr(self.boxes), _lib.stream_ptr()),
+                       "fpv_nn_tile_boxes")
+        self._inv = None
+
+    @property
+    def inv_perm(self) -> torch.Tensor:
+        """original index -> sorted position."""
+        if self._inv is None:
+            inv = torch.empty_like(self.perm)
+            ar = torch.arange(self.M, device=self.perm.device).unsqueeze(0).expand(self.B, -1)
+            inv.scatter_(1, self.perm, ar)
+            self._inv = inv
+        return self._inv
+
+
+def culled_search(queries_grouped: torch.Tensor, q_shared: bool, batches: int, cloud: SortedCloud,
+                  idx_dtype=torch.int32, idx_base: int = 0, stats: torch.Tensor = None):
+    """queries_grouped: [batches,N,3] (or [1,N,3] when q_shared) with 128 consecutive queries spatially compact.
+    Returns (dist [batches,N], idx [batches,N]) with ORIGINAL candidate indices."""
+    L = _lib.lib()
+    q = queries_grouped.contiguous()
+    N = q.shape[1]
+    dev = q.device
+    dist = torch.empty(batches, N, dtype=torch.float32, device=dev)
+    idx = torch.empty(batches, N, dtype=idx_dtype, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(L.fpv_nn_culled_search(_lib.ptr(q), int(q_shared), batches, N, _lib.ptr(cloud.planes),
+                                          _lib.ptr(cloud.boxes), _lib.ptr(cloud.oidx), cloud.B, cloud.M, idx_base,
+                                          _lib.ptr(dist), _lib.ptr(idx), 8 if idx_dtype == torch.int64 else 4,
+                                          _lib.ptr(stats), _lib.stream_ptr()), "fpv_nn_culled_search")
+    return dist, idx
+
+
+_scene_cache: Dict[tuple, tuple] = {}
+_SCENE_CACHE_MAX = 4
+
+
+def cached_scene(scene: torch.Tensor) -> SortedCloud:
+    """Sorted form of a static cloud [1,M,3], rebuilt only when the tensor's storage, version or shape changes.
+
+    Each entry keeps a strong reference to the source tensor: while it is cached its memory cannot be freed and
+    handed to another tensor, so (data_ptr, version, shape) identifies the content (the reference keeps one scene
+    tensor alive for the whole fit, global_optimization.py:175-176)."""
+    key = (scene.data_ptr(), scene._version, tuple(scene.shape), scene.device.index)
+    hit = _scene_cache.get(key)
+    if hit is not None:
+        return hit[1]
+    while len(_scene_cache) >= _SCENE_CACHE_MAX:
+        _scene_cache.pop(next(iter(_scene_cache)))
+    src = scene.detach()
+    sc = SortedCloud(src)
+    _scene_cache[key] = (src, sc)
+    return sc
+
+
+def clear_scene_cache() -> None:
+    _scene_cache.clear()

@@ -80,6 +80,21 @@ int fpv_nn_set_engine(int engine, int tc_eshift);
 /* Debug: device buffer of 1024 int64 receiving a clock64 pipeline timeline of CTA 0 of nn_tc_kernel (NULL = off). */
 int fpv_nn_tc_debug(long long *dbg);
 
+/* Spatially indexed exact search (nn_culled.cu): the candidate cloud is Morton-sorted by the caller and cut
+ * into tiles of fpv_nn_culled_tile() points with bounding boxes; queries come in spatially compact groups of
+ * 128.  Tiles whose box-to-box lower bound exceeds the group's worst best-distance are skipped; the result
+ * (canonical distance, ORIGINAL candidate index, lowest original index on ties) equals fpv_nn_search's.
+ *   planes   : fpv_nn_pack_planes of the sorted candidates        boxes : fpv_nn_tile_boxes
+ *   orig_idx : [cand_batches][Mp] original index of every sorted candidate, Mp = M rounded up to 64,
+ *              padding = INT32_MAX */
+int fpv_nn_culled_tile(void);
+size_t fpv_nn_tile_boxes_floats(int64_t M);
+int fpv_nn_tile_boxes(const float *planes, int64_t batches, int64_t M, float *boxes, fpv_stream_t stream);
+int fpv_nn_culled_search(const float *queries, int q_shared, int64_t batches, int64_t N, const float *planes,
+                         const float *boxes, const int32_t *orig_idx, int64_t cand_batches, int64_t M,
+                         int64_t idx_base, float *dist, void *idx, int idx_bytes,
+                         unsigned long long *tiles_searched, fpv_stream_t stream);
+
 /* distChamfer(a, b) forward, reference output order (chamfer_python.py:28):
  *   d_b2a [bs,M], d_a2b [bs,N], i_b2a [bs,M] (index into a), i_a2b [bs,N] (index into b).
  * b_shared != 0: b is ONE [M,3] cloud for all bs frames (the reference materialises T copies at

@@ -1,0 +1,96 @@
+"""GPU parity of the spatially indexed exact search (nn_culled.cu + spatial.py): identical distances and
+ORIGINAL indices to the oracle, ties resolved to the lowest original index even though tiles are visited
+out of order."""
+import importlib
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import chamfer_oracle as co
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture()
+def spatial_engine(fpv):
+    ch = importlib.import_module("4dcapture-fpv_b200.chamfer")
+    old = ch.ENGINE
+    ch.ENGINE = "spatial"
+    yield ch
+    ch.ENGINE = old
+
+
+def _run(fpv, a, b, dev, idx_dtype=torch.int64):
+    out = fpv.distChamfer(torch.tensor(a, device=dev), torch.tensor(b, device=dev), idx_dtype=idx_dtype)
+    return [o.cpu().numpy() for o in out]
+
+
+def _assert_exact(got, want):
+    assert np.array_equal(got[2], want[2]), f"i_b2a mismatches: {(got[2] != want[2]).sum()}"
+    assert np.array_equal(got[3], want[3]), f"i_a2b mismatches: {(got[3] != want[3]).sum()}"
+    assert np.array_equal(got[0], want[0]) and np.array_equal(got[1], want[1])
+
+
+@pytest.mark.parametrize("T,N,M", [(1, 1, 1), (2, 5, 3), (1, 7, 1025), (3, 1000, 999), (2, 2049, 65), (1, 33, 8193),
+                                   (4, 257, 4100), (2, 10475, 30000), (3, 129, 64), (1, 128, 127)])
+def test_spatial_parity_ragged(fpv, cuda_dev, spatial_engine, T, N, M):
+    rng = np.random.default_rng(T * 7 + N * 13 + M)
+    a = (rng.standard_normal((T, N, 3)) * 0.5 + [1.0, -0.5, 0.3]).astype(np.float32)
+    b = (rng.random((M, 3)) * [8, 8, 3] - [4, 4, 0]).astype(np.float32)
+    _assert_exact(_run(fpv, a, b, cuda_dev), co.dist_chamfer(a, b))
+
+
+def test_spatial_ties_duplicates_lattice(fpv, cuda_dev, spatial_engine):
+    rng = np.random.default_rng(1)
+    a = rng.integers(-8, 9, (2, 3000, 3)).astype(np.float32)
+    b = rng.integers(-8, 9, (5000, 3)).astype(np.float32)          # heavy exact ties across distant tiles
+    _assert_exact(_run(fpv, a, b, cuda_dev), co.dist_chamfer(a, b))
+    same = np.zeros((1, 700, 3), np.float32)
+    d1, d2, i1, i2 = _run(fpv, same, same[0], cuda_dev)
+    assert (i1 == 0).all() and (i2 == 0).all() and (d1 == 0).all()
+    b2 = rng.standard_normal((6000, 3)).astype(np.float32)
+    b2[3000:] = b2[:3000]                                          # every point duplicated 3000 indices later
+    a2 = b2[None, ::7].copy()
+    _assert_exact(_run(fpv, a2, b2, cuda_dev), co.dist_chamfer(a2, b2))
+
+
+def test_spatial_outside_bbox_far_and_special(fpv, cuda_dev, spatial_engine):
+    rng = np.random.default_rng(4)
+    b = (rng.random((5000, 3)) * 2).astype(np.float32)
+    a = (rng.standard_normal((2, 800, 3)) * 20).astype(np.float32)   # most queries far outside the scene box
+    _assert_exact(_run(fpv, a, b, cuda_dev), co.dist_chamfer(a, b))
+    a3 = (100.0 + 0.01 * rng.standard_normal((1, 900, 3))).astype(np.float32)
+    b3 = (100.0 + 0.01 * rng.standard_normal((1300, 3))).astype(np.float32)
+    _assert_exact(_run(fpv, a3, b3, cuda_dev), co.dist_chamfer(a3, b3))
+    x = np.zeros((1, 300, 3), np.float32)
+    x[0, :, 0] = np.arange(300)
+    x[0, 1] = [np.nan, 0, 0]
+    x[0, 2] = [3e38, 3e38, 3e38]
+    x[0, 4] = [np.inf, 0, 0]
+    y = np.zeros((400, 3), np.float32)
+    y[:, 1] = np.arange(400) * 0.5
+    y[0] = [np.nan, 0, 0]
+    y[7] = [-3e38, -3e38, -3e38]
+    y[11] = [np.inf, np.inf, 0]
+    got = _run(fpv, x, y, cuda_dev)
+    want = co.dist_chamfer(x, y)
+    assert np.array_equal(got[2], want[2]) and np.array_equal(got[3], want[3])
+    assert np.array_equal(got[0], want[0], equal_nan=True) and np.array_equal(got[1], want[1], equal_nan=True)
+
+
+def test_spatial_equals_brute_force_at_scale_and_backward(fpv, cuda_dev, spatial_engine):
+    gen = torch.Generator().manual_seed(12)
+    T, V, M = 4, 10475, 400_000
+    scene = (torch.rand(M, 3, generator=gen) * torch.tensor([8.0, 8.0, 3.0]) - torch.tensor([4.0, 4.0, 0.0])).to(cuda_dev)
+    verts = (torch.rand(T, V, 3, generator=gen) * torch.tensor([0.6, 0.6, 1.8]) + torch.tensor([0.5, -1.0, 0.0])).to(cuda_dev)
+    spatial_engine.ENGINE = "brute"
+    ref = [o.clone() for o in fpv.distChamfer(verts, scene.unsqueeze(0), idx_dtype=torch.int32)]
+    spatial_engine.ENGINE = "spatial"
+    va = verts.clone().requires_grad_(True)
+    out = fpv.distChamfer(va, scene.unsqueeze(0), idx_dtype=torch.int32)
+    for o, r in zip(out, ref):
+        assert torch.equal(o, r)
+    print("tiles searched a->b:", spatial_engine.LAST_STATS["tiles_searched"].tolist(), "of", T * V // 128 * (M // 64))
+    (out[0].mean() + out[1].mean()).backward()
+    assert torch.isfinite(va.grad).all()
