@@ -28,7 +28,7 @@ SPATIAL_MIN_POINTS = 4096
 LAST_STATS = {}
 
 
-def _forward_spatial(a_c: torch.Tensor, b_c: torch.Tensor, idx_dtype):
+def _forward_spatial(a_c: torch.Tensor, b_c: torch.Tensor, idx_dtype, idx_base: int = 0):
     """Both chamfer directions with the scene held in Morton order.  a_c [T,N,3], b_c [1,M,3].
 
     a -> b (body vertex -> scene): the scene is static, so the box-culled tile search visits ~1 % of it.
@@ -44,7 +44,7 @@ def _forward_spatial(a_c: torch.Tensor, b_c: torch.Tensor, idx_dtype):
     scene = spatial.cached_scene(b_c)                                   # built once per scene tensor
     body = spatial.SortedCloud(a_c, scene.lo, scene.inv_cell)           # per-step [T,N] Morton argsort
     stats = torch.zeros(1, dtype=torch.int64, device=dev)
-    d_s, i_s = spatial.culled_search(body.sorted, False, T, scene, idx_dtype, stats=stats)
+    d_s, i_s = spatial.culled_search(body.sorted, False, T, scene, idx_dtype, idx_base=idx_base, stats=stats)
     d_a2b = torch.empty_like(d_s).scatter_(1, body.perm, d_s)
     i_a2b = torch.empty_like(i_s).scatter_(1, body.perm, i_s)
     planes_a = pack_planes(a_c)                                         # candidates in ORIGINAL order: native tie-break
@@ -59,6 +59,7 @@ def _forward_spatial(a_c: torch.Tensor, b_c: torch.Tensor, idx_dtype):
     d_b2a = d_s2.index_select(1, inv)
     i_b2a = i_s2.index_select(1, inv)
     LAST_STATS["tiles_searched"] = stats
+    LAST_STATS["sorted"] = (scene, i_s2)      # picked up by _ChamferFn.forward for the spatially ordered backward
     return d_b2a, d_a2b, i_b2a, i_a2b
 
 
@@ -103,8 +104,10 @@ class _ChamferFn(torch.autograd.Function):
         i_a2b = torch.empty(bs, N, dtype=idx_dtype, device=dev)
         idx_bytes = 8 if idx_dtype == torch.int64 else 4
         use_spatial = shared and (ENGINE == "spatial" or (ENGINE == "auto" and M >= SPATIAL_MIN_POINTS))
+        ctx.sorted = None
         if use_spatial:
             d_b2a, d_a2b, i_b2a, i_a2b = _forward_spatial(a_c, b_c, idx_dtype)
+            ctx.sorted = LAST_STATS.pop("sorted", None)
         else:
             with torch.cuda.device(dev):
                 nbytes = L.fpv_chamfer_fwd_workspace_bytes(bs, N, M, int(shared))
@@ -134,6 +137,17 @@ class _ChamferFn(torch.autograd.Function):
         g2 = g_a2b.contiguous().float() if g_a2b is not None else None
         grad_a = torch.empty_like(a)
         grad_b = torch.empty_like(b) if need_b else None
+        if ctx.sorted is not None and not need_b:
+            # Spatially ordered scatter: walk the scene in Morton order so that consecutive scene points hit the same
+            # body vertex and merge in registers (bwd_accum_kernel).  The fixed-point integer sum is order-independent,
+            # so grad_a is bit-identical to the original-order evaluation.
+            scene, i_s2 = ctx.sorted
+            b = scene.sorted
+            i_b2a = i_s2
+            if g1 is not None:
+                g1 = g1.index_select(1, scene.perm[0])
+            if g2 is not None:
+                i_a2b = scene.inv_perm[0].to(i_a2b.dtype)[i_a2b.long()]
         with torch.cuda.device(dev):
             nbytes = L.fpv_chamfer_bwd_workspace_bytes(bs, N, M, int(ctx.shared), int(need_b))
             ws = _lib.workspace(nbytes, dev)

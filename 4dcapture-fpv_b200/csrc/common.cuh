@@ -92,6 +92,9 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t by
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
                  : "memory");
 }
+// Blocks until the phase with the given parity has completed.  The suspend-time hint lets the hardware park the
+// thread until the barrier flips instead of re-issuing the probe every few dozen cycles: spinning waiters were
+// measured to take a third of the issue slots of nn_tc_kernel (profiles/r01_nn_tc_ncu.md).
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
     uint32_t addr = smem_u32(bar);
     uint32_t done;
@@ -99,11 +102,11 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
         asm volatile(
             "{\n"
             ".reg .pred p;\n"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n"
             "selp.u32 %0, 1, 0, p;\n"
             "}\n"
             : "=r"(done)
-            : "r"(addr), "r"(parity)
+            : "r"(addr), "r"(parity), "r"(0x989680u)
             : "memory");
     } while (!done);
 }

@@ -486,26 +486,50 @@ __device__ __forceinline__ int fix_exponent(unsigned cmax_bits, int nb_bits) {
 
 // For every (b,i): j = idx[b,i]; c = 2 g (x_i - y_j).  to_y: acc[b*acc_bstride + 3j..] -= c ; else
 // acc[b*acc_bstride + 3i..] += c (used when the target cloud is shared across batches).
+// Each thread walks BWD_RUN consecutive queries and merges consecutive contributions to the same target in
+// registers before touching memory: when the queries arrive in spatial order (the Morton-sorted scene of the
+// spatial path) neighbours share their nearest body vertex and most atomics disappear.  Integer adds are
+// associative, so the merge order cannot change the result.
+constexpr int BWD_RUN = 8;
+
 template <typename IdxT>
 __global__ void bwd_accum_kernel(const float *__restrict__ x, int64_t x_bstride, int64_t N, const float *__restrict__ y,
                                  int64_t y_bstride, const float *__restrict__ g, const IdxT *__restrict__ idx,
                                  const unsigned *__restrict__ cmax_bits, int nb_bits, int to_y, long long *acc,
                                  int64_t acc_bstride) {
     const int64_t b = blockIdx.y;
-    const int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
-    if (i >= N) return;
+    const int64_t i0 = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) * BWD_RUN;
+    if (i0 >= N) return;
     const float scale = ldexpf(1.f, fix_exponent(*cmax_bits, nb_bits));
-    const int64_t j = static_cast<int64_t>(idx[b * N + i]);
-    const float *xi = x + b * x_bstride + 3 * i, *yj = y + b * y_bstride + 3 * j;
-    const float g2 = __fmul_rn(2.f, g[b * N + i]);
-    unsigned long long *dst =
-        reinterpret_cast<unsigned long long *>(acc + b * acc_bstride + 3 * (to_y ? j : i));
+    unsigned long long *base = reinterpret_cast<unsigned long long *>(acc + b * acc_bstride);
+    long long run[3] = {0, 0, 0};
+    int64_t target = -1;
+    const int64_t i1 = (i0 + BWD_RUN < N) ? i0 + BWD_RUN : N;
+    for (int64_t i = i0; i < i1; ++i) {
+        const int64_t j = static_cast<int64_t>(idx[b * N + i]);
+        const int64_t t = to_y ? j : i;
+        if (t != target) {
+            if (target >= 0) {
 #pragma unroll
-    for (int k = 0; k < 3; ++k) {
-        float c = __fmul_rn(g2, __fsub_rn(xi[k], yj[k]));
-        if (to_y) c = -c;
-        const long long f = __float2ll_rn(__fmul_rn(c, scale));
-        if (f != 0) atomicAdd(dst + k, static_cast<unsigned long long>(f));
+                for (int k = 0; k < 3; ++k)
+                    if (run[k] != 0) atomicAdd(base + 3 * target + k, static_cast<unsigned long long>(run[k]));
+            }
+            target = t;
+            run[0] = run[1] = run[2] = 0;
+        }
+        const float *xi = x + b * x_bstride + 3 * i, *yj = y + b * y_bstride + 3 * j;
+        const float g2 = __fmul_rn(2.f, g[b * N + i]);
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            float c = __fmul_rn(g2, __fsub_rn(xi[k], yj[k]));
+            if (to_y) c = -c;
+            run[k] += __float2ll_rn(__fmul_rn(c, scale));
+        }
+    }
+    if (target >= 0) {
+#pragma unroll
+        for (int k = 0; k < 3; ++k)
+            if (run[k] != 0) atomicAdd(base + 3 * target + k, static_cast<unsigned long long>(run[k]));
     }
 }
 
@@ -558,6 +582,8 @@ static int chamfer_bwd_impl(const float *a, const float *b, int64_t bs, int64_t 
     const int64_t b_bstride = b_shared ? 0 : M * 3;
     FPV_CUDA(cudaMemsetAsync(cmax, 0, 2 * sizeof(unsigned), st));
     dim3 gridN((unsigned)ceil_div(N, 256), (unsigned)bs), gridM((unsigned)ceil_div(M, 256), (unsigned)bs);
+    dim3 gridNr((unsigned)ceil_div(ceil_div(N, BWD_RUN), 256), (unsigned)bs);
+    dim3 gridMr((unsigned)ceil_div(ceil_div(M, BWD_RUN), 256), (unsigned)bs);
 
     // ---- grad_a = 2 g_a2b (a_i - b_idx)  +  sum_{j: i_b2a[j]==i} 2 g_b2a[j] (a_i - b_j)
     const int nb_a = ilog2_ceil(M) + 1;
@@ -565,7 +591,7 @@ static int chamfer_bwd_impl(const float *a, const float *b, int64_t bs, int64_t 
         FPV_CUDA(cudaMemsetAsync(acc_a, 0, size_t(bs * N * 3) * sizeof(long long), st));
         bwd_cmax_kernel<IdxT><<<gridM, 256, 0, st>>>(b, b_bstride, M, a, N * 3, g_b2a, i_b2a, cmax);
         FPV_LAUNCH_CHECK("bwd_cmax_kernel");
-        bwd_accum_kernel<IdxT><<<gridM, 256, 0, st>>>(b, b_bstride, M, a, N * 3, g_b2a, i_b2a, cmax, nb_a, 1, acc_a,
+        bwd_accum_kernel<IdxT><<<gridMr, 256, 0, st>>>(b, b_bstride, M, a, N * 3, g_b2a, i_b2a, cmax, nb_a, 1, acc_a,
                                                       N * 3);
         FPV_LAUNCH_CHECK("bwd_accum_kernel");
     }
@@ -585,13 +611,13 @@ static int chamfer_bwd_impl(const float *a, const float *b, int64_t bs, int64_t 
             FPV_LAUNCH_CHECK("bwd_cmax_kernel");
         }
         if (g_a2b) {
-            bwd_accum_kernel<IdxT><<<gridN, 256, 0, st>>>(a, N * 3, N, b, b_bstride, g_a2b, i_a2b, cmax + 1, nb_b, 1,
+            bwd_accum_kernel<IdxT><<<gridNr, 256, 0, st>>>(a, N * 3, N, b, b_bstride, g_a2b, i_a2b, cmax + 1, nb_b, 1,
                                                           acc_b, b_shared ? 0 : M * 3);
             FPV_LAUNCH_CHECK("bwd_accum_kernel");
         }
         if (b_shared) {
             if (g_b2a) {
-                bwd_accum_kernel<IdxT><<<gridM, 256, 0, st>>>(b, 0, M, a, N * 3, g_b2a, i_b2a, cmax + 1, nb_b, 0,
+                bwd_accum_kernel<IdxT><<<gridMr, 256, 0, st>>>(b, 0, M, a, N * 3, g_b2a, i_b2a, cmax + 1, nb_b, 0,
                                                               acc_b, 0);
                 FPV_LAUNCH_CHECK("bwd_accum_kernel");
             }

@@ -26,12 +26,14 @@
 
 namespace fpv {
 
-constexpr int TC_QT = 4;           // query tiles per CTA
+constexpr int TC_SETS = 4;         // epilogue warp sets (4 warps each, one per TMEM lane quarter)
+constexpr int TC_TPS = 1;          // query tiles per epilogue set
+constexpr int TC_QT = TC_TPS * TC_SETS;  // query tiles per CTA
 constexpr int TC_M = 128;          // rows per query tile (MMA M)
 constexpr int TC_N = 256;          // candidates per tile (MMA N)
 constexpr int TC_K = 16;           // TF32 slots per pair
 constexpr int TC_STAGES = 3;
-constexpr int TC_THREADS = 384;
+constexpr int TC_THREADS = 128 + TC_SETS * 128;
 constexpr int TC_PLANE_BYTES = 3 * TC_N * 4;             // 3 KB   fp32 xyz planes of one candidate tile
 constexpr int TC_BOP_BYTES = TC_N * TC_K * 4;            // 16 KB  TF32 operand of one candidate tile
 constexpr int TC_AOP_BYTES = TC_M * TC_K * 4;            // 8 KB   TF32 operand of one query tile
@@ -42,7 +44,7 @@ constexpr size_t TC_SMEM = size_t(TC_QT) * TC_AOP_BYTES + size_t(TC_STAGES) * TC
 
 static int g_tc_eshift = 15;
 static long long *g_tc_dbg = nullptr;
-static int g_tc_ns = 128;  // accumulator sub-tile width (64 | 128 | 256)
+static int g_tc_ns = 128;  // accumulator sub-tile width (64 | 128)
 
 struct NNTCParams {
     const float *q;
@@ -175,12 +177,26 @@ __device__ __forceinline__ void tc_eval(const float *px, const float *py, const 
     }
 }
 
-// One group of 32 accumulator columns of one query row: FMNMX3 tree, and -- only if the group's minimum
-// can beat the best exact distance -- the exact re-check of the columns under the threshold.
-__device__ __forceinline__ void tc_group(const uint32_t (&r)[32], const float *px, const float *py, const float *pz,
-                                         int col0, int jglob0, int jmax, float qx, float qy, float qz, float qe,
-                                         float &bd, int &bj) {
-    float pm[8];
+// Exact re-check of the columns of one 32-column group that fall under the threshold (slow path).
+__device__ __forceinline__ void tc_recheck(const uint32_t (&r)[32], const float (&pm)[8], const float *px,
+                                           const float *py, const float *pz, int col0, int jglob0, int jmax, float qx,
+                                           float qy, float qz, float qe, float &bd, int &bj) {
+    float thresh = bd + qe;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+        if (!(pm[c] > thresh)) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                if (!(__uint_as_float(r[4 * c + i]) > thresh)) {
+                    tc_eval(px, py, pz, col0 + 4 * c + i, jglob0 + 4 * c + i, jmax, qx, qy, qz, bd, bj);
+                    thresh = bd + qe;
+                }
+            }
+        }
+    }
+}
+
+__device__ __forceinline__ float tc_tree(const uint32_t (&r)[32], float (&pm)[8]) {
 #pragma unroll
     for (int c = 0; c < 8; ++c)
         pm[c] = fminf(fmin3(__uint_as_float(r[4 * c]), __uint_as_float(r[4 * c + 1]), __uint_as_float(r[4 * c + 2])),
@@ -188,22 +204,18 @@ __device__ __forceinline__ void tc_group(const uint32_t (&r)[32], const float *p
     float m = fmin3(pm[0], pm[1], pm[2]);
     m = fmin3(m, pm[3], pm[4]);
     m = fmin3(m, pm[5], pm[6]);
-    m = fminf(m, pm[7]);
-    float thresh = bd + qe;
-    if (!(m > thresh)) {  // rare on long scans; no warp-aligned instruction inside, so divergence is legal
-#pragma unroll
-        for (int c = 0; c < 8; ++c) {
-            if (!(pm[c] > thresh)) {
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    if (!(__uint_as_float(r[4 * c + i]) > thresh)) {
-                        tc_eval(px, py, pz, col0 + 4 * c + i, jglob0 + 4 * c + i, jmax, qx, qy, qz, bd, bj);
-                        thresh = bd + qe;
-                    }
-                }
-            }
-        }
-    }
+    return fminf(m, pm[7]);
+}
+
+// One group of 32 accumulator columns of one query row: FMNMX3 tree, and -- only if the group's minimum
+// can beat the best exact distance -- the exact re-check of the columns under the threshold.
+__device__ __forceinline__ void tc_group(const uint32_t (&r)[32], const float *px, const float *py, const float *pz,
+                                         int col0, int jglob0, int jmax, float qx, float qy, float qz, float qe,
+                                         float &bd, int &bj) {
+    float pm[8];
+    const float m = tc_tree(r, pm);
+    if (!(m > bd + qe))  // rare on long scans; no warp-aligned instruction inside, so divergence is legal
+        tc_recheck(r, pm, px, py, pz, col0, jglob0, jmax, qx, qy, qz, qe, bd, bj);
 }
 
 // NS = accumulator sub-tile width (columns per MMA): 512/NS TMEM buffers are in flight, which is what hides the
@@ -238,7 +250,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) nn_tc_kernel(const NNTCParams p
         for (int s = 0; s < TC_STAGES; ++s) {
             mbar_init(&pl_full[s], 1);
             mbar_init(&bop_full[s], 2);
-            mbar_init(&stage_empty[s], 8);
+            mbar_init(&stage_empty[s], 4 * TC_SETS);
         }
         for (int i = 0; i < NBUF; ++i) {
             mbar_init(&acc_full[i], 1);
@@ -248,13 +260,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) nn_tc_kernel(const NNTCParams p
     }
     if (warp == 3) tcx_alloc(tmem_slot, 512);
 
-    // ---- epilogue threads: set 0 (warps 4-7) owns query tiles 0,2,..; set 1 (warps 8-11) owns tiles 1,3,..
+    // ---- epilogue threads: set e (warps 4+4e .. 7+4e) owns query tiles e, e+TC_SETS, ..
     //      Each thread keeps the search state of its row in registers. ----
-    static_assert(TC_QT % 2 == 0 && NBUF % 2 == 0, "query tiles alternate between the two epilogue sets");
-    constexpr int TPS = TC_QT / 2;  // tiles per epilogue set
+    constexpr int TPS = TC_TPS;
+    // Every TMEM buffer must always be consumed by the same epilogue set: a waiter may only ever be one mbarrier
+    // phase behind (parity waits alias modulo 2), which static ownership guarantees.
+    static_assert(NBUF % TC_SETS == 0 && TC_QT % TC_SETS == 0, "accumulator buffers are statically owned by epilogue sets");
     const bool is_epi = warp >= 4;
-    const int eset = (warp - 4) >> 2;
-    const int quarter = warp & 3;
+    const int eset = (warp - 4) >> 2;  // which epilogue set
+    const int quarter = warp & 3;      // TMEM lane quarter == warp index % 4
     const int row = quarter * 32 + lane;
     float qx[TPS], qy[TPS], qz[TPS], qe[TPS], bd[TPS];
     int bj[TPS];
@@ -262,7 +276,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) nn_tc_kernel(const NNTCParams p
         const float ymax = p.ymax[b * p.ymax_bstride];
 #pragma unroll
         for (int u = 0; u < TPS; ++u) {
-            const int t = 2 * u + eset;
+            const int t = TC_SETS * u + eset;
             int64_t qi = qbase + int64_t(t) * TC_M + row;
             if (qi > p.N - 1) qi = p.N - 1;
             const float x = __ldg(qsrc + 3 * qi), y = __ldg(qsrc + 3 * qi + 1), z = __ldg(qsrc + 3 * qi + 2);
@@ -429,7 +443,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) nn_tc_kernel(const NNTCParams p
             for (int sub = 0; sub < NSUB; ++sub) {
 #pragma unroll
                 for (int u = 0; u < TPS; ++u) {
-                    const uint32_t seq = uint32_t((k * NSUB + sub) * TC_QT + 2 * u + eset);
+                    const uint32_t seq = uint32_t((k * NSUB + sub) * TC_QT + TC_SETS * u + eset);
                     const uint32_t buf = seq % NBUF;
                     const bool stamp = p.dbg && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && seq < 256 &&
                                        quarter == 0 && lane == 0;
@@ -439,17 +453,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) nn_tc_kernel(const NNTCParams p
                     tcx_fence_after();
                     const uint32_t taddr0 = tlane + buf * NS;
                     const int c0 = sub * NS;
-                    uint32_t va[32], vb[32];
-                    tcx_ld32_issue(taddr0, va);
+                    uint32_t va[32];
 #pragma unroll 1
-                    for (int g = 0; g < NS / 32; g += 2) {  // software-pipelined: the next load flies during the min tree
-                        tcx_ld32_issue(taddr0 + uint32_t((g + 1) * 32), vb);
-                        tcx_ld32_wait(va);  // (waits for both outstanding loads; vb is fenced again below)
+                    for (int g = 0; g < NS / 32; ++g) {  // 4 warps per scheduler hide the TMEM load latency
+                        tcx_ld32_issue(taddr0 + uint32_t(g * 32), va);
+                        tcx_ld32_wait(va);
                         tc_group(va, px, py, pz, c0 + g * 32, jt0 + c0 + g * 32, jmax, qx[u], qy[u], qz[u], qe[u], bd[u], bj[u]);
-                        tcx_ld32_wait(vb);
-                        if (g + 2 < NS / 32) tcx_ld32_issue(taddr0 + uint32_t((g + 2) * 32), va);
-                        tc_group(vb, px, py, pz, c0 + (g + 1) * 32, jt0 + c0 + (g + 1) * 32, jmax, qx[u], qy[u], qz[u], qe[u],
-                                 bd[u], bj[u]);
                     }
                     tcx_fence_before();
                     __syncwarp();
@@ -462,7 +471,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) nn_tc_kernel(const NNTCParams p
         }
 #pragma unroll
         for (int u = 0; u < TPS; ++u) {
-            const int t = 2 * u + eset;
+            const int t = TC_SETS * u + eset;
             state[t * TC_M + row] = bd[u];
             state[(TC_QT + t) * TC_M + row] = __int_as_float(bj[u]);
         }
@@ -520,7 +529,7 @@ size_t nn_tc_workspace_bytes(int64_t cand_batches) { return align_up(size_t(cand
 
 void nn_tc_set_debug(long long *dbg) { g_tc_dbg = dbg; }
 void nn_tc_set_eshift(int e) { g_tc_eshift = (e >= 8 && e <= 30) ? e : 15; }
-void nn_tc_set_subtile(int ns) { g_tc_ns = (ns == 64 || ns == 128 || ns == 256) ? ns : 128; }
+void nn_tc_set_subtile(int ns) { g_tc_ns = (ns == 64 || ns == 128) ? ns : 128; }
 
 template <int NS>
 static cudaError_t nn_tc_dispatch(const NNTCParams &p, dim3 grid, cudaStream_t st) {
@@ -582,9 +591,7 @@ int nn_tc_launch(const float *queries, int64_t q_bstride, int64_t eb, int64_t eN
     p.keys_atomic = keys_atomic;
     p.dbg = g_tc_dbg;
     dim3 grid((unsigned)ceil_div(eN, int64_t(TC_QT) * TC_M), (unsigned)nsplit, (unsigned)eb);
-    cudaError_t e = g_tc_ns == 256 ? nn_tc_dispatch<256>(p, grid, st)
-                    : g_tc_ns == 128 ? nn_tc_dispatch<128>(p, grid, st)
-                                     : nn_tc_dispatch<64>(p, grid, st);
+    cudaError_t e = g_tc_ns == 64 ? nn_tc_dispatch<64>(p, grid, st) : nn_tc_dispatch<128>(p, grid, st);
     count_launch();
     if (e != cudaSuccess) {
         set_error("nn_tc_kernel launch failed: %s", cudaGetErrorString(e));

@@ -63,19 +63,25 @@ class _ShardedChamferFn(torch.autograd.Function):
         Ms = b_c.shape[1]
         ws = dist.get_world_size(group) if (dist.is_available() and dist.is_initialized()) else 1
         if search is None:
-            planes_b = chamfer.pack_planes(b_c)
-            keys = chamfer.nn_search(a_c, planes_b, Ms, ref_batches=1, idx_base=idx_base, want_keys=True)
+            if chamfer.ENGINE != "brute" and Ms >= chamfer.SPATIAL_MIN_POINTS:
+                # shard-local search through the spatial index (global indices via idx_base), then the combine
+                d_b2a, d_loc, i_b2a, i_glob = chamfer._forward_spatial(a_c, b_c, torch.int64, idx_base)
+                chamfer.LAST_STATS.pop("sorted", None)
+                keys = pack_keys_torch(d_loc, i_glob)
+            else:
+                planes_b = chamfer.pack_planes(b_c)
+                keys = chamfer.nn_search(a_c, planes_b, Ms, ref_batches=1, idx_base=idx_base, want_keys=True)
+                planes_a = chamfer.pack_planes(a_c)
+                L = _lib.lib()
+                d_b2a = torch.empty(T, Ms, dtype=torch.float32, device=a_c.device)
+                i_b2a = torch.empty(T, Ms, dtype=torch.int64, device=a_c.device)
+                with torch.cuda.device(a_c.device):
+                    wsb = _lib.workspace(L.fpv_nn_search_workspace_bytes(T, Ms, N), a_c.device)
+                    _lib.check(L.fpv_nn_search(_lib.ptr(b_c), 1, T, Ms, _lib.ptr(planes_a), T, N, 0, _lib.ptr(d_b2a),
+                                               _lib.ptr(i_b2a), 8, None, _lib.ptr(wsb), wsb.numel(),
+                                               _lib.stream_ptr()), "fpv_nn_search")
             combine_keys(keys, group)
             d_a2b, i_a2b = chamfer.unpack_keys(keys, torch.int64)
-            planes_a = chamfer.pack_planes(a_c)
-            L = _lib.lib()
-            d_b2a = torch.empty(T, Ms, dtype=torch.float32, device=a_c.device)
-            i_b2a = torch.empty(T, Ms, dtype=torch.int64, device=a_c.device)
-            with torch.cuda.device(a_c.device):
-                wsb = _lib.workspace(L.fpv_nn_search_workspace_bytes(T, Ms, N), a_c.device)
-                _lib.check(L.fpv_nn_search(_lib.ptr(b_c), 1, T, Ms, _lib.ptr(planes_a), T, N, 0, _lib.ptr(d_b2a),
-                                           _lib.ptr(i_b2a), 8, None, _lib.ptr(wsb), wsb.numel(),
-                                           _lib.stream_ptr()), "fpv_nn_search")
         else:  # injected search (CPU oracle in the gloo tests): same combine logic, no CUDA
             d_loc, i_loc, d_b2a, i_b2a = search(a_c, b_c)
             keys = pack_keys_torch(d_loc, i_loc + idx_base)

@@ -242,33 +242,50 @@ def run_b200(args):
     dom = max(by.items(), key=lambda kv: sum(x[0] for x in kv[1]))
     dms = statistics.mean(x[0] for x in dom[1])
     dbytes, dwork = dom[1][0][1], dom[1][0][2]
-    achieved = dbytes / (dms * 1e-3) / 1e9
     fma = ctypes.c_double()
     pkg._lib.check(L.fpv_fp32_probe(ctypes.byref(fma), pkg._lib.stream_ptr()), "fpv_fp32_probe")
-    lane_ops = dwork * 6.0 / (dms * 1e-3)                      # 3 sub + 1 mul + 2 fma per pair
     kernel_ms = sum(x[0] for v in by.values() for x in v) / K
     value = K / (ms_total * 1e-3)
+    hbm_gbs = dbytes / (dms * 1e-3) / 1e9
+    extra = {}
+    if dom[0].startswith("nn_tc"):
+        # tensor-core filter: one K=16 TF32 contraction (32 flop) per query-candidate pair
+        tf = dwork * 32.0 / (dms * 1e-3) / 1e12
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {}
+        tpeak = float(peaks.get("bf16_tflops", 1590.0))
+        roofline = {"bound": "tensor", "kernel": dom[0], "achieved": tf, "peak": tpeak, "unit": "TFLOP/s", "frac": tf / tpeak,
+                    "traffic": None, "peak_source": ("measured bf16 (MEASURED_PEAKS.json)" if peaks else "fallback bf16 (B200_PROFILING.md)") +
+                    "; the kernel issues kind::tf32 MMAs whose nominal dense rate is half the bf16 rate",
+                    "flop_per_pair": 32, "pairs_per_launch": dwork, "pairs_per_s": dwork / (dms * 1e-3), "ms_per_launch": dms,
+                    "hbm_algorithmic_GBps": hbm_gbs,
+                    "note": "co-limited by the fp32 min-reduction of the accumulators on the ALU pipe (profiles/r01_nn_tc_ncu.md)"}
+    else:
+        roofline = {"bound": "hbm", "kernel": dom[0], "achieved": hbm_gbs, "peak": hbm_peak, "unit": "GB/s",
+                    "frac": hbm_gbs / hbm_peak, "traffic": None, "peak_source": peak_src,
+                    "algorithmic_bytes_per_launch": dbytes, "ms_per_launch": dms}
+        if dom[0].startswith("nn_search"):
+            lane_ops = dwork * 6.0 / (dms * 1e-3)                  # 3 sub + 1 mul + 2 fma per pair
+            roofline["note"] = "exact brute force is FP32-issue-bound, not HBM-bound: see `simt`"
+            extra["simt"] = {"pairs_per_launch": dwork, "pairs_per_s": dwork / (dms * 1e-3), "fp32_lane_ops_per_pair": 6,
+                             "achieved_lane_ops_per_s": lane_ops, "peak_lane_fma_per_s_measured": fma.value,
+                             "frac": lane_ops / fma.value if fma.value else None}
     line = {
         "metric": METRIC, "value": value, "unit": "steps/s", "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"configs[1]: T={args.T} frames, V={V}, M={args.M}-point uniform scene, both chamfer directions, brute force exact",
+        "config": {"workload": f"configs[1]: T={args.T} frames, V={V}, M={args.M}-point uniform scene, both chamfer directions, exact",
                    "frames": args.T, "scene_points": args.M, "scene_sharding": f"{world} contiguous index ranges" if world > 1 else "none",
                    "index_dtype": "int64" if args.idx64 else "int32",
+                   "search": "body->scene: Morton-tiled box-culled exact search; scene->body: tensor-core filter + exact fp32 re-check",
                    "l2": "per-step working set (>=2.4 GB of [T,M] outputs) exceeds the 126 MB L2; no explicit flush"},
-        "roofline": {"bound": "hbm", "kernel": dom[0], "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
-                     "frac": achieved / hbm_peak, "traffic": None, "peak_source": peak_src,
-                     "algorithmic_bytes_per_launch": dbytes, "ms_per_launch": dms,
-                     "note": "exact brute force is FP32-issue-bound, not HBM-bound: see `simt`"},
-        "simt": {"pairs_per_launch": dwork, "pairs_per_s": dwork / (dms * 1e-3), "fp32_lane_ops_per_pair": 6,
-                 "achieved_lane_ops_per_s": lane_ops, "peak_lane_fma_per_s_measured": fma.value,
-                 "frac": lane_ops / fma.value if fma.value else None,
-                 "nn_kernels_share_of_step": kernel_ms / (ms_total / K)},
+        "roofline": roofline,
         "e2e": {"value": K / (ms_e2e * 1e-3), "unit": "steps/s", "h2d_bytes_per_step": prob.h2d_bytes(),
                 "d2h_bytes_per_step": prob.d2h_bytes(), "wall_s": wall_e2e},
-        "gpu_launches": launches, "clocks": clocks,
+        "gpu_launches": launches, "clocks": clocks, "fp32_lane_fma_per_s_measured": fma.value,
+        "nn_kernels_share_of_step": kernel_ms / (ms_total / K),
         "kernels": {k: {"launches_per_step": len(v) / K, "ms_mean": statistics.mean(x[0] for x in v)} for k, v in by.items()},
     }
+    line.update(extra)
     if world == 1 and not args.no_cpu_baseline:
         v, cores, sample, _ = cpu_reference_step(args.T, args.M, budget_s=12.0)
         line["cpu_baseline"] = {"value": v, "unit": "steps/s", "cores": cores, "kind": "port", "sample": sample}

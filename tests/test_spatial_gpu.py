@@ -92,5 +92,14 @@ def test_spatial_equals_brute_force_at_scale_and_backward(fpv, cuda_dev, spatial
     for o, r in zip(out, ref):
         assert torch.equal(o, r)
     print("tiles searched a->b:", spatial_engine.LAST_STATS["tiles_searched"].tolist(), "of", T * V // 128 * (M // 64))
-    (out[0].mean() + out[1].mean()).backward()
-    assert torch.isfinite(va.grad).all()
+    g = torch.Generator().manual_seed(3)
+    w1 = torch.rand(T, M, generator=g).to(cuda_dev)
+    w2 = torch.rand(T, V, generator=g).to(cuda_dev)
+    ((out[0] * w1).sum() + (out[1] * w2).sum()).backward()
+    # the spatially ordered backward must equal the original-order backward bit for bit (integer fixed-point sum)
+    spatial_engine.ENGINE = "brute"
+    vb = verts.clone().requires_grad_(True)
+    o2 = fpv.distChamfer(vb, scene.unsqueeze(0), idx_dtype=torch.int32)
+    ((o2[0] * w1).sum() + (o2[1] * w2).sum()).backward()
+    assert torch.equal(va.grad, vb.grad)
+    spatial_engine.ENGINE = "spatial"
