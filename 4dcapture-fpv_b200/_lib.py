@@ -47,11 +47,11 @@ SIGNATURES = {
     "fpv_nn_set_tuning": (c_int, [c_int, c_int, c_int]),
     "fpv_nn_set_engine": (c_int, [c_int, c_int]),
     "fpv_nn_tc_debug": (c_int, [c_void_p]),
-    "fpv_nn_culled_tile": (c_int, []),
-    "fpv_nn_tile_boxes_floats": (c_size_t, [c_int64]),
-    "fpv_nn_tile_boxes": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_void_p]),
+    "fpv_nn_culled_tile": (c_int, [c_int]),
+    "fpv_nn_tile_boxes_floats": (c_size_t, [c_int64, c_int]),
+    "fpv_nn_tile_boxes": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int, c_void_p, c_void_p]),
     "fpv_nn_culled_search": (c_int, [c_void_p, c_int, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_int64, c_int64,
-                                     c_int64, c_void_p, c_void_p, c_int, c_void_p, c_void_p]),
+                                     c_int, c_int64, c_void_p, c_void_p, c_int, c_void_p, c_void_p]),
     "fpv_chamfer_fwd_workspace_bytes": (c_size_t, [c_int64, c_int64, c_int64, c_int]),
     "fpv_chamfer_fwd": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int, c_void_p, c_void_p,
                                 c_void_p, c_void_p, c_int, c_void_p, c_size_t, c_void_p]),

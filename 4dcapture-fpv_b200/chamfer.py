@@ -25,6 +25,9 @@ from . import _lib, spatial
 # Every strategy returns bit-identical results.
 ENGINE = "auto"
 SPATIAL_MIN_POINTS = 4096
+# scene -> body inside the spatial path: "rep" = per-query representative/radius culling over 32-vertex clusters of the
+# (per-frame Morton-sorted) body (nn_culled.cu rep mode); "tc" = tensor-core filter over all vertices (nn_tc.cu).
+B2A_ENGINE = "rep"
 LAST_STATS = {}
 
 
@@ -42,19 +45,24 @@ def _forward_spatial(a_c: torch.Tensor, b_c: torch.Tensor, idx_dtype, idx_base: 
     dev = a_c.device
     L = _lib.lib()
     scene = spatial.cached_scene(b_c)                                   # built once per scene tensor
-    body = spatial.SortedCloud(a_c, scene.lo, scene.inv_cell)           # per-step [T,N] Morton argsort
+    body = spatial.SortedCloud(a_c, scene.lo, scene.inv_cell, mode=1)   # per-step [T,N] Morton argsort + cluster table
     stats = torch.zeros(1, dtype=torch.int64, device=dev)
     d_s, i_s = spatial.culled_search(body.sorted, False, T, scene, idx_dtype, idx_base=idx_base, stats=stats)
     d_a2b = torch.empty_like(d_s).scatter_(1, body.perm, d_s)
     i_a2b = torch.empty_like(i_s).scatter_(1, body.perm, i_s)
-    planes_a = pack_planes(a_c)                                         # candidates in ORIGINAL order: native tie-break
-    d_s2 = torch.empty(T, M, dtype=torch.float32, device=dev)
-    i_s2 = torch.empty(T, M, dtype=idx_dtype, device=dev)
-    with torch.cuda.device(dev):
-        ws = _lib.workspace(L.fpv_nn_search_workspace_bytes(T, M, N), dev)
-        _lib.check(L.fpv_nn_search(_lib.ptr(scene.sorted), 1, T, M, _lib.ptr(planes_a), T, N, 0, _lib.ptr(d_s2),
-                                   _lib.ptr(i_s2), 8 if idx_dtype == torch.int64 else 4, None, _lib.ptr(ws),
-                                   ws.numel(), _lib.stream_ptr()), "fpv_nn_search")
+    if B2A_ENGINE == "rep":
+        stats2 = torch.zeros(1, dtype=torch.int64, device=dev)
+        d_s2, i_s2 = spatial.culled_search(scene.sorted, True, T, body, idx_dtype, stats=stats2)
+        LAST_STATS["tiles_searched_b2a"] = stats2
+    else:
+        planes_a = pack_planes(a_c)                                     # candidates in ORIGINAL order: native tie-break
+        d_s2 = torch.empty(T, M, dtype=torch.float32, device=dev)
+        i_s2 = torch.empty(T, M, dtype=idx_dtype, device=dev)
+        with torch.cuda.device(dev):
+            ws = _lib.workspace(L.fpv_nn_search_workspace_bytes(T, M, N), dev)
+            _lib.check(L.fpv_nn_search(_lib.ptr(scene.sorted), 1, T, M, _lib.ptr(planes_a), T, N, 0, _lib.ptr(d_s2),
+                                       _lib.ptr(i_s2), 8 if idx_dtype == torch.int64 else 4, None, _lib.ptr(ws),
+                                       ws.numel(), _lib.stream_ptr()), "fpv_nn_search")
     inv = scene.inv_perm[0]
     d_b2a = d_s2.index_select(1, inv)
     i_b2a = i_s2.index_select(1, inv)

@@ -46,13 +46,14 @@ def grid_of(points: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
 class SortedCloud:
     """[B,M,3] cloud sorted per batch along the Morton curve + everything nn_culled_kernel needs."""
 
-    def __init__(self, points: torch.Tensor, lo: torch.Tensor = None, inv_cell: torch.Tensor = None):
+    def __init__(self, points: torch.Tensor, lo: torch.Tensor = None, inv_cell: torch.Tensor = None, mode: int = 0):
+        """mode 0: 64-point tiles with bounding boxes; mode 1: 32-point tiles with representative + radius."""
         if points.dim() == 2:
             points = points.unsqueeze(0)
         _lib.require_cuda(points)
         L = _lib.lib()
         B, M, _ = points.shape
-        self.B, self.M = B, M
+        self.B, self.M, self.mode = B, M, mode
         if lo is None:
             lo, inv_cell = grid_of(points)
         self.lo, self.inv_cell = lo, inv_cell
@@ -66,9 +67,9 @@ class SortedCloud:
             self.planes = torch.empty(L.fpv_nn_planes_bytes(B, M) // 4, dtype=torch.float32, device=points.device)
             _lib.check(L.fpv_nn_pack_planes(_lib.ptr(self.sorted), B, M, _lib.ptr(self.planes), _lib.stream_ptr()),
                        "fpv_nn_pack_planes")
-            self.boxes = torch.empty(B * L.fpv_nn_tile_boxes_floats(M), dtype=torch.float32, device=points.device)
-            _lib.check(L.fpv_nn_tile_boxes(_lib.ptr(self.planes), B, M, _lib.ptr(self.boxes), _lib.stream_ptr()),
-                       "fpv_nn_tile_boxes")
+            self.boxes = torch.empty(B * L.fpv_nn_tile_boxes_floats(M, mode), dtype=torch.float32, device=points.device)
+            _lib.check(L.fpv_nn_tile_boxes(_lib.ptr(self.planes), _lib.ptr(self.oidx), B, M, mode, _lib.ptr(self.boxes),
+                                           _lib.stream_ptr()), "fpv_nn_tile_boxes")
         self._inv = None
 
     @property
@@ -94,7 +95,7 @@ def culled_search(queries_grouped: torch.Tensor, q_shared: bool, batches: int, c
     idx = torch.empty(batches, N, dtype=idx_dtype, device=dev)
     with torch.cuda.device(dev):
         _lib.check(L.fpv_nn_culled_search(_lib.ptr(q), int(q_shared), batches, N, _lib.ptr(cloud.planes),
-                                          _lib.ptr(cloud.boxes), _lib.ptr(cloud.oidx), cloud.B, cloud.M, idx_base,
+                                          _lib.ptr(cloud.boxes), _lib.ptr(cloud.oidx), cloud.B, cloud.M, cloud.mode, idx_base,
                                           _lib.ptr(dist), _lib.ptr(idx), 8 if idx_dtype == torch.int64 else 4,
                                           _lib.ptr(stats), _lib.stream_ptr()), "fpv_nn_culled_search")
     return dist, idx

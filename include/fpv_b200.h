@@ -82,16 +82,19 @@ int fpv_nn_tc_debug(long long *dbg);
 
 /* Spatially indexed exact search (nn_culled.cu): the candidate cloud is Morton-sorted by the caller and cut
  * into tiles of fpv_nn_culled_tile() points with bounding boxes; queries come in spatially compact groups of
- * 128.  Tiles whose box-to-box lower bound exceeds the group's worst best-distance are skipped; the result
- * (canonical distance, ORIGINAL candidate index, lowest original index on ties) equals fpv_nn_search's.
+ * 128.  Tiles that provably cannot hold a winner are skipped -- mode 0: box-to-box gap against the group's worst
+ * best-distance; mode 1: per-query triangle inequality through each tile's representative point and covering
+ * radius -- and the result (canonical distance, ORIGINAL candidate index, lowest original index on ties) equals
+ * fpv_nn_search's.
  *   planes   : fpv_nn_pack_planes of the sorted candidates        boxes : fpv_nn_tile_boxes
  *   orig_idx : [cand_batches][Mp] original index of every sorted candidate, Mp = M rounded up to 64,
  *              padding = INT32_MAX */
-int fpv_nn_culled_tile(void);
-size_t fpv_nn_tile_boxes_floats(int64_t M);
-int fpv_nn_tile_boxes(const float *planes, int64_t batches, int64_t M, float *boxes, fpv_stream_t stream);
+int fpv_nn_culled_tile(int mode); /* mode 0: box culling, tiles of 64; mode 1: representative + radius, tiles of 32 */
+size_t fpv_nn_tile_boxes_floats(int64_t M, int mode);
+int fpv_nn_tile_boxes(const float *planes, const int32_t *orig_idx, int64_t batches, int64_t M, int mode,
+                      float *boxes, fpv_stream_t stream);
 int fpv_nn_culled_search(const float *queries, int q_shared, int64_t batches, int64_t N, const float *planes,
-                         const float *boxes, const int32_t *orig_idx, int64_t cand_batches, int64_t M,
+                         const float *boxes, const int32_t *orig_idx, int64_t cand_batches, int64_t M, int mode,
                          int64_t idx_base, float *dist, void *idx, int idx_bytes,
                          unsigned long long *tiles_searched, fpv_stream_t stream);
 

@@ -12,13 +12,14 @@ from oracle import chamfer_oracle as co
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture()
-def spatial_engine(fpv):
+@pytest.fixture(params=["rep", "tc"])
+def spatial_engine(fpv, request):
     ch = importlib.import_module("4dcapture-fpv_b200.chamfer")
-    old = ch.ENGINE
+    old = (ch.ENGINE, ch.B2A_ENGINE)
     ch.ENGINE = "spatial"
+    ch.B2A_ENGINE = request.param
     yield ch
-    ch.ENGINE = old
+    ch.ENGINE, ch.B2A_ENGINE = old
 
 
 def _run(fpv, a, b, dev, idx_dtype=torch.int64):

@@ -26,16 +26,19 @@ def timeit(fn, reps=3):
     return best
 
 res = {}
-for eng, lib_engine in (("brute", 1), ("brute", 2), ("spatial", 1), ("spatial", 2)):
+for eng, lib_engine, b2a in (("brute", 1, "tc"), ("brute", 2, "tc"), ("spatial", 2, "tc"), ("spatial", 2, "rep")):
     ch.ENGINE = eng
+    ch.B2A_ENGINE = b2a
     L.fpv_nn_set_engine(lib_engine, 0)
-    name = f"{eng}/{'simt' if lib_engine == 1 else 'tc'}"
+    name = f"{eng}/{'simt' if lib_engine == 1 else 'tc'}" + ("+rep" if (eng == "spatial" and b2a == "rep") else "")
     res[name] = [o.clone() for o in fpv.distChamfer(verts, prob.scene, idx_dtype=torch.int32)]
     ms = timeit(lambda: fpv.distChamfer(verts, prob.scene, idx_dtype=torch.int32))
     extra = ""
     if eng == "spatial":
         st = ch.LAST_STATS["tiles_searched"].tolist()
         extra = f"  tiles searched a->b {st[0] / (T * 10475 / 128 * (M / 64)):.4%}"
+        if b2a == "rep":
+            extra += f"  b->a {ch.LAST_STATS['tiles_searched_b2a'].item() / (T * (M / 128) * (10475 / 32)):.2%}"
     print(f"{name:16s} T={T} M={M}: {ms:9.3f} ms{extra}", flush=True)
 L.fpv_nn_set_engine(0, 0)
 names = list(res)
