@@ -25,9 +25,13 @@ from . import _lib, spatial
 # Every strategy returns bit-identical results.
 ENGINE = "auto"
 SPATIAL_MIN_POINTS = 4096
-# scene -> body inside the spatial path: "rep" = per-query representative/radius culling over 32-vertex clusters of the
-# (per-frame Morton-sorted) body (nn_culled.cu rep mode); "tc" = tensor-core filter over all vertices (nn_tc.cu).
-B2A_ENGINE = "rep"
+# scene -> body inside the spatial path:
+#   "sphere"  three-level bounding-sphere hierarchy over the per-frame Morton-sorted body, per-query triangle-inequality
+#             tests, temporal seeding from the previous frame's winner (nn_culled.cu nn_sphere_kernel)   [default]
+#   "rep"     single-level representative/radius culling over 32-vertex clusters (nn_culled.cu rep mode)
+#   "tc"      tensor-core filter over all vertices (nn_tc.cu)
+B2A_ENGINE = "sphere"
+SPHERE_TILE = 16
 LAST_STATS = {}
 
 
@@ -45,12 +49,17 @@ def _forward_spatial(a_c: torch.Tensor, b_c: torch.Tensor, idx_dtype, idx_base: 
     dev = a_c.device
     L = _lib.lib()
     scene = spatial.cached_scene(b_c)                                   # built once per scene tensor
-    body = spatial.SortedCloud(a_c, scene.lo, scene.inv_cell, mode=1)   # per-step [T,N] Morton argsort + cluster table
+    body = spatial.SortedCloud(a_c, scene.lo, scene.inv_cell, mode=1,   # per-step [T,N] Morton argsort + cluster table
+                               sphere_tile=SPHERE_TILE if B2A_ENGINE == "sphere" else 0)
     stats = torch.zeros(1, dtype=torch.int64, device=dev)
     d_s, i_s = spatial.culled_search(body.sorted, False, T, scene, idx_dtype, idx_base=idx_base, stats=stats)
     d_a2b = torch.empty_like(d_s).scatter_(1, body.perm, d_s)
     i_a2b = torch.empty_like(i_s).scatter_(1, body.perm, i_s)
-    if B2A_ENGINE == "rep":
+    if B2A_ENGINE == "sphere":
+        stats2 = torch.zeros(1, dtype=torch.int64, device=dev)
+        d_s2, i_s2 = spatial.sphere_search(scene.sorted, True, T, body, cand_orig=a_c, idx_dtype=idx_dtype, stats=stats2)
+        LAST_STATS["tiles_searched_b2a"] = stats2
+    elif B2A_ENGINE == "rep":
         stats2 = torch.zeros(1, dtype=torch.int64, device=dev)
         d_s2, i_s2 = spatial.culled_search(scene.sorted, True, T, body, idx_dtype, stats=stats2)
         LAST_STATS["tiles_searched_b2a"] = stats2

@@ -393,6 +393,212 @@ __global__ void super_boxes_kernel(const float *__restrict__ planes, int64_t M, 
     }
 }
 
+
+// =====================================================================================================
+// Sphere-hierarchy mode (scene -> body): candidates are per-frame Morton-sorted body vertices cut into
+// clusters of TILE points with a 3-level hierarchy of bounding spheres (TILE, 4*TILE, 16*TILE points).
+// A query needs a cluster only if |x - c| <= sqrt(best_x) + r  (triangle inequality, PER QUERY; the warp
+// searches a cluster when any of its 128 spatially adjacent queries needs it).  When the query set is shared
+// by consecutive frames of a clip, a warp walks a chunk of frames and seeds every query with the exact distance
+// to its previous frame's winner (the body moves centimetres per frame), so only the first frame of a chunk pays
+// for a seeding pass.  Results are identical to brute force (lexicographic rule on ORIGINAL indices).
+// =====================================================================================================
+struct SphereParams {
+    const float *q;
+    int64_t q_bstride, N;
+    const float *planes;
+    int64_t plane_bstride, Mp, M;
+    const float4 *table;  // [cand batches][n0 + n1 + n2] spheres (cx, cy, cz, r)
+    int64_t table_bstride;
+    const int *oidx;
+    int64_t oidx_bstride;
+    const float *cand_orig;  // [cand batches][M][3] candidates in ORIGINAL order (temporal seeding), may be null
+    int n0, n1, n2;
+    int batches, frames_per_cta;
+    int64_t idx_base;
+    float *dist;
+    void *idx;
+    int idx_bytes;
+    unsigned long long *tiles_searched;
+};
+
+// does any of this lane's 4 queries (held as two packed pairs) need the sphere (c, r)?
+__device__ __forceinline__ bool sphere_needed(const float4 e, const float2 (&qx2)[2], const float2 (&qy2)[2],
+                                              const float2 (&qz2)[2], const float2 (&sq2)[2]) {
+    bool need = false;
+    const float2 ncx = make_float2(-e.x, -e.x), ncy = make_float2(-e.y, -e.y), ncz = make_float2(-e.z, -e.z);
+    const float2 rr = make_float2(e.w, e.w);
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        const float2 dx = __fadd2_rn(qx2[h], ncx), dy = __fadd2_rn(qy2[h], ncy), dz = __fadd2_rn(qz2[h], ncz);
+        float2 d = __fmul2_rn(dx, dx);
+        d = __ffma2_rn(dy, dy, d);
+        d = __ffma2_rn(dz, dz, d);
+        const float2 lim = __fadd2_rn(sq2[h], rr);
+        const float2 l2 = __fmul2_rn(lim, lim);
+        need |= (d.x <= l2.x) | (d.y <= l2.y);  // NaN distances (NaN query / empty cluster) never ask
+    }
+    return need;
+}
+
+template <int TILE>
+__global__ void __launch_bounds__(CU_WARPS * 32) nn_sphere_kernel(const SphereParams p) {
+    __shared__ __align__(16) float stile[CU_WARPS][3][TILE < 32 ? 32 : TILE];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t group = int64_t(blockIdx.x) * CU_WARPS + warp;
+    const int64_t q0 = group * CU_GROUP;
+    if (q0 >= p.N) return;
+    const int b0 = blockIdx.y * p.frames_per_cta;
+    const int b1 = (b0 + p.frames_per_cta < p.batches) ? b0 + p.frames_per_cta : p.batches;
+    float *sx = stile[warp][0], *sy = stile[warp][1], *sz = stile[warp][2];
+    float qx[CU_QPT], qy[CU_QPT], qz[CU_QPT], best[CU_QPT];
+    int bidx[CU_QPT];
+    unsigned long long searched = 0;
+
+    for (int b = b0; b < b1; ++b) {
+        if (b == b0 || p.q_bstride != 0) {
+            const float *qsrc = p.q + int64_t(b) * p.q_bstride;
+#pragma unroll
+            for (int k = 0; k < CU_QPT; ++k) {
+                int64_t qi = q0 + k * 32 + lane;
+                if (qi > p.N - 1) qi = p.N - 1;
+                qx[k] = __ldg(qsrc + 3 * qi);
+                qy[k] = __ldg(qsrc + 3 * qi + 1);
+                qz[k] = __ldg(qsrc + 3 * qi + 2);
+            }
+        }
+        const float *planes = p.planes + int64_t(b) * p.plane_bstride;
+        const float4 *tab = p.table + int64_t(b) * p.table_bstride;
+        const int *oidx = p.oidx + int64_t(b) * p.oidx_bstride;
+        const bool temporal = (b > b0) && p.q_bstride == 0 && p.cand_orig != nullptr;
+        if (temporal) {
+            // seed: exact distance to the previous frame's winner, re-evaluated on this frame's vertices
+            const float *co = p.cand_orig + int64_t(b) * p.M * 3;
+#pragma unroll
+            for (int k = 0; k < CU_QPT; ++k) {
+                if (best[k] < CUDART_INF_F) {
+                    const float *y = co + 3 * int64_t(bidx[k]);
+                    best[k] = cu_d2(qx[k], qy[k], qz[k], __ldg(y), __ldg(y + 1), __ldg(y + 2));
+                    if (!(best[k] < CUDART_INF_F)) {
+                        best[k] = CUDART_INF_F;
+                        bidx[k] = 0;
+                    }
+                } else {
+                    bidx[k] = 0;
+                }
+            }
+        } else {
+            // seed: the first point of every level-1 group (real candidates)
+#pragma unroll
+            for (int k = 0; k < CU_QPT; ++k) {
+                best[k] = CUDART_INF_F;
+                bidx[k] = 0;
+            }
+            for (int m = 0; m < p.n1; ++m) {
+                const int64_t j = int64_t(m) * 4 * TILE;
+                const float rx = __ldg(planes + j), ry = __ldg(planes + p.Mp + j), rz = __ldg(planes + 2 * p.Mp + j);
+                const int o = __ldg(oidx + j);
+#pragma unroll
+                for (int k = 0; k < CU_QPT; ++k) {
+                    const float d = cu_d2(qx[k], qy[k], qz[k], rx, ry, rz);
+                    if (d <= best[k] && (d < best[k] || o < bidx[k])) {
+                        best[k] = d;
+                        bidx[k] = o;
+                    }
+                }
+            }
+        }
+        float2 qx2[2] = {make_float2(qx[0], qx[1]), make_float2(qx[2], qx[3])};
+        float2 qy2[2] = {make_float2(qy[0], qy[1]), make_float2(qy[2], qy[3])};
+        float2 qz2[2] = {make_float2(qz[0], qz[1]), make_float2(qz[2], qz[3])};
+        float2 sq2[2];
+        auto refresh = [&]() {
+            sq2[0] = make_float2(sqrtf(best[0]) * 1.000001f, sqrtf(best[1]) * 1.000001f);
+            sq2[1] = make_float2(sqrtf(best[2]) * 1.000001f, sqrtf(best[3]) * 1.000001f);
+        };
+        refresh();
+        const float4 *t0 = tab, *t1 = tab + p.n0, *t2 = tab + p.n0 + p.n1;
+        for (int u = 0; u < p.n2; ++u) {
+            if (!__ballot_sync(0xffffffffu, sphere_needed(__ldg(t2 + u), qx2, qy2, qz2, sq2))) continue;
+            const int m1 = (4 * u + 4 < p.n1) ? 4 * u + 4 : p.n1;
+            for (int m = 4 * u; m < m1; ++m) {
+                if (!__ballot_sync(0xffffffffu, sphere_needed(__ldg(t1 + m), qx2, qy2, qz2, sq2))) continue;
+                const int c1 = (4 * m + 4 < p.n0) ? 4 * m + 4 : p.n0;
+                for (int c = 4 * m; c < c1; ++c) {
+                    if (!__ballot_sync(0xffffffffu, sphere_needed(__ldg(t0 + c), qx2, qy2, qz2, sq2))) continue;
+                    const int64_t j0 = int64_t(c) * TILE;
+                    __syncwarp();
+                    if (TILE >= 32 || lane < TILE) {
+#pragma unroll
+                        for (int cc = 0; cc < TILE; cc += 32) {
+                            sx[cc + lane] = planes[j0 + cc + lane];
+                            sy[cc + lane] = planes[p.Mp + j0 + cc + lane];
+                            sz[cc + lane] = planes[2 * p.Mp + j0 + cc + lane];
+                        }
+                    }
+                    __syncwarp();
+                    cu_search_tile<TILE>(sx, sy, sz, oidx + j0, qx, qy, qz, best, bidx);
+                    refresh();
+                    ++searched;
+                }
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < CU_QPT; ++k) {
+            const int64_t qi = q0 + k * 32 + lane;
+            if (qi < p.N) {
+                const int64_t o = int64_t(b) * p.N + qi;
+                const int64_t gi = p.idx_base + bidx[k];
+                p.dist[o] = best[k];
+                if (p.idx_bytes == 8)
+                    static_cast<long long *>(p.idx)[o] = gi;
+                else
+                    static_cast<int *>(p.idx)[o] = int(gi);
+            }
+        }
+    }
+    if (p.tiles_searched && lane == 0) atomicAdd(p.tiles_searched, searched);
+}
+
+// one thread per sphere of any level: box centre of the finite member points, covering radius (inflated)
+__global__ void sphere_table_kernel(const float *__restrict__ planes, int64_t M, int64_t Mp, int tile, int n0, int n1,
+                                    int n2, float4 *__restrict__ table) {
+    const int64_t b = blockIdx.y;
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n0 + n1 + n2) return;
+    int64_t span = tile, first = e;
+    if (e >= n0 + n1) {
+        span = int64_t(tile) * 16;
+        first = e - n0 - n1;
+    } else if (e >= n0) {
+        span = int64_t(tile) * 4;
+        first = e - n0;
+    }
+    const int64_t j0 = first * span;
+    const int64_t j1 = (j0 + span < M) ? j0 + span : M;
+    const float *P = planes + b * 3 * Mp;
+    float lo[3] = {CUDART_INF_F, CUDART_INF_F, CUDART_INF_F}, hi[3] = {-CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F};
+    for (int64_t j = j0; j < j1; ++j) {
+        const float x = P[j], y = P[Mp + j], z = P[2 * Mp + j];
+        if (fabsf(x) < CUDART_INF_F && fabsf(y) < CUDART_INF_F && fabsf(z) < CUDART_INF_F) {  // finite points only
+            lo[0] = fminf(lo[0], x); hi[0] = fmaxf(hi[0], x);
+            lo[1] = fminf(lo[1], y); hi[1] = fmaxf(hi[1], y);
+            lo[2] = fminf(lo[2], z); hi[2] = fmaxf(hi[2], z);
+        }
+    }
+    const float cx = 0.5f * lo[0] + 0.5f * hi[0], cy = 0.5f * lo[1] + 0.5f * hi[1], cz = 0.5f * lo[2] + 0.5f * hi[2];
+    float r2 = 0.f;
+    for (int64_t j = j0; j < j1; ++j) {
+        const float x = P[j], y = P[Mp + j], z = P[2 * Mp + j];
+        if (fabsf(x) < CUDART_INF_F && fabsf(y) < CUDART_INF_F && fabsf(z) < CUDART_INF_F) {
+            const float dx = x - cx, dy = y - cy, dz = z - cz;
+            r2 = fmaxf(r2, dx * dx + dy * dy + dz * dz);
+        }
+    }
+    // an empty sphere has a NaN centre: every test against it is false, it is never searched (it cannot win)
+    table[b * int64_t(n0 + n1 + n2) + e] = make_float4(cx, cy, cz, sqrtf(r2) * 1.00001f + 1e-30f);
+}
+
 }  // namespace fpv
 
 using namespace fpv;
@@ -486,6 +692,86 @@ int fpv_nn_culled_search(const float *queries, int q_shared, int64_t batches, in
         nn_culled_kernel<CU_TILE, false><<<grid, CU_WARPS * 32, 0, st>>>(p);
     profile_end(st);
     FPV_LAUNCH_CHECK("nn_culled_kernel");
+    return FPV_OK;
+}
+
+
+/* ---- sphere-hierarchy mode (tile = 16 or 32 points) ---- */
+size_t fpv_nn_sphere_table_floats(int64_t M, int tile) {
+    const int64_t n0 = ceil_div(M, tile), n1 = ceil_div(n0, 4), n2 = ceil_div(n1, 4);
+    return size_t(n0 + n1 + n2) * 4;
+}
+
+int fpv_nn_sphere_table(const float *planes, int64_t batches, int64_t M, int tile, float *table, fpv_stream_t stream) {
+    FPV_CHECK_ARG(planes && table && batches > 0 && M > 0 && batches <= 65535, "fpv_nn_sphere_table: bad arguments");
+    FPV_CHECK_ARG(tile == 16 || tile == 32, "fpv_nn_sphere_table: tile must be 16 or 32");
+    const int64_t Mp = ceil_div(M, 64) * 64;
+    const int n0 = int(ceil_div(M, tile)), n1 = (n0 + 3) / 4, n2 = (n1 + 3) / 4;
+    dim3 grid((unsigned)ceil_div(n0 + n1 + n2, 128), (unsigned)batches);
+    sphere_table_kernel<<<grid, 128, 0, static_cast<cudaStream_t>(stream)>>>(planes, M, Mp, tile, n0, n1, n2,
+                                                                              reinterpret_cast<float4 *>(table));
+    FPV_LAUNCH_CHECK("sphere_table_kernel");
+    return FPV_OK;
+}
+
+/* Exact NN through the sphere hierarchy.  cand_orig (optional): the candidates in ORIGINAL order
+ * [cand_batches][M][3]; with a shared query set it enables temporal seeding across consecutive batches (frames). */
+int fpv_nn_sphere_search(const float *queries, int q_shared, int64_t batches, int64_t N, const float *planes,
+                         const float *table, const int32_t *orig_idx, const float *cand_orig, int64_t M, int tile,
+                         int64_t idx_base, float *dist, void *idx, int idx_bytes,
+                         unsigned long long *tiles_searched, fpv_stream_t stream) {
+    FPV_CHECK_ARG(queries && planes && table && orig_idx && dist && idx, "fpv_nn_sphere_search: null pointer");
+    FPV_CHECK_ARG(batches > 0 && N > 0 && M > 0 && batches <= 65535, "fpv_nn_sphere_search: empty input");
+    FPV_CHECK_ARG(idx_bytes == 4 || idx_bytes == 8, "fpv_nn_sphere_search: idx_bytes must be 4 or 8");
+    FPV_CHECK_ARG(tile == 16 || tile == 32, "fpv_nn_sphere_search: tile must be 16 or 32");
+    FPV_CHECK_ARG((reinterpret_cast<uintptr_t>(table) & 15) == 0, "fpv_nn_sphere_search: table must be 16-byte aligned");
+    SphereParams p;
+    p.q = queries;
+    p.q_bstride = q_shared ? 0 : N * 3;
+    p.N = N;
+    p.planes = planes;
+    p.Mp = ceil_div(M, 64) * 64;
+    p.M = M;
+    p.plane_bstride = 3 * p.Mp;
+    p.n0 = int(ceil_div(M, tile));
+    p.n1 = (p.n0 + 3) / 4;
+    p.n2 = (p.n1 + 3) / 4;
+    p.table = reinterpret_cast<const float4 *>(table);
+    p.table_bstride = p.n0 + p.n1 + p.n2;
+    p.oidx = orig_idx;
+    p.oidx_bstride = p.Mp;
+    p.cand_orig = cand_orig;
+    p.batches = int(batches);
+    p.idx_base = idx_base;
+    p.dist = dist;
+    p.idx = idx;
+    p.idx_bytes = idx_bytes;
+    p.tiles_searched = tiles_searched;
+    const int64_t ctas_x = ceil_div(ceil_div(N, CU_GROUP), CU_WARPS);
+    int64_t nchunks = batches;
+    if (q_shared && cand_orig) {  // walk frames inside the warp, but keep >= ~2 resident waves of CTAs
+        nchunks = ceil_div(int64_t(sm_count()) * 32, ctas_x);
+        if (nchunks < 1) nchunks = 1;
+        if (nchunks > batches) nchunks = batches;
+    }
+    p.frames_per_cta = int(ceil_div(batches, nchunks));
+    nchunks = ceil_div(batches, p.frames_per_cta);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    dim3 grid((unsigned)ctas_x, (unsigned)nchunks);
+    if (profile_on()) {
+        char nm[48];
+        snprintf(nm, sizeof(nm), "nn_sphere<%d> Q=%lld M=%lld", tile, (long long)(batches * N), (long long)M);
+        profile_begin(nm, st,
+                      12.0 * double(q_shared ? N : batches * N) + 24.0 * double(M) * double(batches) +
+                          (4.0 + idx_bytes) * double(batches * N),
+                      double(batches * N) * double(M));
+    }
+    if (tile == 16)
+        nn_sphere_kernel<16><<<grid, CU_WARPS * 32, 0, st>>>(p);
+    else
+        nn_sphere_kernel<32><<<grid, CU_WARPS * 32, 0, st>>>(p);
+    profile_end(st);
+    FPV_LAUNCH_CHECK("nn_sphere_kernel");
     return FPV_OK;
 }
 

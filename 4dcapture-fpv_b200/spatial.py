@@ -46,8 +46,10 @@ def grid_of(points: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
 class SortedCloud:
     """[B,M,3] cloud sorted per batch along the Morton curve + everything nn_culled_kernel needs."""
 
-    def __init__(self, points: torch.Tensor, lo: torch.Tensor = None, inv_cell: torch.Tensor = None, mode: int = 0):
-        """mode 0: 64-point tiles with bounding boxes; mode 1: 32-point tiles with representative + radius."""
+    def __init__(self, points: torch.Tensor, lo: torch.Tensor = None, inv_cell: torch.Tensor = None, mode: int = 0,
+                 sphere_tile: int = 0):
+        """mode 0: 64-point tiles with bounding boxes; mode 1: 32-point tiles with representative + radius.
+        sphere_tile (16 | 32): build the three-level bounding-sphere table of nn_sphere_kernel instead."""
         if points.dim() == 2:
             points = points.unsqueeze(0)
         _lib.require_cuda(points)
@@ -67,9 +69,16 @@ class SortedCloud:
             self.planes = torch.empty(L.fpv_nn_planes_bytes(B, M) // 4, dtype=torch.float32, device=points.device)
             _lib.check(L.fpv_nn_pack_planes(_lib.ptr(self.sorted), B, M, _lib.ptr(self.planes), _lib.stream_ptr()),
                        "fpv_nn_pack_planes")
-            self.boxes = torch.empty(B * L.fpv_nn_tile_boxes_floats(M, mode), dtype=torch.float32, device=points.device)
-            _lib.check(L.fpv_nn_tile_boxes(_lib.ptr(self.planes), _lib.ptr(self.oidx), B, M, mode, _lib.ptr(self.boxes),
-                                           _lib.stream_ptr()), "fpv_nn_tile_boxes")
+            self.sphere_tile = sphere_tile
+            if sphere_tile:
+                self.boxes = torch.empty(B * L.fpv_nn_sphere_table_floats(M, sphere_tile), dtype=torch.float32,
+                                         device=points.device)
+                _lib.check(L.fpv_nn_sphere_table(_lib.ptr(self.planes), B, M, sphere_tile, _lib.ptr(self.boxes),
+                                                 _lib.stream_ptr()), "fpv_nn_sphere_table")
+            else:
+                self.boxes = torch.empty(B * L.fpv_nn_tile_boxes_floats(M, mode), dtype=torch.float32, device=points.device)
+                _lib.check(L.fpv_nn_tile_boxes(_lib.ptr(self.planes), _lib.ptr(self.oidx), B, M, mode, _lib.ptr(self.boxes),
+                                               _lib.stream_ptr()), "fpv_nn_tile_boxes")
         self._inv = None
 
     @property
@@ -98,6 +107,26 @@ def culled_search(queries_grouped: torch.Tensor, q_shared: bool, batches: int, c
                                           _lib.ptr(cloud.boxes), _lib.ptr(cloud.oidx), cloud.B, cloud.M, cloud.mode, idx_base,
                                           _lib.ptr(dist), _lib.ptr(idx), 8 if idx_dtype == torch.int64 else 4,
                                           _lib.ptr(stats), _lib.stream_ptr()), "fpv_nn_culled_search")
+    return dist, idx
+
+
+def sphere_search(queries_grouped: torch.Tensor, q_shared: bool, batches: int, cloud: SortedCloud,
+                  cand_orig: torch.Tensor = None, idx_dtype=torch.int32, idx_base: int = 0, stats: torch.Tensor = None):
+    """Exact NN through the bounding-sphere hierarchy of `cloud` (built with sphere_tile).  cand_orig [batches,M,3]
+    (the candidates in original order) enables temporal seeding across consecutive batches when q_shared."""
+    L = _lib.lib()
+    q = queries_grouped.contiguous()
+    N = q.shape[1]
+    dev = q.device
+    dist = torch.empty(batches, N, dtype=torch.float32, device=dev)
+    idx = torch.empty(batches, N, dtype=idx_dtype, device=dev)
+    co = cand_orig.contiguous() if cand_orig is not None else None
+    with torch.cuda.device(dev):
+        _lib.check(L.fpv_nn_sphere_search(_lib.ptr(q), int(q_shared), batches, N, _lib.ptr(cloud.planes),
+                                          _lib.ptr(cloud.boxes), _lib.ptr(cloud.oidx), _lib.ptr(co), cloud.M,
+                                          cloud.sphere_tile, idx_base, _lib.ptr(dist), _lib.ptr(idx),
+                                          8 if idx_dtype == torch.int64 else 4, _lib.ptr(stats), _lib.stream_ptr()),
+                   "fpv_nn_sphere_search")
     return dist, idx
 
 

@@ -263,11 +263,12 @@ def run_b200(args):
         roofline = {"bound": "hbm", "kernel": dom[0], "achieved": hbm_gbs, "peak": hbm_peak, "unit": "GB/s",
                     "frac": hbm_gbs / hbm_peak, "traffic": None, "peak_source": peak_src,
                     "algorithmic_bytes_per_launch": dbytes, "ms_per_launch": dms}
-        if dom[0].startswith("nn_culled"):
+        if dom[0].startswith("nn_culled") or dom[0].startswith("nn_sphere"):
             ch = importlib.import_module("4dcapture-fpv_b200.chamfer")
-            st = ch.LAST_STATS.get("tiles_searched_b2a" if "rep" in dom[0] else "tiles_searched")
+            b2a = "rep" in dom[0] or dom[0].startswith("nn_sphere")
+            st = ch.LAST_STATS.get("tiles_searched_b2a" if b2a else "tiles_searched")
             if st is not None:
-                tile = 32 if "rep" in dom[0] else 64
+                tile = ch.SPHERE_TILE if dom[0].startswith("nn_sphere") else (32 if "rep" in dom[0] else 64)
                 pairs = float(st.item()) * tile * 128.0          # 128 queries of a warp meet every point of a searched tile
                 lane_ops = pairs * 6.0 / (dms * 1e-3)
                 roofline["note"] = ("exact search with culling: the binding resource is FP32 issue on the surviving tiles "
@@ -288,7 +289,7 @@ def run_b200(args):
         "config": {"workload": f"configs[1]: T={args.T} frames, V={V}, M={args.M}-point uniform scene, both chamfer directions, exact",
                    "frames": args.T, "scene_points": args.M, "scene_sharding": f"{world} contiguous index ranges" if world > 1 else "none",
                    "index_dtype": "int64" if args.idx64 else "int32",
-                   "search": "body->scene: Morton-tiled box-culled exact search; scene->body: per-query representative/radius culling over 32-vertex clusters (exact)",
+                   "search": "body->scene: Morton-tiled box-culled exact search; scene->body: per-query bounding-sphere hierarchy over the Morton-sorted body with temporal seeding (exact)",
                    "l2": "per-step working set (>=2.4 GB of [T,M] outputs) exceeds the 126 MB L2; no explicit flush"},
         "roofline": roofline,
         "e2e": {"value": K / (ms_e2e * 1e-3), "unit": "steps/s", "h2d_bytes_per_step": prob.h2d_bytes(),

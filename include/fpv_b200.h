@@ -98,6 +98,18 @@ int fpv_nn_culled_search(const float *queries, int q_shared, int64_t batches, in
                          int64_t idx_base, float *dist, void *idx, int idx_bytes,
                          unsigned long long *tiles_searched, fpv_stream_t stream);
 
+/* Sphere-hierarchy variant for moving candidate sets (scene -> body): clusters of `tile` (16 | 32) sorted points
+ * with bounding spheres on three levels; a query needs a cluster only if |x - c| <= sqrt(best_x) + r.  With a
+ * shared query set and cand_orig (the candidates in ORIGINAL order, [batches][M][3]) consecutive batches (frames)
+ * seed each other: every query starts from the exact distance to its previous frame's winner. */
+size_t fpv_nn_sphere_table_floats(int64_t M, int tile);
+int fpv_nn_sphere_table(const float *planes, int64_t batches, int64_t M, int tile, float *table,
+                        fpv_stream_t stream);
+int fpv_nn_sphere_search(const float *queries, int q_shared, int64_t batches, int64_t N, const float *planes,
+                         const float *table, const int32_t *orig_idx, const float *cand_orig, int64_t M,
+                         int tile, int64_t idx_base, float *dist, void *idx, int idx_bytes,
+                         unsigned long long *tiles_searched, fpv_stream_t stream);
+
 /* distChamfer(a, b) forward, reference output order (chamfer_python.py:28):
  *   d_b2a [bs,M], d_a2b [bs,N], i_b2a [bs,M] (index into a), i_a2b [bs,N] (index into b).
  * b_shared != 0: b is ONE [M,3] cloud for all bs frames (the reference materialises T copies at

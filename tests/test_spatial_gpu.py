@@ -12,14 +12,15 @@ from oracle import chamfer_oracle as co
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(params=["rep", "tc"])
+@pytest.fixture(params=["sphere16", "sphere32", "rep", "tc"])
 def spatial_engine(fpv, request):
     ch = importlib.import_module("4dcapture-fpv_b200.chamfer")
-    old = (ch.ENGINE, ch.B2A_ENGINE)
+    old = (ch.ENGINE, ch.B2A_ENGINE, ch.SPHERE_TILE)
     ch.ENGINE = "spatial"
-    ch.B2A_ENGINE = request.param
+    ch.B2A_ENGINE = "sphere" if request.param.startswith("sphere") else request.param
+    ch.SPHERE_TILE = 32 if request.param == "sphere32" else 16
     yield ch
-    ch.ENGINE, ch.B2A_ENGINE = old
+    ch.ENGINE, ch.B2A_ENGINE, ch.SPHERE_TILE = old
 
 
 def _run(fpv, a, b, dev, idx_dtype=torch.int64):

@@ -26,19 +26,23 @@ def timeit(fn, reps=3):
     return best
 
 res = {}
-for eng, lib_engine, b2a in (("brute", 1, "tc"), ("brute", 2, "tc"), ("spatial", 2, "tc"), ("spatial", 2, "rep")):
+for eng, lib_engine, b2a in (("brute", 1, "tc"), ("spatial", 2, "tc"), ("spatial", 2, "rep"), ("spatial", 2, "sphere16"), ("spatial", 2, "sphere32")):
     ch.ENGINE = eng
+    ch.SPHERE_TILE = 32 if b2a == "sphere32" else 16
+    tile_b2a = 32 if b2a in ("rep", "sphere32") else 16
+    b2a_name = b2a
+    b2a = "sphere" if b2a.startswith("sphere") else b2a
     ch.B2A_ENGINE = b2a
     L.fpv_nn_set_engine(lib_engine, 0)
-    name = f"{eng}/{'simt' if lib_engine == 1 else 'tc'}" + ("+rep" if (eng == "spatial" and b2a == "rep") else "")
+    name = f"{eng}/{'simt' if lib_engine == 1 else 'tc'}" + (("+" + b2a_name) if (eng == "spatial" and b2a != "tc") else "")
     res[name] = [o.clone() for o in fpv.distChamfer(verts, prob.scene, idx_dtype=torch.int32)]
     ms = timeit(lambda: fpv.distChamfer(verts, prob.scene, idx_dtype=torch.int32))
     extra = ""
     if eng == "spatial":
         st = ch.LAST_STATS["tiles_searched"].tolist()
         extra = f"  tiles searched a->b {st[0] / (T * 10475 / 128 * (M / 64)):.4%}"
-        if b2a == "rep":
-            extra += f"  b->a {ch.LAST_STATS['tiles_searched_b2a'].item() / (T * (M / 128) * (10475 / 32)):.2%}"
+        if b2a != "tc":
+            extra += f"  b->a {ch.LAST_STATS['tiles_searched_b2a'].item() / (T * (M / 128) * (10475 / tile_b2a)):.2%}"
     print(f"{name:16s} T={T} M={M}: {ms:9.3f} ms{extra}", flush=True)
 L.fpv_nn_set_engine(0, 0)
 names = list(res)
