@@ -72,9 +72,12 @@ def _forward_spatial(a_c: torch.Tensor, b_c: torch.Tensor, idx_dtype, idx_base: 
             _lib.check(L.fpv_nn_search(_lib.ptr(scene.sorted), 1, T, M, _lib.ptr(planes_a), T, N, 0, _lib.ptr(d_s2),
                                        _lib.ptr(i_s2), 8 if idx_dtype == torch.int64 else 4, None, _lib.ptr(ws),
                                        ws.numel(), _lib.stream_ptr()), "fpv_nn_search")
-    inv = scene.inv_perm[0]
-    d_b2a = d_s2.index_select(1, inv)
-    i_b2a = i_s2.index_select(1, inv)
+    if scene.identity:
+        d_b2a, i_b2a = d_s2, i_s2
+    else:
+        inv = scene.inv_perm[0]
+        d_b2a = d_s2.index_select(1, inv)
+        i_b2a = i_s2.index_select(1, inv)
     LAST_STATS["tiles_searched"] = stats
     LAST_STATS["sorted"] = (scene, i_s2)      # picked up by _ChamferFn.forward for the spatially ordered backward
     return d_b2a, d_a2b, i_b2a, i_a2b
@@ -159,12 +162,13 @@ class _ChamferFn(torch.autograd.Function):
             # body vertex and merge in registers (bwd_accum_kernel).  The fixed-point integer sum is order-independent,
             # so grad_a is bit-identical to the original-order evaluation.
             scene, i_s2 = ctx.sorted
-            b = scene.sorted
-            i_b2a = i_s2
-            if g1 is not None:
-                g1 = g1.index_select(1, scene.perm[0])
-            if g2 is not None:
-                i_a2b = scene.inv_perm[0].to(i_a2b.dtype)[i_a2b.long()]
+            if not scene.identity:
+                b = scene.sorted
+                i_b2a = i_s2
+                if g1 is not None:
+                    g1 = g1.index_select(1, scene.perm[0])
+                if g2 is not None:
+                    i_a2b = scene.inv_perm[0].to(i_a2b.dtype)[i_a2b.long()]
         with torch.cuda.device(dev):
             nbytes = L.fpv_chamfer_bwd_workspace_bytes(bs, N, M, int(ctx.shared), int(need_b))
             ws = _lib.workspace(nbytes, dev)

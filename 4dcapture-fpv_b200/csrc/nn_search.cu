@@ -453,30 +453,20 @@ static int pack_planes_impl(const float *pts, int64_t batches, int64_t M, float 
 // ---------------------------------------------------------------------------------------------
 // chamfer backward: gather for the direct term, fixed-point integer scatter for the argmin term
 // ---------------------------------------------------------------------------------------------
-template <typename IdxT>
-__global__ void bwd_cmax_kernel(const float *__restrict__ x, int64_t x_bstride, int64_t N, const float *__restrict__ y,
-                                int64_t y_bstride, const float *__restrict__ g, const IdxT *__restrict__ idx,
-                                unsigned *cmax_bits) {
-    const int64_t b = blockIdx.y;
-    const int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
-    float c = 0.f;
-    if (i < N) {
-        const int64_t j = static_cast<int64_t>(idx[b * N + i]);
-        const float *xi = x + b * x_bstride + 3 * i, *yj = y + b * y_bstride + 3 * j;
-        const float g2 = fabsf(__fmul_rn(2.f, g[b * N + i]));
-        const float m = fmaxf(fabsf(__fsub_rn(xi[0], yj[0])),
-                              fmaxf(fabsf(__fsub_rn(xi[1], yj[1])), fabsf(__fsub_rn(xi[2], yj[2]))));
-        c = __fmul_rn(g2, m);
-        if (!(c == c)) c = CUDART_INF_F;
-    }
+// max |p[i]| over a flat array (NaNs ignored), as float bits through atomicMax: order-independent, deterministic
+__global__ void absmax_kernel(const float *__restrict__ p, int64_t n, unsigned *out) {
+    float m = 0.f;
+    for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += int64_t(gridDim.x) * blockDim.x)
+        m = fmaxf(m, fabsf(p[i]));
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) c = fmaxf(c, __shfl_xor_sync(0xffffffffu, c, o));
-    if ((threadIdx.x & 31) == 0 && c > 0.f) atomicMax(cmax_bits, __float_as_uint(c));
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0 && m > 0.f) atomicMax(out, __float_as_uint(m));
 }
 
 // power-of-two fixed-point exponent: |c| <= cmax < 2^e, at most 2^nb addends => sum < 2^(e+nb+k) <= 2^62
-__device__ __forceinline__ int fix_exponent(unsigned cmax_bits, int nb_bits) {
-    const float cm = __uint_as_float(cmax_bits);
+// bound[0..2] = max|g|, max|x coordinate|, max|y coordinate|  =>  |2 g (x - y)| <= 2 gmax (xmax + ymax)
+__device__ __forceinline__ int fix_exponent(const unsigned *bound, int nb_bits) {
+    const float cm = 2.000001f * __uint_as_float(bound[0]) * (__uint_as_float(bound[1]) + __uint_as_float(bound[2]));
     if (!(cm > 0.f)) return 0;
     int e;
     frexpf(cm, &e);
@@ -500,7 +490,7 @@ __global__ void bwd_accum_kernel(const float *__restrict__ x, int64_t x_bstride,
     const int64_t b = blockIdx.y;
     const int64_t i0 = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) * BWD_RUN;
     if (i0 >= N) return;
-    const float scale = ldexpf(1.f, fix_exponent(*cmax_bits, nb_bits));
+    const float scale = ldexpf(1.f, fix_exponent(cmax_bits, nb_bits));
     unsigned long long *base = reinterpret_cast<unsigned long long *>(acc + b * acc_bstride);
     long long run[3] = {0, 0, 0};
     int64_t target = -1;
@@ -551,7 +541,7 @@ __global__ void bwd_finish_kernel(const float *__restrict__ x, int64_t N, const 
         for (int k = 0; k < 3; ++k) d[k] = __fmul_rn(g2, __fsub_rn(xi[k], yj[k]));
     }
     if (acc) {
-        const double inv = ldexp(1.0, -fix_exponent(*cmax_bits, nb_bits));
+        const double inv = ldexp(1.0, -fix_exponent(cmax_bits, nb_bits));
 #pragma unroll
         for (int k = 0; k < 3; ++k) d[k] = __fadd_rn(d[k], float(double(acc[(b * N + i) * 3 + k]) * inv));
     }
@@ -570,7 +560,7 @@ static int chamfer_bwd_impl(const float *a, const float *b, int64_t bs, int64_t 
                             const float *g_b2a, const float *g_a2b, const IdxT *i_b2a, const IdxT *i_a2b,
                             float *grad_a, float *grad_b, void *workspace, size_t workspace_bytes, cudaStream_t st) {
     Arena ar(workspace, workspace_bytes);
-    unsigned *cmax = ar.take<unsigned>(2);
+    unsigned *cmax = ar.take<unsigned>(8);  // [0..2] bound triple for grad_a, [4..6] for grad_b
     long long *acc_a = g_b2a ? ar.take<long long>(size_t(bs * N * 3)) : nullptr;
     const int64_t gb_batches = b_shared ? 1 : bs;
     const bool need_acc_b = grad_b && (g_a2b || (b_shared && g_b2a));
@@ -580,7 +570,20 @@ static int chamfer_bwd_impl(const float *a, const float *b, int64_t bs, int64_t 
         return FPV_ERR_WORKSPACE;
     }
     const int64_t b_bstride = b_shared ? 0 : M * 3;
-    FPV_CUDA(cudaMemsetAsync(cmax, 0, 2 * sizeof(unsigned), st));
+    FPV_CUDA(cudaMemsetAsync(cmax, 0, 8 * sizeof(unsigned), st));
+    auto absmax = [&](const float *ptr, int64_t n, unsigned *out) {
+        int nb = int(ceil_div(n, 256 * 16));
+        nb = nb < 1 ? 1 : (nb > 148 * 16 ? 148 * 16 : nb);
+        absmax_kernel<<<nb, 256, 0, st>>>(ptr, n, out);
+    };
+    // the contribution bound only needs max|g| and the coordinate ranges: three cheap streaming reductions instead of a
+    // pass that re-gathers every (query, winner) pair
+    absmax(a, bs * N * 3, cmax + 1);
+    absmax(b, gb_batches * M * 3, cmax + 2);
+    FPV_CUDA(cudaMemcpyAsync(cmax + 5, cmax + 2, sizeof(unsigned), cudaMemcpyDeviceToDevice, st));
+    FPV_CUDA(cudaMemcpyAsync(cmax + 6, cmax + 1, sizeof(unsigned), cudaMemcpyDeviceToDevice, st));
+    count_launch();
+    count_launch();
     dim3 gridN((unsigned)ceil_div(N, 256), (unsigned)bs), gridM((unsigned)ceil_div(M, 256), (unsigned)bs);
     dim3 gridNr((unsigned)ceil_div(ceil_div(N, BWD_RUN), 256), (unsigned)bs);
     dim3 gridMr((unsigned)ceil_div(ceil_div(M, BWD_RUN), 256), (unsigned)bs);
@@ -589,8 +592,8 @@ static int chamfer_bwd_impl(const float *a, const float *b, int64_t bs, int64_t 
     const int nb_a = ilog2_ceil(M) + 1;
     if (g_b2a) {
         FPV_CUDA(cudaMemsetAsync(acc_a, 0, size_t(bs * N * 3) * sizeof(long long), st));
-        bwd_cmax_kernel<IdxT><<<gridM, 256, 0, st>>>(b, b_bstride, M, a, N * 3, g_b2a, i_b2a, cmax);
-        FPV_LAUNCH_CHECK("bwd_cmax_kernel");
+        absmax(g_b2a, bs * M, cmax);
+        FPV_LAUNCH_CHECK("absmax_kernel");
         bwd_accum_kernel<IdxT><<<gridMr, 256, 0, st>>>(b, b_bstride, M, a, N * 3, g_b2a, i_b2a, cmax, nb_a, 1, acc_a,
                                                       N * 3);
         FPV_LAUNCH_CHECK("bwd_accum_kernel");
@@ -603,29 +606,29 @@ static int chamfer_bwd_impl(const float *a, const float *b, int64_t bs, int64_t 
         const int nb_b = ilog2_ceil(b_shared ? bs * (N + 1) : N) + 1;
         if (acc_b) FPV_CUDA(cudaMemsetAsync(acc_b, 0, size_t(gb_batches * M * 3) * sizeof(long long), st));
         if (g_a2b) {
-            bwd_cmax_kernel<IdxT><<<gridN, 256, 0, st>>>(a, N * 3, N, b, b_bstride, g_a2b, i_a2b, cmax + 1);
-            FPV_LAUNCH_CHECK("bwd_cmax_kernel");
+            absmax(g_a2b, bs * N, cmax + 4);
+            FPV_LAUNCH_CHECK("absmax_kernel");
         }
         if (b_shared && g_b2a) {
-            bwd_cmax_kernel<IdxT><<<gridM, 256, 0, st>>>(b, 0, M, a, N * 3, g_b2a, i_b2a, cmax + 1);
-            FPV_LAUNCH_CHECK("bwd_cmax_kernel");
+            absmax(g_b2a, bs * M, cmax + 4);
+            FPV_LAUNCH_CHECK("absmax_kernel");
         }
         if (g_a2b) {
-            bwd_accum_kernel<IdxT><<<gridNr, 256, 0, st>>>(a, N * 3, N, b, b_bstride, g_a2b, i_a2b, cmax + 1, nb_b, 1,
+            bwd_accum_kernel<IdxT><<<gridNr, 256, 0, st>>>(a, N * 3, N, b, b_bstride, g_a2b, i_a2b, cmax + 4, nb_b, 1,
                                                           acc_b, b_shared ? 0 : M * 3);
             FPV_LAUNCH_CHECK("bwd_accum_kernel");
         }
         if (b_shared) {
             if (g_b2a) {
-                bwd_accum_kernel<IdxT><<<gridMr, 256, 0, st>>>(b, 0, M, a, N * 3, g_b2a, i_b2a, cmax + 1, nb_b, 0,
+                bwd_accum_kernel<IdxT><<<gridMr, 256, 0, st>>>(b, 0, M, a, N * 3, g_b2a, i_b2a, cmax + 4, nb_b, 0,
                                                               acc_b, 0);
                 FPV_LAUNCH_CHECK("bwd_accum_kernel");
             }
             dim3 grid1((unsigned)ceil_div(M, 256), 1);
-            bwd_finish_kernel<IdxT><<<grid1, 256, 0, st>>>(b, M, a, 0, nullptr, i_b2a, cmax + 1, nb_b, acc_b, grad_b);
+            bwd_finish_kernel<IdxT><<<grid1, 256, 0, st>>>(b, M, a, 0, nullptr, i_b2a, cmax + 4, nb_b, acc_b, grad_b);
             FPV_LAUNCH_CHECK("bwd_finish_kernel");
         } else {
-            bwd_finish_kernel<IdxT><<<gridM, 256, 0, st>>>(b, M, a, N * 3, g_b2a, i_b2a, cmax + 1, nb_b, acc_b, grad_b);
+            bwd_finish_kernel<IdxT><<<gridM, 256, 0, st>>>(b, M, a, N * 3, g_b2a, i_b2a, cmax + 4, nb_b, acc_b, grad_b);
             FPV_LAUNCH_CHECK("bwd_finish_kernel");
         }
     }

@@ -47,11 +47,18 @@ def contact_vertex_ids(constants: Dict[str, torch.Tensor]) -> torch.Tensor:
     return torch.nonzero(leg[dom]).squeeze(1)
 
 
+def _morton_sorted(points: torch.Tensor) -> torch.Tensor:
+    """[M,3] CPU cloud re-ordered along the Morton curve of its own bounding grid (same arithmetic as spatial.py)."""
+    from . import spatial
+    lo, inv_cell = spatial.grid_of(points)
+    return points[torch.argsort(spatial.morton_keys(points, lo, inv_cell), stable=True)].contiguous()
+
+
 class FitProblem:
     """Synthetic clip + scene + body model on one device, and the per-step forward/backward."""
 
     def __init__(self, T: int, M: int, device, seed: int = 1234, scene_kind: str = "uniform",
-                 rank: int = 0, world_size: int = 1, group=None, idx_dtype=torch.int64):
+                 rank: int = 0, world_size: int = 1, group=None, idx_dtype=torch.int64, presort_scene: bool = True):
         self.T, self.M, self.device = T, M, torch.device(device)
         self.rank, self.world, self.group = rank, world_size, group
         self.idx_dtype = idx_dtype
@@ -65,6 +72,16 @@ class FitProblem:
         self.host_scale = clip["scale"].clone().reshape(1)
         self.contact_ids = contact_vertex_ids(constants).to(self.device)
         self.begin, self.end = sharded.shard_range(M, world_size, rank)
+        if presort_scene:
+            # One-time host-side data preparation: the losses do not depend on the order of the scene points (every
+            # term is a min / mean over them), so the scene is stored along the Morton curve -- globally, which makes
+            # each rank's contiguous shard spatially compact, then within each shard on the shard's own grid, which is
+            # the order spatial.cached_scene would sort it into (its permutation becomes the identity and the per-step
+            # gathers that undo it disappear).
+            self.host_scene = _morton_sorted(self.host_scene)
+            for r in range(world_size):
+                b0, e0 = sharded.shard_range(M, world_size, r)
+                self.host_scene[b0:e0] = _morton_sorted(self.host_scene[b0:e0])
         self.upload()
 
     def upload(self, non_blocking: bool = False):

@@ -47,7 +47,7 @@ class SortedCloud:
     """[B,M,3] cloud sorted per batch along the Morton curve + everything nn_culled_kernel needs."""
 
     def __init__(self, points: torch.Tensor, lo: torch.Tensor = None, inv_cell: torch.Tensor = None, mode: int = 0,
-                 sphere_tile: int = 0):
+                 sphere_tile: int = 0, check_identity: bool = False):
         """mode 0: 64-point tiles with bounding boxes; mode 1: 32-point tiles with representative + radius.
         sphere_tile (16 | 32): build the three-level bounding-sphere table of nn_sphere_kernel instead."""
         if points.dim() == 2:
@@ -60,8 +60,13 @@ class SortedCloud:
             lo, inv_cell = grid_of(points)
         self.lo, self.inv_cell = lo, inv_cell
         keys = morton_keys(points, lo, inv_cell)
-        self.perm = torch.argsort(keys, dim=1)                                   # sorted position -> original index
-        self.sorted = torch.gather(points, 1, self.perm.unsqueeze(-1).expand(-1, -1, 3)).contiguous()
+        self.perm = torch.argsort(keys, dim=1, stable=(B == 1))                  # sorted position -> original index
+        # a cloud that already arrives in Morton order (FitProblem pre-sorts its scene once) needs no gather on the
+        # way in and no un-permute of the results on the way out; checked once per cached cloud, never per step
+        self.identity = bool(check_identity and B == 1 and
+                             torch.equal(self.perm[0], torch.arange(M, device=points.device)))
+        self.sorted = points.contiguous() if self.identity else \
+            torch.gather(points, 1, self.perm.unsqueeze(-1).expand(-1, -1, 3)).contiguous()
         Mp = (M + 63) // 64 * 64
         self.oidx = torch.full((B, Mp), INT32_MAX, dtype=torch.int32, device=points.device)
         self.oidx[:, :M] = self.perm.to(torch.int32)
@@ -147,7 +152,7 @@ def cached_scene(scene: torch.Tensor) -> SortedCloud:
     while len(_scene_cache) >= _SCENE_CACHE_MAX:
         _scene_cache.pop(next(iter(_scene_cache)))
     src = scene.detach()
-    sc = SortedCloud(src)
+    sc = SortedCloud(src, check_identity=True)
     _scene_cache[key] = (src, sc)
     return sc
 

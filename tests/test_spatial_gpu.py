@@ -105,3 +105,24 @@ def test_spatial_equals_brute_force_at_scale_and_backward(fpv, cuda_dev, spatial
     ((o2[0] * w1).sum() + (o2[1] * w2).sum()).backward()
     assert torch.equal(va.grad, vb.grad)
     spatial_engine.ENGINE = "spatial"
+
+
+def test_spatial_presorted_scene_identity(fpv, cuda_dev, spatial_engine):
+    """A scene already in Morton order takes the no-gather path (SortedCloud.identity) with the same exact results
+    and the same gradient as the oracle."""
+    fit = importlib.import_module("4dcapture-fpv_b200.fit")
+    sp = importlib.import_module("4dcapture-fpv_b200.spatial")
+    rng = np.random.default_rng(17)
+    b = fit._morton_sorted(torch.tensor((rng.random((20000, 3)) * [6, 6, 2]).astype(np.float32)))
+    a = (rng.standard_normal((3, 2000, 3)) * 0.4 + [3, 3, 1]).astype(np.float32)
+    bt = b.to(cuda_dev).unsqueeze(0)
+    assert sp.cached_scene(bt).identity
+    at = torch.tensor(a, device=cuda_dev, requires_grad=True)
+    out = fpv.distChamfer(at, bt)
+    want = co.dist_chamfer(a, b.numpy())
+    _assert_exact([o.detach().cpu().numpy() for o in out], want)
+    g1 = rng.standard_normal(want[0].shape).astype(np.float32)
+    g2 = rng.standard_normal(want[1].shape).astype(np.float32)
+    (out[0] * torch.tensor(g1, device=cuda_dev)).sum().add((out[1] * torch.tensor(g2, device=cuda_dev)).sum()).backward()
+    ga, _ = co.dist_chamfer_bwd(a, b.numpy()[None], g1, g2, want[2], want[3])
+    np.testing.assert_allclose(at.grad.cpu().numpy(), ga, rtol=1e-5, atol=1e-5 * np.abs(ga).max())
