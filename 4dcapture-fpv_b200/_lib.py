@@ -46,6 +46,7 @@ SIGNATURES = {
     "fpv_nn_unpack_keys": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_int, c_void_p]),
     "fpv_nn_set_tuning": (c_int, [c_int, c_int, c_int]),
     "fpv_nn_set_engine": (c_int, [c_int, c_int]),
+    "fpv_nn_sphere_set_chunking": (c_int, [c_int]),
     "fpv_nn_tc_debug": (c_int, [c_void_p]),
     "fpv_nn_culled_tile": (c_int, [c_int]),
     "fpv_nn_tile_boxes_floats": (c_size_t, [c_int64, c_int]),

@@ -56,11 +56,11 @@ def _forward_spatial(a_c: torch.Tensor, b_c: torch.Tensor, idx_dtype, idx_base: 
     d_a2b = torch.empty_like(d_s).scatter_(1, body.perm, d_s)
     i_a2b = torch.empty_like(i_s).scatter_(1, body.perm, i_s)
     if B2A_ENGINE == "sphere":
-        stats2 = torch.zeros(1, dtype=torch.int64, device=dev)
+        stats2 = torch.zeros(2, dtype=torch.int64, device=dev)
         d_s2, i_s2 = spatial.sphere_search(scene.sorted, True, T, body, cand_orig=a_c, idx_dtype=idx_dtype, stats=stats2)
         LAST_STATS["tiles_searched_b2a"] = stats2
     elif B2A_ENGINE == "rep":
-        stats2 = torch.zeros(1, dtype=torch.int64, device=dev)
+        stats2 = torch.zeros(2, dtype=torch.int64, device=dev)
         d_s2, i_s2 = spatial.culled_search(scene.sorted, True, T, body, idx_dtype, stats=stats2)
         LAST_STATS["tiles_searched_b2a"] = stats2
     else:

@@ -402,14 +402,26 @@ __global__ void super_boxes_kernel(const float *__restrict__ planes, int64_t M, 
 // by consecutive frames of a clip, a warp walks a chunk of frames and seeds every query with the exact distance
 // to its previous frame's winner (the body moves centimetres per frame), so only the first frame of a chunk pays
 // for a seeding pass.  Results are identical to brute force (lexicographic rule on ORIGINAL indices).
+//
+// Both inner loops run on EXPANDED forms with a conservative slack, and fall back to the canonical
+// (x-y)^2 evaluation only where the expanded form cannot rule a candidate out:
+//   sphere test : |x|^2 - sq^2 - 2 x.c - 2 sq r  <=  r^2 - |c|^2           (4 packed FMAs per two queries)
+//   tile search : |y|^2 - 2 x.y                  <=  best - |x|^2          (3 packed FMAs per two candidates)
+// with sq = sqrt(best) inflated.  Every fp32 evaluation error of these forms is bounded by 2^-19.7 (|x|^2 + |c|^2
+// + ...); the thresholds carry 2^-18 of the same magnitudes, so a cluster / candidate that the canonical
+// arithmetic would accept is never dropped.  Candidates that pass the filter are re-evaluated canonically and
+// compared lexicographically, so distances and indices stay bit-identical to brute force.  A warp holding a
+// query with |x|^2 > 1e30 (where the expanded forms overflow) searches every cluster canonically instead.
 // =====================================================================================================
+constexpr float SPH_SLACK = 1.0f / 262144.0f;  // 2^-18
+
 struct SphereParams {
     const float *q;
     int64_t q_bstride, N;
     const float *planes;
     int64_t plane_bstride, Mp, M;
-    const float4 *table;  // [cand batches][n0 + n1 + n2] spheres (cx, cy, cz, r)
-    int64_t table_bstride;
+    const float4 *table;  // [cand batches][n0 + n1 + n2] entries of two float4:
+    int64_t table_bstride;  //   (-2cx, -2cy, -2cz, -2r) and (r^2 - |c|^2 + slack, (|c| + r)^2, -, -);  stride in float4
     const int *oidx;
     int64_t oidx_bstride;
     const float *cand_orig;  // [cand batches][M][3] candidates in ORIGINAL order (temporal seeding), may be null
@@ -422,42 +434,107 @@ struct SphereParams {
     unsigned long long *tiles_searched;
 };
 
-// does any of this lane's 4 queries (held as two packed pairs) need the sphere (c, r)?
-__device__ __forceinline__ bool sphere_needed(const float4 e, const float2 (&qx2)[2], const float2 (&qy2)[2],
-                                              const float2 (&qz2)[2], const float2 (&sq2)[2]) {
+// does any of this lane's 4 queries (two packed pairs) need the sphere?  a2 = |x|^2(1-s) - sq^2(1+s), sq2 = sq
+__device__ __forceinline__ bool sphere_needed(const float4 e, const float lim, const float2 (&qx2)[2],
+                                              const float2 (&qy2)[2], const float2 (&qz2)[2], const float2 (&sq2)[2],
+                                              const float2 (&a2)[2]) {
+    const float2 mx = make_float2(e.x, e.x), my = make_float2(e.y, e.y), mz = make_float2(e.z, e.z);
+    const float2 mr = make_float2(e.w, e.w);
     bool need = false;
-    const float2 ncx = make_float2(-e.x, -e.x), ncy = make_float2(-e.y, -e.y), ncz = make_float2(-e.z, -e.z);
-    const float2 rr = make_float2(e.w, e.w);
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
-        const float2 dx = __fadd2_rn(qx2[h], ncx), dy = __fadd2_rn(qy2[h], ncy), dz = __fadd2_rn(qz2[h], ncz);
-        float2 d = __fmul2_rn(dx, dx);
-        d = __ffma2_rn(dy, dy, d);
-        d = __ffma2_rn(dz, dz, d);
-        const float2 lim = __fadd2_rn(sq2[h], rr);
-        const float2 l2 = __fmul2_rn(lim, lim);
-        need |= (d.x <= l2.x) | (d.y <= l2.y);  // NaN distances (NaN query / empty cluster) never ask
+        float2 t = __ffma2_rn(qx2[h], mx, a2[h]);
+        t = __ffma2_rn(qy2[h], my, t);
+        t = __ffma2_rn(qz2[h], mz, t);
+        t = __ffma2_rn(sq2[h], mr, t);
+        need |= (t.x <= lim) | (t.y <= lim);  // NaN (NaN / infinite query) never asks
     }
     return need;
 }
 
+// Search one cluster staged as (-2y, |y|^2) for the warp's 128 queries; returns true when a query of this lane
+// improved.  thr[q] = best[q] - |x_q|^2 (1 - s) + s (|c| + r)^2.
 template <int TILE>
-__global__ void __launch_bounds__(CU_WARPS * 32) nn_sphere_kernel(const SphereParams p) {
-    __shared__ __align__(16) float stile[CU_WARPS][3][TILE < 32 ? 32 : TILE];
+__device__ __forceinline__ bool sphere_search_tile(const float *smx, const float *smy, const float *smz, const float *sy2,
+                                                   const float *__restrict__ planes_tile, int64_t Mp,
+                                                   const int *__restrict__ oidx_tile, const float (&qx)[CU_QPT],
+                                                   const float (&qy)[CU_QPT], const float (&qz)[CU_QPT],
+                                                   const float (&thr)[CU_QPT], float (&best)[CU_QPT],
+                                                   int (&bidx)[CU_QPT]) {
+    const float4 *X = reinterpret_cast<const float4 *>(smx);
+    const float4 *Y = reinterpret_cast<const float4 *>(smy);
+    const float4 *Z = reinterpret_cast<const float4 *>(smz);
+    const float4 *W = reinterpret_cast<const float4 *>(sy2);
+    bool improved = false;
+#pragma unroll 2
+    for (int j4 = 0; j4 < TILE / 4; ++j4) {
+        const float4 mx = X[j4], my = Y[j4], mz = Z[j4], y2 = W[j4];
+        const float2 mx0 = make_float2(mx.x, mx.y), mx1 = make_float2(mx.z, mx.w);
+        const float2 my0 = make_float2(my.x, my.y), my1 = make_float2(my.z, my.w);
+        const float2 mz0 = make_float2(mz.x, mz.y), mz1 = make_float2(mz.z, mz.w);
+        const float2 w0 = make_float2(y2.x, y2.y), w1 = make_float2(y2.z, y2.w);
+        bool hit[CU_QPT];
+        bool any = false;
+#pragma unroll
+        for (int q = 0; q < CU_QPT; ++q) {
+            const float2 bx = make_float2(qx[q], qx[q]), by = make_float2(qy[q], qy[q]), bz = make_float2(qz[q], qz[q]);
+            float2 s0 = __ffma2_rn(bx, mx0, w0), s1 = __ffma2_rn(bx, mx1, w1);
+            s0 = __ffma2_rn(by, my0, s0);
+            s1 = __ffma2_rn(by, my1, s1);
+            s0 = __ffma2_rn(bz, mz0, s0);
+            s1 = __ffma2_rn(bz, mz1, s1);
+            hit[q] = fminf(fmin3(s0.x, s0.y, s1.x), s1.y) <= thr[q];
+            any |= hit[q];
+        }
+        if (any) {  // rare: canonical re-evaluation of the four candidates, lexicographic update
+            float rx[4], ry[4], rz[4];
+            int o[4];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                rx[c] = __ldg(planes_tile + 4 * j4 + c);
+                ry[c] = __ldg(planes_tile + Mp + 4 * j4 + c);
+                rz[c] = __ldg(planes_tile + 2 * Mp + 4 * j4 + c);
+                o[c] = __ldg(oidx_tile + 4 * j4 + c);
+            }
+#pragma unroll
+            for (int q = 0; q < CU_QPT; ++q) {
+                if (hit[q]) {
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+                        const float e = cu_d2(qx[q], qy[q], qz[q], rx[c], ry[c], rz[c]);
+                        if (e <= best[q] && (e < best[q] || o[c] < bidx[q])) {
+                            best[q] = e;
+                            bidx[q] = o[c];
+                            improved = true;
+                        }
+                    }
+                }
+            }
+        }
+    }
+    return improved;
+}
+
+template <int TILE>
+__global__ void __launch_bounds__(CU_WARPS * 32, 5) nn_sphere_kernel(const SphereParams p) {
+    constexpr int ST = TILE < 32 ? 32 : TILE;
+    __shared__ __align__(16) float stile[CU_WARPS][4][ST];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int64_t group = int64_t(blockIdx.x) * CU_WARPS + warp;
     const int64_t q0 = group * CU_GROUP;
     if (q0 >= p.N) return;
     const int b0 = blockIdx.y * p.frames_per_cta;
     const int b1 = (b0 + p.frames_per_cta < p.batches) ? b0 + p.frames_per_cta : p.batches;
-    float *sx = stile[warp][0], *sy = stile[warp][1], *sz = stile[warp][2];
-    float qx[CU_QPT], qy[CU_QPT], qz[CU_QPT], best[CU_QPT];
+    float *smx = stile[warp][0], *smy = stile[warp][1], *smz = stile[warp][2], *sy2 = stile[warp][3];
+    float qx[CU_QPT], qy[CU_QPT], qz[CU_QPT], best[CU_QPT], xs[CU_QPT];
     int bidx[CU_QPT];
+    bool canonical = false;  // warp-uniform: a query too large for the expanded forms
     unsigned long long searched = 0;
 
     for (int b = b0; b < b1; ++b) {
         if (b == b0 || p.q_bstride != 0) {
             const float *qsrc = p.q + int64_t(b) * p.q_bstride;
+            bool big = false;
 #pragma unroll
             for (int k = 0; k < CU_QPT; ++k) {
                 int64_t qi = q0 + k * 32 + lane;
@@ -465,7 +542,11 @@ __global__ void __launch_bounds__(CU_WARPS * 32) nn_sphere_kernel(const SpherePa
                 qx[k] = __ldg(qsrc + 3 * qi);
                 qy[k] = __ldg(qsrc + 3 * qi + 1);
                 qz[k] = __ldg(qsrc + 3 * qi + 2);
+                const float x2 = fmaf(qz[k], qz[k], fmaf(qy[k], qy[k], qx[k] * qx[k]));
+                big |= x2 > 1e30f;
+                xs[k] = x2 * (1.0f - SPH_SLACK);
             }
+            canonical = __ballot_sync(0xffffffffu, big) != 0;
         }
         const float *planes = p.planes + int64_t(b) * p.plane_bstride;
         const float4 *tab = p.table + int64_t(b) * p.table_bstride;
@@ -508,38 +589,95 @@ __global__ void __launch_bounds__(CU_WARPS * 32) nn_sphere_kernel(const SpherePa
                 }
             }
         }
-        float2 qx2[2] = {make_float2(qx[0], qx[1]), make_float2(qx[2], qx[3])};
-        float2 qy2[2] = {make_float2(qy[0], qy[1]), make_float2(qy[2], qy[3])};
-        float2 qz2[2] = {make_float2(qz[0], qz[1]), make_float2(qz[2], qz[3])};
-        float2 sq2[2];
+        const float2 qx2[2] = {make_float2(qx[0], qx[1]), make_float2(qx[2], qx[3])};
+        const float2 qy2[2] = {make_float2(qy[0], qy[1]), make_float2(qy[2], qy[3])};
+        const float2 qz2[2] = {make_float2(qz[0], qz[1]), make_float2(qz[2], qz[3])};
+        float2 sq2[2], a2[2];
+        float thrb[CU_QPT];
         auto refresh = [&]() {
-            sq2[0] = make_float2(sqrtf(best[0]) * 1.000001f, sqrtf(best[1]) * 1.000001f);
-            sq2[1] = make_float2(sqrtf(best[2]) * 1.000001f, sqrtf(best[3]) * 1.000001f);
+            float sq[CU_QPT], a[CU_QPT];
+#pragma unroll
+            for (int k = 0; k < CU_QPT; ++k) {
+                sq[k] = sqrtf(best[k]) * 1.000001f;
+                a[k] = fmaf(-sq[k] * sq[k], 1.0f + SPH_SLACK, xs[k]);
+                thrb[k] = best[k] - xs[k];
+            }
+            sq2[0] = make_float2(sq[0], sq[1]);
+            sq2[1] = make_float2(sq[2], sq[3]);
+            a2[0] = make_float2(a[0], a[1]);
+            a2[1] = make_float2(a[2], a[3]);
         };
         refresh();
-        const float4 *t0 = tab, *t1 = tab + p.n0, *t2 = tab + p.n0 + p.n1;
-        for (int u = 0; u < p.n2; ++u) {
-            if (!__ballot_sync(0xffffffffu, sphere_needed(__ldg(t2 + u), qx2, qy2, qz2, sq2))) continue;
-            const int m1 = (4 * u + 4 < p.n1) ? 4 * u + 4 : p.n1;
-            for (int m = 4 * u; m < m1; ++m) {
-                if (!__ballot_sync(0xffffffffu, sphere_needed(__ldg(t1 + m), qx2, qy2, qz2, sq2))) continue;
-                const int c1 = (4 * m + 4 < p.n0) ? 4 * m + 4 : p.n0;
-                for (int c = 4 * m; c < c1; ++c) {
-                    if (!__ballot_sync(0xffffffffu, sphere_needed(__ldg(t0 + c), qx2, qy2, qz2, sq2))) continue;
-                    const int64_t j0 = int64_t(c) * TILE;
-                    __syncwarp();
-                    if (TILE >= 32 || lane < TILE) {
+        const float4 *t0 = tab, *t1 = tab + 2 * p.n0, *t2 = tab + 2 * (p.n0 + p.n1);
+        // four sibling spheres at a time (independent loads and FMA chains); bit i of the result is warp-uniform
+        auto test4 = [&](const float4 *lvl, int first, int n) -> unsigned {
+            float4 e[4];
+            float lim[4];
 #pragma unroll
-                        for (int cc = 0; cc < TILE; cc += 32) {
-                            sx[cc + lane] = planes[j0 + cc + lane];
-                            sy[cc + lane] = planes[p.Mp + j0 + cc + lane];
-                            sz[cc + lane] = planes[2 * p.Mp + j0 + cc + lane];
+            for (int i = 0; i < 4; ++i) {
+                const int s = (first + i < n) ? first + i : n - 1;
+                e[i] = __ldg(lvl + 2 * s);
+                lim[i] = __ldg(reinterpret_cast<const float *>(lvl + 2 * s + 1));
+            }
+            unsigned mask = 0;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const bool need = (first + i < n) && (canonical || sphere_needed(e[i], lim[i], qx2, qy2, qz2, sq2, a2));
+                if (__ballot_sync(0xffffffffu, need)) mask |= 1u << i;
+            }
+            return mask;
+        };
+        for (int u0 = 0; u0 < p.n2; u0 += 4) {
+            unsigned m2 = test4(t2, u0, p.n2);
+            while (m2) {
+                const int u = u0 + __ffs(m2) - 1;
+                m2 &= m2 - 1;
+                unsigned m1 = test4(t1, 4 * u, p.n1);
+                while (m1) {
+                    const int m = 4 * u + __ffs(m1) - 1;
+                    m1 &= m1 - 1;
+                    unsigned m0 = test4(t0, 4 * m, p.n0);
+                    while (m0) {
+                        const int c = 4 * m + __ffs(m0) - 1;
+                        m0 &= m0 - 1;
+                        const int64_t j0 = int64_t(c) * TILE;
+                        bool improved;
+                        __syncwarp();
+                        if (!canonical) {
+                            if (TILE >= 32 || lane < TILE) {
+#pragma unroll
+                                for (int cc = 0; cc < TILE; cc += 32) {
+                                    const float x = planes[j0 + cc + lane], y = planes[p.Mp + j0 + cc + lane];
+                                    const float z = planes[2 * p.Mp + j0 + cc + lane];
+                                    smx[cc + lane] = -2.0f * x;
+                                    smy[cc + lane] = -2.0f * y;
+                                    smz[cc + lane] = -2.0f * z;
+                                    sy2[cc + lane] = fmaf(z, z, fmaf(y, y, x * x));
+                                }
+                            }
+                            const float cr2s = SPH_SLACK * __ldg(reinterpret_cast<const float *>(t0 + 2 * c + 1) + 1);
+                            float thr[CU_QPT];
+#pragma unroll
+                            for (int k = 0; k < CU_QPT; ++k) thr[k] = thrb[k] + cr2s;
+                            __syncwarp();
+                            improved = sphere_search_tile<TILE>(smx, smy, smz, sy2, planes + j0, p.Mp, oidx + j0, qx, qy, qz,
+                                                                thr, best, bidx);
+                        } else {
+                            if (TILE >= 32 || lane < TILE) {
+#pragma unroll
+                                for (int cc = 0; cc < TILE; cc += 32) {
+                                    smx[cc + lane] = planes[j0 + cc + lane];
+                                    smy[cc + lane] = planes[p.Mp + j0 + cc + lane];
+                                    smz[cc + lane] = planes[2 * p.Mp + j0 + cc + lane];
+                                }
+                            }
+                            __syncwarp();
+                            cu_search_tile<TILE>(smx, smy, smz, oidx + j0, qx, qy, qz, best, bidx);
+                            improved = false;
                         }
+                        if (improved) refresh();
+                        ++searched;
                     }
-                    __syncwarp();
-                    cu_search_tile<TILE>(sx, sy, sz, oidx + j0, qx, qy, qz, best, bidx);
-                    refresh();
-                    ++searched;
                 }
             }
         }
@@ -560,7 +698,8 @@ __global__ void __launch_bounds__(CU_WARPS * 32) nn_sphere_kernel(const SpherePa
     if (p.tiles_searched && lane == 0) atomicAdd(p.tiles_searched, searched);
 }
 
-// one thread per sphere of any level: box centre of the finite member points, covering radius (inflated)
+// one thread per sphere of any level: box centre of the finite member points, covering radius (inflated), stored in
+// the expanded-test form (see above)
 __global__ void sphere_table_kernel(const float *__restrict__ planes, int64_t M, int64_t Mp, int tile, int n0, int n1,
                                     int n2, float4 *__restrict__ table) {
     const int64_t b = blockIdx.y;
@@ -586,6 +725,12 @@ __global__ void sphere_table_kernel(const float *__restrict__ planes, int64_t M,
             lo[2] = fminf(lo[2], z); hi[2] = fmaxf(hi[2], z);
         }
     }
+    float4 *out = table + 2 * (b * int64_t(n0 + n1 + n2) + e);
+    if (lo[0] > hi[0]) {  // no finite member: nothing in here can win; never asked for (lim = -inf)
+        out[0] = make_float4(0.f, 0.f, 0.f, -2e-30f);
+        out[1] = make_float4(-CUDART_INF_F, 0.f, 0.f, 0.f);
+        return;
+    }
     const float cx = 0.5f * lo[0] + 0.5f * hi[0], cy = 0.5f * lo[1] + 0.5f * hi[1], cz = 0.5f * lo[2] + 0.5f * hi[2];
     float r2 = 0.f;
     for (int64_t j = j0; j < j1; ++j) {
@@ -595,8 +740,16 @@ __global__ void sphere_table_kernel(const float *__restrict__ planes, int64_t M,
             r2 = fmaxf(r2, dx * dx + dy * dy + dz * dz);
         }
     }
-    // an empty sphere has a NaN centre: every test against it is false, it is never searched (it cannot win)
-    table[b * int64_t(n0 + n1 + n2) + e] = make_float4(cx, cy, cz, sqrtf(r2) * 1.00001f + 1e-30f);
+    const float r = sqrtf(r2) * 1.00001f + 1e-30f;
+    const float c2 = cx * cx + cy * cy + cz * cz, rr = r * r;
+    if (!(c2 + rr < 1e30f)) {  // the expanded test would overflow: always asked for (lim = +inf), full slack
+        out[0] = make_float4(0.f, 0.f, 0.f, -2e-30f);
+        out[1] = make_float4(CUDART_INF_F, CUDART_INF_F, 0.f, 0.f);
+        return;
+    }
+    const float cr = sqrtf(c2) + r;
+    out[0] = make_float4(-2.f * cx, -2.f * cy, -2.f * cz, -2.f * r);
+    out[1] = make_float4((rr - c2) + SPH_SLACK * (c2 + rr), cr * cr * 1.00001f, 0.f, 0.f);
 }
 
 }  // namespace fpv
@@ -699,7 +852,7 @@ int fpv_nn_culled_search(const float *queries, int q_shared, int64_t batches, in
 /* ---- sphere-hierarchy mode (tile = 16 or 32 points) ---- */
 size_t fpv_nn_sphere_table_floats(int64_t M, int tile) {
     const int64_t n0 = ceil_div(M, tile), n1 = ceil_div(n0, 4), n2 = ceil_div(n1, 4);
-    return size_t(n0 + n1 + n2) * 4;
+    return size_t(n0 + n1 + n2) * 8;
 }
 
 int fpv_nn_sphere_table(const float *planes, int64_t batches, int64_t M, int tile, float *table, fpv_stream_t stream) {
@@ -711,6 +864,16 @@ int fpv_nn_sphere_table(const float *planes, int64_t batches, int64_t M, int til
     sphere_table_kernel<<<grid, 128, 0, static_cast<cudaStream_t>(stream)>>>(planes, M, Mp, tile, n0, n1, n2,
                                                                               reinterpret_cast<float4 *>(table));
     FPV_LAUNCH_CHECK("sphere_table_kernel");
+    return FPV_OK;
+}
+
+static int g_sphere_ctas_per_sm = 256;
+
+/* Frame chunking of the temporally seeded sphere search: the grid is sized to about ctas_per_sm CTAs per SM
+ * (more CTAs = better load balance over the heavy-tailed per-group cost, but every chunk pays one unseeded frame). */
+int fpv_nn_sphere_set_chunking(int ctas_per_sm) {
+    FPV_CHECK_ARG(ctas_per_sm >= 1 && ctas_per_sm <= 4096, "fpv_nn_sphere_set_chunking: ctas_per_sm out of range");
+    g_sphere_ctas_per_sm = ctas_per_sm;
     return FPV_OK;
 }
 
@@ -737,7 +900,7 @@ int fpv_nn_sphere_search(const float *queries, int q_shared, int64_t batches, in
     p.n1 = (p.n0 + 3) / 4;
     p.n2 = (p.n1 + 3) / 4;
     p.table = reinterpret_cast<const float4 *>(table);
-    p.table_bstride = p.n0 + p.n1 + p.n2;
+    p.table_bstride = 2 * int64_t(p.n0 + p.n1 + p.n2);
     p.oidx = orig_idx;
     p.oidx_bstride = p.Mp;
     p.cand_orig = cand_orig;
@@ -750,7 +913,7 @@ int fpv_nn_sphere_search(const float *queries, int q_shared, int64_t batches, in
     const int64_t ctas_x = ceil_div(ceil_div(N, CU_GROUP), CU_WARPS);
     int64_t nchunks = batches;
     if (q_shared && cand_orig) {  // walk frames inside the warp, but keep >= ~2 resident waves of CTAs
-        nchunks = ceil_div(int64_t(sm_count()) * 32, ctas_x);
+        nchunks = ceil_div(int64_t(sm_count()) * g_sphere_ctas_per_sm, ctas_x);
         if (nchunks < 1) nchunks = 1;
         if (nchunks > batches) nchunks = batches;
     }

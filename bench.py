@@ -269,7 +269,7 @@ def run_b200(args):
             st = ch.LAST_STATS.get("tiles_searched_b2a" if b2a else "tiles_searched")
             if st is not None:
                 tile = ch.SPHERE_TILE if dom[0].startswith("nn_sphere") else (32 if "rep" in dom[0] else 64)
-                pairs = float(st.item()) * tile * 128.0          # 128 queries of a warp meet every point of a searched tile
+                pairs = float(st.reshape(-1)[0].item()) * tile * 128.0          # 128 queries of a warp meet every point of a searched tile
                 lane_ops = pairs * 6.0 / (dms * 1e-3)
                 roofline["note"] = ("exact search with culling: the binding resource is FP32 issue on the surviving tiles "
                                     "plus the per-query cluster tests, not HBM: see `simt`")

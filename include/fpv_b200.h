@@ -98,10 +98,16 @@ int fpv_nn_culled_search(const float *queries, int q_shared, int64_t batches, in
                          int64_t idx_base, float *dist, void *idx, int idx_bytes,
                          unsigned long long *tiles_searched, fpv_stream_t stream);
 
+/* Frame chunking of fpv_nn_sphere_search with temporal seeding: size the grid to about ctas_per_sm CTAs per SM
+ * (default 256).  More chunks balance the heavy-tailed per-group cost; every chunk pays one unseeded frame. */
+int fpv_nn_sphere_set_chunking(int ctas_per_sm);
+
 /* Sphere-hierarchy variant for moving candidate sets (scene -> body): clusters of `tile` (16 | 32) sorted points
  * with bounding spheres on three levels; a query needs a cluster only if |x - c| <= sqrt(best_x) + r.  With a
  * shared query set and cand_orig (the candidates in ORIGINAL order, [batches][M][3]) consecutive batches (frames)
- * seed each other: every query starts from the exact distance to its previous frame's winner. */
+ * seed each other: every query starts from the exact distance to its previous frame's winner.
+ * Table: 8 floats per sphere (expanded-test form, see nn_culled.cu).  tiles_searched (optional, device):
+ * += clusters searched by a warp. */
 size_t fpv_nn_sphere_table_floats(int64_t M, int tile);
 int fpv_nn_sphere_table(const float *planes, int64_t batches, int64_t M, int tile, float *table,
                         fpv_stream_t stream);

@@ -42,7 +42,7 @@ for eng, lib_engine, b2a in (("brute", 1, "tc"), ("spatial", 2, "tc"), ("spatial
         st = ch.LAST_STATS["tiles_searched"].tolist()
         extra = f"  tiles searched a->b {st[0] / (T * 10475 / 128 * (M / 64)):.4%}"
         if b2a != "tc":
-            extra += f"  b->a {ch.LAST_STATS['tiles_searched_b2a'].item() / (T * (M / 128) * (10475 / tile_b2a)):.2%}"
+            extra += f"  b->a {ch.LAST_STATS['tiles_searched_b2a'].reshape(-1)[0].item() / (T * (M / 128) * (10475 / tile_b2a)):.2%}"
     print(f"{name:16s} T={T} M={M}: {ms:9.3f} ms{extra}", flush=True)
 L.fpv_nn_set_engine(0, 0)
 names = list(res)
