@@ -420,8 +420,11 @@ struct SphereParams {
     int64_t q_bstride, N;
     const float *planes;
     int64_t plane_bstride, Mp, M;
-    const float4 *table;  // [cand batches][n0 + n1 + n2] entries of two float4:
-    int64_t table_bstride;  //   (-2cx, -2cy, -2cz, -2r) and (r^2 - |c|^2 + slack, (|c| + r)^2, -, -);  stride in float4
+    const float4 *table;    // [cand batches] { [n0p + n1p + n2p] sphere entries of two float4:
+    int64_t table_bstride;  //   (-2cx, -2cy, -2cz, -2r) and (r^2 - |c|^2 + slack, (|c| + r)^2, -, -), every level padded to
+                            //   whole sibling groups of 4 with never-asked entries (lim = NaN);
+                            //   [n0p * TILE / 4] expanded candidate groups of four float4: -2x, -2y, -2z, |y|^2 of 4 points }
+                            // stride in float4
     const int *oidx;
     int64_t oidx_bstride;
     const float *cand_orig;  // [cand batches][M][3] candidates in ORIGINAL order (temporal seeding), may be null
@@ -452,23 +455,21 @@ __device__ __forceinline__ bool sphere_needed(const float4 e, const float lim, c
     return need;
 }
 
-// Search one cluster staged as (-2y, |y|^2) for the warp's 128 queries; returns true when a query of this lane
+// Search one cluster, read as expanded groups (-2y, |y|^2) straight from L1, for the warp's 128 queries; returns true when a query of this lane
 // improved.  thr[q] = best[q] - |x_q|^2 (1 - s) + s (|c| + r)^2.
 template <int TILE>
-__device__ __forceinline__ bool sphere_search_tile(const float *smx, const float *smy, const float *smz, const float *sy2,
+__device__ __forceinline__ bool sphere_search_tile(const float4 *__restrict__ xp_tile,
                                                    const float *__restrict__ planes_tile, int64_t Mp,
                                                    const int *__restrict__ oidx_tile, const float (&qx)[CU_QPT],
                                                    const float (&qy)[CU_QPT], const float (&qz)[CU_QPT],
                                                    const float (&thr)[CU_QPT], float (&best)[CU_QPT],
                                                    int (&bidx)[CU_QPT]) {
-    const float4 *X = reinterpret_cast<const float4 *>(smx);
-    const float4 *Y = reinterpret_cast<const float4 *>(smy);
-    const float4 *Z = reinterpret_cast<const float4 *>(smz);
-    const float4 *W = reinterpret_cast<const float4 *>(sy2);
     bool improved = false;
 #pragma unroll 2
     for (int j4 = 0; j4 < TILE / 4; ++j4) {
-        const float4 mx = X[j4], my = Y[j4], mz = Z[j4], y2 = W[j4];
+        // warp-uniform addresses: every load is one broadcast request served by L1
+        const float4 mx = __ldg(xp_tile + 4 * j4), my = __ldg(xp_tile + 4 * j4 + 1), mz = __ldg(xp_tile + 4 * j4 + 2),
+                     y2 = __ldg(xp_tile + 4 * j4 + 3);
         const float2 mx0 = make_float2(mx.x, mx.y), mx1 = make_float2(mx.z, mx.w);
         const float2 my0 = make_float2(my.x, my.y), my1 = make_float2(my.z, my.w);
         const float2 mz0 = make_float2(mz.x, mz.y), mz1 = make_float2(mz.z, mz.w);
@@ -515,17 +516,17 @@ __device__ __forceinline__ bool sphere_search_tile(const float *smx, const float
     return improved;
 }
 
-template <int TILE>
-__global__ void __launch_bounds__(CU_WARPS * 32, 5) nn_sphere_kernel(const SphereParams p) {
+template <int TILE, int MINB>
+__global__ void __launch_bounds__(CU_WARPS * 32, MINB) nn_sphere_kernel(const SphereParams p) {
     constexpr int ST = TILE < 32 ? 32 : TILE;
-    __shared__ __align__(16) float stile[CU_WARPS][4][ST];
+    __shared__ __align__(16) float stile[CU_WARPS][3][ST];  // canonical fallback path only
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int64_t group = int64_t(blockIdx.x) * CU_WARPS + warp;
     const int64_t q0 = group * CU_GROUP;
     if (q0 >= p.N) return;
     const int b0 = blockIdx.y * p.frames_per_cta;
     const int b1 = (b0 + p.frames_per_cta < p.batches) ? b0 + p.frames_per_cta : p.batches;
-    float *smx = stile[warp][0], *smy = stile[warp][1], *smz = stile[warp][2], *sy2 = stile[warp][3];
+    float *smx = stile[warp][0], *smy = stile[warp][1], *smz = stile[warp][2];
     float qx[CU_QPT], qy[CU_QPT], qz[CU_QPT], best[CU_QPT], xs[CU_QPT];
     int bidx[CU_QPT];
     bool canonical = false;  // warp-uniform: a query too large for the expanded forms
@@ -608,61 +609,52 @@ __global__ void __launch_bounds__(CU_WARPS * 32, 5) nn_sphere_kernel(const Spher
             a2[1] = make_float2(a[2], a[3]);
         };
         refresh();
-        const float4 *t0 = tab, *t1 = tab + 2 * p.n0, *t2 = tab + 2 * (p.n0 + p.n1);
-        // four sibling spheres at a time (independent loads and FMA chains); bit i of the result is warp-uniform
-        auto test4 = [&](const float4 *lvl, int first, int n) -> unsigned {
+        // entry index space: level 0 at [0, n0p), level 1 at [n0p, n0p + n1p), level 2 behind; n0p = 4 n1, n1p = 4 n2
+        const int n0p = 4 * p.n1, n1p = 4 * p.n2, n2p = (p.n2 + 3) & ~3;
+        const float4 *xp = tab + 2 * (n0p + n1p + n2p);
+        // four sibling spheres at a time (one 128-byte line, independent FMA chains); bit i of the result is warp-uniform
+        auto test4 = [&](int first) -> unsigned {
+            const float4 *g = tab + 2 * first;
             float4 e[4];
             float lim[4];
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-                const int s = (first + i < n) ? first + i : n - 1;
-                e[i] = __ldg(lvl + 2 * s);
-                lim[i] = __ldg(reinterpret_cast<const float *>(lvl + 2 * s + 1));
+                e[i] = __ldg(g + 2 * i);
+                lim[i] = __ldg(reinterpret_cast<const float *>(g + 2 * i + 1));
             }
             unsigned mask = 0;
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-                const bool need = (first + i < n) && (canonical || sphere_needed(e[i], lim[i], qx2, qy2, qz2, sq2, a2));
+                // canonical mode asks for everything that is not padding (lim != NaN)
+                const bool need = canonical ? (lim[i] == lim[i]) : sphere_needed(e[i], lim[i], qx2, qy2, qz2, sq2, a2);
                 if (__ballot_sync(0xffffffffu, need)) mask |= 1u << i;
             }
             return mask;
         };
-        for (int u0 = 0; u0 < p.n2; u0 += 4) {
-            unsigned m2 = test4(t2, u0, p.n2);
+        for (int u0 = 0; u0 < n2p; u0 += 4) {
+            unsigned m2 = test4(n0p + n1p + u0);
             while (m2) {
                 const int u = u0 + __ffs(m2) - 1;
                 m2 &= m2 - 1;
-                unsigned m1 = test4(t1, 4 * u, p.n1);
+                unsigned m1 = test4(n0p + 4 * u);
                 while (m1) {
                     const int m = 4 * u + __ffs(m1) - 1;
                     m1 &= m1 - 1;
-                    unsigned m0 = test4(t0, 4 * m, p.n0);
+                    unsigned m0 = test4(4 * m);
                     while (m0) {
                         const int c = 4 * m + __ffs(m0) - 1;
                         m0 &= m0 - 1;
-                        const int64_t j0 = int64_t(c) * TILE;
-                        bool improved;
-                        __syncwarp();
+                        const int j0 = c * TILE;
+                        ++searched;
                         if (!canonical) {
-                            if (TILE >= 32 || lane < TILE) {
-#pragma unroll
-                                for (int cc = 0; cc < TILE; cc += 32) {
-                                    const float x = planes[j0 + cc + lane], y = planes[p.Mp + j0 + cc + lane];
-                                    const float z = planes[2 * p.Mp + j0 + cc + lane];
-                                    smx[cc + lane] = -2.0f * x;
-                                    smy[cc + lane] = -2.0f * y;
-                                    smz[cc + lane] = -2.0f * z;
-                                    sy2[cc + lane] = fmaf(z, z, fmaf(y, y, x * x));
-                                }
-                            }
-                            const float cr2s = SPH_SLACK * __ldg(reinterpret_cast<const float *>(t0 + 2 * c + 1) + 1);
+                            const float cr2s = SPH_SLACK * __ldg(reinterpret_cast<const float *>(tab + 2 * c + 1) + 1);
                             float thr[CU_QPT];
 #pragma unroll
                             for (int k = 0; k < CU_QPT; ++k) thr[k] = thrb[k] + cr2s;
-                            __syncwarp();
-                            improved = sphere_search_tile<TILE>(smx, smy, smz, sy2, planes + j0, p.Mp, oidx + j0, qx, qy, qz,
-                                                                thr, best, bidx);
+                            if (sphere_search_tile<TILE>(xp + j0, planes + j0, p.Mp, oidx + j0, qx, qy, qz, thr, best, bidx))
+                                refresh();
                         } else {
+                            __syncwarp();
                             if (TILE >= 32 || lane < TILE) {
 #pragma unroll
                                 for (int cc = 0; cc < TILE; cc += 32) {
@@ -673,10 +665,7 @@ __global__ void __launch_bounds__(CU_WARPS * 32, 5) nn_sphere_kernel(const Spher
                             }
                             __syncwarp();
                             cu_search_tile<TILE>(smx, smy, smz, oidx + j0, qx, qy, qz, best, bidx);
-                            improved = false;
                         }
-                        if (improved) refresh();
-                        ++searched;
                     }
                 }
             }
@@ -698,20 +687,45 @@ __global__ void __launch_bounds__(CU_WARPS * 32, 5) nn_sphere_kernel(const Spher
     if (p.tiles_searched && lane == 0) atomicAdd(p.tiles_searched, searched);
 }
 
-// one thread per sphere of any level: box centre of the finite member points, covering radius (inflated), stored in
-// the expanded-test form (see above)
-__global__ void sphere_table_kernel(const float *__restrict__ planes, int64_t M, int64_t Mp, int tile, int n0, int n1,
-                                    int n2, float4 *__restrict__ table) {
+// Padded level sizes of the sphere table (whole sibling groups of 4 on every level).
+struct SphereLayout {
+    int n0, n1, n2, n0p, n1p, n2p;
+    __host__ __device__ SphereLayout(int64_t M, int tile) {
+        n0 = int((M + tile - 1) / tile);
+        n1 = (n0 + 3) / 4;
+        n2 = (n1 + 3) / 4;
+        n0p = 4 * n1;
+        n1p = 4 * n2;
+        n2p = (n2 + 3) & ~3;
+    }
+    __host__ __device__ int entries() const { return n0p + n1p + n2p; }
+    __host__ __device__ int64_t float4s(int tile) const { return 2 * int64_t(entries()) + int64_t(n0p) * tile; }
+};
+
+// one thread per (padded) sphere entry of any level: box centre of the finite member points, covering radius
+// (inflated), stored in the expanded-test form (see above); padding entries are never asked for
+__global__ void sphere_table_kernel(const float *__restrict__ planes, int64_t M, int64_t Mp, int tile,
+                                    float4 *__restrict__ table) {
+    const SphereLayout L(M, tile);
     const int64_t b = blockIdx.y;
     const int e = blockIdx.x * blockDim.x + threadIdx.x;
-    if (e >= n0 + n1 + n2) return;
+    if (e >= L.entries()) return;
     int64_t span = tile, first = e;
-    if (e >= n0 + n1) {
+    int real = L.n0;
+    if (e >= L.n0p + L.n1p) {
         span = int64_t(tile) * 16;
-        first = e - n0 - n1;
-    } else if (e >= n0) {
+        first = e - L.n0p - L.n1p;
+        real = L.n2;
+    } else if (e >= L.n0p) {
         span = int64_t(tile) * 4;
-        first = e - n0;
+        first = e - L.n0p;
+        real = L.n1;
+    }
+    float4 *out = table + b * L.float4s(tile) + 2 * int64_t(e);
+    if (first >= real) {  // padding: NaN limit, every comparison is false
+        out[0] = make_float4(0.f, 0.f, 0.f, 0.f);
+        out[1] = make_float4(__int_as_float(0x7fc00000), 0.f, 0.f, 0.f);
+        return;
     }
     const int64_t j0 = first * span;
     const int64_t j1 = (j0 + span < M) ? j0 + span : M;
@@ -725,8 +739,7 @@ __global__ void sphere_table_kernel(const float *__restrict__ planes, int64_t M,
             lo[2] = fminf(lo[2], z); hi[2] = fmaxf(hi[2], z);
         }
     }
-    float4 *out = table + 2 * (b * int64_t(n0 + n1 + n2) + e);
-    if (lo[0] > hi[0]) {  // no finite member: nothing in here can win; never asked for (lim = -inf)
+    if (lo[0] > hi[0]) {  // no finite member: nothing in here can win; asked for only by queries without any bound
         out[0] = make_float4(0.f, 0.f, 0.f, -2e-30f);
         out[1] = make_float4(-CUDART_INF_F, 0.f, 0.f, 0.f);
         return;
@@ -750,6 +763,32 @@ __global__ void sphere_table_kernel(const float *__restrict__ planes, int64_t M,
     const float cr = sqrtf(c2) + r;
     out[0] = make_float4(-2.f * cx, -2.f * cy, -2.f * cz, -2.f * r);
     out[1] = make_float4((rr - c2) + SPH_SLACK * (c2 + rr), cr * cr * 1.00001f, 0.f, 0.f);
+}
+
+// one thread per group of four sorted candidates: (-2x, -2y, -2z, |y|^2) x 4 behind the sphere entries
+__global__ void sphere_expand_kernel(const float *__restrict__ planes, int64_t M, int64_t Mp, int tile,
+                                     float4 *__restrict__ table) {
+    const SphereLayout L(M, tile);
+    const int64_t b = blockIdx.y;
+    const int64_t g = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (g >= int64_t(L.n0p) * tile / 4) return;
+    const float *P = planes + b * 3 * Mp;
+    float x[4], y[4], z[4], w[4];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        const int64_t j = 4 * g + c;
+        const bool in = j < M;  // beyond M: +inf like the plane padding (never a candidate)
+        const float px = in ? P[j] : CUDART_INF_F, py = in ? P[Mp + j] : CUDART_INF_F, pz = in ? P[2 * Mp + j] : CUDART_INF_F;
+        x[c] = -2.0f * px;
+        y[c] = -2.0f * py;
+        z[c] = -2.0f * pz;
+        w[c] = fmaf(pz, pz, fmaf(py, py, px * px));
+    }
+    float4 *out = table + b * L.float4s(tile) + 2 * int64_t(L.entries()) + 4 * g;
+    out[0] = make_float4(x[0], x[1], x[2], x[3]);
+    out[1] = make_float4(y[0], y[1], y[2], y[3]);
+    out[2] = make_float4(z[0], z[1], z[2], z[3]);
+    out[3] = make_float4(w[0], w[1], w[2], w[3]);
 }
 
 }  // namespace fpv
@@ -851,29 +890,35 @@ int fpv_nn_culled_search(const float *queries, int q_shared, int64_t batches, in
 
 /* ---- sphere-hierarchy mode (tile = 16 or 32 points) ---- */
 size_t fpv_nn_sphere_table_floats(int64_t M, int tile) {
-    const int64_t n0 = ceil_div(M, tile), n1 = ceil_div(n0, 4), n2 = ceil_div(n1, 4);
-    return size_t(n0 + n1 + n2) * 8;
+    if (M <= 0 || (tile != 16 && tile != 32)) return 0;
+    return size_t(SphereLayout(M, tile).float4s(tile)) * 4;
 }
 
 int fpv_nn_sphere_table(const float *planes, int64_t batches, int64_t M, int tile, float *table, fpv_stream_t stream) {
     FPV_CHECK_ARG(planes && table && batches > 0 && M > 0 && batches <= 65535, "fpv_nn_sphere_table: bad arguments");
     FPV_CHECK_ARG(tile == 16 || tile == 32, "fpv_nn_sphere_table: tile must be 16 or 32");
+    FPV_CHECK_ARG((reinterpret_cast<uintptr_t>(table) & 15) == 0, "fpv_nn_sphere_table: table must be 16-byte aligned");
     const int64_t Mp = ceil_div(M, 64) * 64;
-    const int n0 = int(ceil_div(M, tile)), n1 = (n0 + 3) / 4, n2 = (n1 + 3) / 4;
-    dim3 grid((unsigned)ceil_div(n0 + n1 + n2, 128), (unsigned)batches);
-    sphere_table_kernel<<<grid, 128, 0, static_cast<cudaStream_t>(stream)>>>(planes, M, Mp, tile, n0, n1, n2,
-                                                                              reinterpret_cast<float4 *>(table));
+    const SphereLayout L(M, tile);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    dim3 grid((unsigned)ceil_div(L.entries(), 128), (unsigned)batches);
+    sphere_table_kernel<<<grid, 128, 0, st>>>(planes, M, Mp, tile, reinterpret_cast<float4 *>(table));
     FPV_LAUNCH_CHECK("sphere_table_kernel");
+    dim3 grid2((unsigned)ceil_div(int64_t(L.n0p) * tile / 4, 128), (unsigned)batches);
+    sphere_expand_kernel<<<grid2, 128, 0, st>>>(planes, M, Mp, tile, reinterpret_cast<float4 *>(table));
+    FPV_LAUNCH_CHECK("sphere_expand_kernel");
     return FPV_OK;
 }
 
 static int g_sphere_ctas_per_sm = 256;
+static int g_sphere_minb = 8;  // resident CTAs per SM the kernel variant is compiled for (8 -> 64 registers)
 
 /* Frame chunking of the temporally seeded sphere search: the grid is sized to about ctas_per_sm CTAs per SM
  * (more CTAs = better load balance over the heavy-tailed per-group cost, but every chunk pays one unseeded frame). */
 int fpv_nn_sphere_set_chunking(int ctas_per_sm) {
-    FPV_CHECK_ARG(ctas_per_sm >= 1 && ctas_per_sm <= 4096, "fpv_nn_sphere_set_chunking: ctas_per_sm out of range");
-    g_sphere_ctas_per_sm = ctas_per_sm;
+    FPV_CHECK_ARG((ctas_per_sm & 0xffff) >= 1 && (ctas_per_sm & 0xffff) <= 4096, "fpv_nn_sphere_set_chunking: ctas_per_sm out of range");
+    g_sphere_ctas_per_sm = ctas_per_sm & 0xffff;
+    g_sphere_minb = ctas_per_sm >> 16;
     return FPV_OK;
 }
 
@@ -896,11 +941,12 @@ int fpv_nn_sphere_search(const float *queries, int q_shared, int64_t batches, in
     p.Mp = ceil_div(M, 64) * 64;
     p.M = M;
     p.plane_bstride = 3 * p.Mp;
-    p.n0 = int(ceil_div(M, tile));
-    p.n1 = (p.n0 + 3) / 4;
-    p.n2 = (p.n1 + 3) / 4;
+    const SphereLayout L(M, tile);
+    p.n0 = L.n0;
+    p.n1 = L.n1;
+    p.n2 = L.n2;
     p.table = reinterpret_cast<const float4 *>(table);
-    p.table_bstride = 2 * int64_t(p.n0 + p.n1 + p.n2);
+    p.table_bstride = L.float4s(tile);
     p.oidx = orig_idx;
     p.oidx_bstride = p.Mp;
     p.cand_orig = cand_orig;
@@ -929,10 +975,16 @@ int fpv_nn_sphere_search(const float *queries, int q_shared, int64_t batches, in
                           (4.0 + idx_bytes) * double(batches * N),
                       double(batches * N) * double(M));
     }
-    if (tile == 16)
-        nn_sphere_kernel<16><<<grid, CU_WARPS * 32, 0, st>>>(p);
-    else
-        nn_sphere_kernel<32><<<grid, CU_WARPS * 32, 0, st>>>(p);
+    if (tile == 16) {
+        if (g_sphere_minb == 8)
+            nn_sphere_kernel<16, 8><<<grid, CU_WARPS * 32, 0, st>>>(p);
+        else if (g_sphere_minb == 6)
+            nn_sphere_kernel<16, 6><<<grid, CU_WARPS * 32, 0, st>>>(p);
+        else
+            nn_sphere_kernel<16, 5><<<grid, CU_WARPS * 32, 0, st>>>(p);
+    } else {
+        nn_sphere_kernel<32, 5><<<grid, CU_WARPS * 32, 0, st>>>(p);
+    }
     profile_end(st);
     FPV_LAUNCH_CHECK("nn_sphere_kernel");
     return FPV_OK;
