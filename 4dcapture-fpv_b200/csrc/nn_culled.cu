@@ -292,6 +292,20 @@ __global__ void __launch_bounds__(CU_WARPS * 32) nn_culled_kernel(const CulledPa
                 const int l = __ffs(mask) - 1;
                 mask &= mask - 1;
                 if (__shfl_sync(0xffffffffu, lb, l) <= worst) {  // the group's worst distance may have shrunk
+                    // per-query refinement: point-to-box gap (deflated like box_lb) against the query's OWN best
+                    const float *e = boxes + int64_t(t0 + l) * CU_SLOT;
+                    const float lx = __ldg(e), ly = __ldg(e + 1), lz = __ldg(e + 2);
+                    const float hx = __ldg(e + 3), hy = __ldg(e + 4), hz = __ldg(e + 5);
+                    bool need = false;
+#pragma unroll
+                    for (int k = 0; k < CU_QPT; ++k) {
+                        const float gx = fmaxf(fmaxf(lx - qx[k], qx[k] - hx), 0.f);
+                        const float gy = fmaxf(fmaxf(ly - qy[k], qy[k] - hy), 0.f);
+                        const float gz = fmaxf(fmaxf(lz - qz[k], qz[k] - hz), 0.f);
+                        const float g2 = fmaf(gz, gz, fmaf(gy, gy, gx * gx)) * (1.0f - 1.0f / 262144.0f);
+                        need |= g2 <= best[k];  // a NaN query never asks
+                    }
+                    if (!__ballot_sync(0xffffffffu, need)) continue;
                     stage_and_search(t0 + l);
                     worst = group_worst();
                     ++searched;

@@ -480,13 +480,20 @@ __device__ __forceinline__ int fix_exponent(const unsigned *bound, int nb_bits) 
 // registers before touching memory: when the queries arrive in spatial order (the Morton-sorted scene of the
 // spatial path) neighbours share their nearest body vertex and most atomics disappear.  Integer adds are
 // associative, so the merge order cannot change the result.
-constexpr int BWD_RUN = 8;
+static int bwd_run_len() {
+    static int v = [] {
+        const char *e = getenv("FPV_BWD_RUN");
+        const int r = e ? atoi(e) : 8;
+        return r < 1 ? 1 : (r > 4096 ? 4096 : r);
+    }();
+    return v;
+}
 
 template <typename IdxT>
 __global__ void bwd_accum_kernel(const float *__restrict__ x, int64_t x_bstride, int64_t N, const float *__restrict__ y,
                                  int64_t y_bstride, const float *__restrict__ g, const IdxT *__restrict__ idx,
                                  const unsigned *__restrict__ cmax_bits, int nb_bits, int to_y, long long *acc,
-                                 int64_t acc_bstride) {
+                                 int64_t acc_bstride, int BWD_RUN) {
     const int64_t b = blockIdx.y;
     const int64_t i0 = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) * BWD_RUN;
     if (i0 >= N) return;
@@ -585,6 +592,7 @@ static int chamfer_bwd_impl(const float *a, const float *b, int64_t bs, int64_t 
     count_launch();
     count_launch();
     dim3 gridN((unsigned)ceil_div(N, 256), (unsigned)bs), gridM((unsigned)ceil_div(M, 256), (unsigned)bs);
+    const int BWD_RUN = bwd_run_len();
     dim3 gridNr((unsigned)ceil_div(ceil_div(N, BWD_RUN), 256), (unsigned)bs);
     dim3 gridMr((unsigned)ceil_div(ceil_div(M, BWD_RUN), 256), (unsigned)bs);
 
@@ -595,7 +603,7 @@ static int chamfer_bwd_impl(const float *a, const float *b, int64_t bs, int64_t 
         absmax(g_b2a, bs * M, cmax);
         FPV_LAUNCH_CHECK("absmax_kernel");
         bwd_accum_kernel<IdxT><<<gridMr, 256, 0, st>>>(b, b_bstride, M, a, N * 3, g_b2a, i_b2a, cmax, nb_a, 1, acc_a,
-                                                      N * 3);
+                                                      N * 3, BWD_RUN);
         FPV_LAUNCH_CHECK("bwd_accum_kernel");
     }
     bwd_finish_kernel<IdxT><<<gridN, 256, 0, st>>>(a, N, b, b_bstride, g_a2b, i_a2b, cmax, nb_a, acc_a, grad_a);
@@ -615,13 +623,13 @@ static int chamfer_bwd_impl(const float *a, const float *b, int64_t bs, int64_t 
         }
         if (g_a2b) {
             bwd_accum_kernel<IdxT><<<gridNr, 256, 0, st>>>(a, N * 3, N, b, b_bstride, g_a2b, i_a2b, cmax + 4, nb_b, 1,
-                                                          acc_b, b_shared ? 0 : M * 3);
+                                                          acc_b, b_shared ? 0 : M * 3, BWD_RUN);
             FPV_LAUNCH_CHECK("bwd_accum_kernel");
         }
         if (b_shared) {
             if (g_b2a) {
                 bwd_accum_kernel<IdxT><<<gridMr, 256, 0, st>>>(b, 0, M, a, N * 3, g_b2a, i_b2a, cmax + 4, nb_b, 0,
-                                                              acc_b, 0);
+                                                              acc_b, 0, BWD_RUN);
                 FPV_LAUNCH_CHECK("bwd_accum_kernel");
             }
             dim3 grid1((unsigned)ceil_div(M, 256), 1);
