@@ -476,57 +476,62 @@ __device__ __forceinline__ int fix_exponent(const unsigned *bound, int nb_bits) 
 
 // For every (b,i): j = idx[b,i]; c = 2 g (x_i - y_j).  to_y: acc[b*acc_bstride + 3j..] -= c ; else
 // acc[b*acc_bstride + 3i..] += c (used when the target cloud is shared across batches).
-// Each thread walks BWD_RUN consecutive queries and merges consecutive contributions to the same target in
-// registers before touching memory: when the queries arrive in spatial order (the Morton-sorted scene of the
-// spatial path) neighbours share their nearest body vertex and most atomics disappear.  Integer adds are
-// associative, so the merge order cannot change the result.
-static int bwd_run_len() {
-    static int v = [] {
-        const char *e = getenv("FPV_BWD_RUN");
-        const int r = e ? atoi(e) : 8;
-        return r < 1 ? 1 : (r > 4096 ? 4096 : r);
-    }();
-    return v;
-}
+// A warp walks rows of 32 consecutive queries (coalesced loads) and merges runs of consecutive lanes with the same
+// target by a segmented scan before touching memory: when the queries arrive in spatial order (the Morton-sorted
+// scene of the spatial path) neighbours share their nearest body vertex and most atomics disappear.  Integer adds
+// are associative, so the merge order cannot change the result.
+constexpr int BWD_ROWS = 8;  // rows of 32 consecutive elements per warp
 
 template <typename IdxT>
-__global__ void bwd_accum_kernel(const float *__restrict__ x, int64_t x_bstride, int64_t N, const float *__restrict__ y,
-                                 int64_t y_bstride, const float *__restrict__ g, const IdxT *__restrict__ idx,
-                                 const unsigned *__restrict__ cmax_bits, int nb_bits, int to_y, long long *acc,
-                                 int64_t acc_bstride, int BWD_RUN) {
+__global__ void __launch_bounds__(256) bwd_accum_kernel(const float *__restrict__ x, int64_t x_bstride, int64_t N,
+                                                        const float *__restrict__ y, int64_t y_bstride,
+                                                        const float *__restrict__ g, const IdxT *__restrict__ idx,
+                                                        const unsigned *__restrict__ cmax_bits, int nb_bits, int to_y,
+                                                        long long *acc, int64_t acc_bstride) {
     const int64_t b = blockIdx.y;
-    const int64_t i0 = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) * BWD_RUN;
-    if (i0 >= N) return;
+    const int lane = threadIdx.x & 31;
+    const int64_t row0 = (int64_t(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5)) * (32 * BWD_ROWS);
+    if (row0 >= N) return;
     const float scale = ldexpf(1.f, fix_exponent(cmax_bits, nb_bits));
     unsigned long long *base = reinterpret_cast<unsigned long long *>(acc + b * acc_bstride);
-    long long run[3] = {0, 0, 0};
-    int64_t target = -1;
-    const int64_t i1 = (i0 + BWD_RUN < N) ? i0 + BWD_RUN : N;
-    for (int64_t i = i0; i < i1; ++i) {
-        const int64_t j = static_cast<int64_t>(idx[b * N + i]);
-        const int64_t t = to_y ? j : i;
-        if (t != target) {
-            if (target >= 0) {
+    const float *xb = x + b * x_bstride, *yb = y + b * y_bstride;
+#pragma unroll 2
+    for (int r = 0; r < BWD_ROWS; ++r) {
+        const int64_t i = row0 + r * 32 + lane;  // lane-consecutive: index, weight and point loads are coalesced
+        if (row0 + r * 32 >= N) break;
+        const bool valid = i < N;
+        long long v[3] = {0, 0, 0};
+        long long t = -1 - lane;  // a lane past the end is its own empty run
+        if (valid) {
+            const int64_t j = static_cast<int64_t>(idx[b * N + i]);
+            t = to_y ? j : i;
+            const float *xi = xb + 3 * i, *yj = yb + 3 * j;
+            const float g2 = __fmul_rn(2.f, g[b * N + i]);
 #pragma unroll
-                for (int k = 0; k < 3; ++k)
-                    if (run[k] != 0) atomicAdd(base + 3 * target + k, static_cast<unsigned long long>(run[k]));
+            for (int k = 0; k < 3; ++k) {
+                float c = __fmul_rn(g2, __fsub_rn(xi[k], yj[k]));
+                if (to_y) c = -c;
+                v[k] = __float2ll_rn(__fmul_rn(c, scale));
             }
-            target = t;
-            run[0] = run[1] = run[2] = 0;
         }
-        const float *xi = x + b * x_bstride + 3 * i, *yj = y + b * y_bstride + 3 * j;
-        const float g2 = __fmul_rn(2.f, g[b * N + i]);
+        // runs of equal targets over consecutive lanes: segmented inclusive scan, the last lane of a run owns its sum
+        const long long tp = __shfl_up_sync(0xffffffffu, t, 1);
+        const unsigned heads = __ballot_sync(0xffffffffu, lane == 0 || tp != t);
+        const int start = 31 - __clz(heads & (0xffffffffu >> (31 - lane)));
 #pragma unroll
-        for (int k = 0; k < 3; ++k) {
-            float c = __fmul_rn(g2, __fsub_rn(xi[k], yj[k]));
-            if (to_y) c = -c;
-            run[k] += __float2ll_rn(__fmul_rn(c, scale));
+        for (int o = 1; o < 32; o <<= 1) {
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                const long long u = __shfl_up_sync(0xffffffffu, v[k], o);
+                if (lane - o >= start) v[k] += u;
+            }
         }
-    }
-    if (target >= 0) {
+        const bool tail = lane == 31 || ((heads >> (lane + 1)) & 1u);
+        if (tail && t >= 0) {
 #pragma unroll
-        for (int k = 0; k < 3; ++k)
-            if (run[k] != 0) atomicAdd(base + 3 * target + k, static_cast<unsigned long long>(run[k]));
+            for (int k = 0; k < 3; ++k)
+                if (v[k] != 0) atomicAdd(base + 3 * t + k, static_cast<unsigned long long>(v[k]));
+        }
     }
 }
 
@@ -592,9 +597,8 @@ static int chamfer_bwd_impl(const float *a, const float *b, int64_t bs, int64_t 
     count_launch();
     count_launch();
     dim3 gridN((unsigned)ceil_div(N, 256), (unsigned)bs), gridM((unsigned)ceil_div(M, 256), (unsigned)bs);
-    const int BWD_RUN = bwd_run_len();
-    dim3 gridNr((unsigned)ceil_div(ceil_div(N, BWD_RUN), 256), (unsigned)bs);
-    dim3 gridMr((unsigned)ceil_div(ceil_div(M, BWD_RUN), 256), (unsigned)bs);
+    dim3 gridNr((unsigned)ceil_div(N, 256 * BWD_ROWS), (unsigned)bs);
+    dim3 gridMr((unsigned)ceil_div(M, 256 * BWD_ROWS), (unsigned)bs);
 
     // ---- grad_a = 2 g_a2b (a_i - b_idx)  +  sum_{j: i_b2a[j]==i} 2 g_b2a[j] (a_i - b_j)
     const int nb_a = ilog2_ceil(M) + 1;
@@ -603,7 +607,7 @@ static int chamfer_bwd_impl(const float *a, const float *b, int64_t bs, int64_t 
         absmax(g_b2a, bs * M, cmax);
         FPV_LAUNCH_CHECK("absmax_kernel");
         bwd_accum_kernel<IdxT><<<gridMr, 256, 0, st>>>(b, b_bstride, M, a, N * 3, g_b2a, i_b2a, cmax, nb_a, 1, acc_a,
-                                                      N * 3, BWD_RUN);
+                                                      N * 3);
         FPV_LAUNCH_CHECK("bwd_accum_kernel");
     }
     bwd_finish_kernel<IdxT><<<gridN, 256, 0, st>>>(a, N, b, b_bstride, g_a2b, i_a2b, cmax, nb_a, acc_a, grad_a);
@@ -623,13 +627,13 @@ static int chamfer_bwd_impl(const float *a, const float *b, int64_t bs, int64_t 
         }
         if (g_a2b) {
             bwd_accum_kernel<IdxT><<<gridNr, 256, 0, st>>>(a, N * 3, N, b, b_bstride, g_a2b, i_a2b, cmax + 4, nb_b, 1,
-                                                          acc_b, b_shared ? 0 : M * 3, BWD_RUN);
+                                                          acc_b, b_shared ? 0 : M * 3);
             FPV_LAUNCH_CHECK("bwd_accum_kernel");
         }
         if (b_shared) {
             if (g_b2a) {
                 bwd_accum_kernel<IdxT><<<gridMr, 256, 0, st>>>(b, 0, M, a, N * 3, g_b2a, i_b2a, cmax + 4, nb_b, 0,
-                                                              acc_b, 0, BWD_RUN);
+                                                              acc_b, 0);
                 FPV_LAUNCH_CHECK("bwd_accum_kernel");
             }
             dim3 grid1((unsigned)ceil_div(M, 256), 1);
