@@ -584,14 +584,14 @@ __global__ void __launch_bounds__(CU_WARPS * 32, MINB) nn_sphere_kernel(const Sp
                 }
             }
         } else {
-            // seed: the first point of every level-1 group (real candidates)
+            // seed: the first point of every level-2 group (real candidates)
 #pragma unroll
             for (int k = 0; k < CU_QPT; ++k) {
                 best[k] = CUDART_INF_F;
                 bidx[k] = 0;
             }
-            for (int m = 0; m < p.n1; ++m) {
-                const int64_t j = int64_t(m) * 4 * TILE;
+            for (int m = 0; m < p.n2; ++m) {
+                const int64_t j = int64_t(m) * 16 * TILE;
                 const float rx = __ldg(planes + j), ry = __ldg(planes + p.Mp + j), rz = __ldg(planes + 2 * p.Mp + j);
                 const int o = __ldg(oidx + j);
 #pragma unroll
@@ -924,15 +924,13 @@ int fpv_nn_sphere_table(const float *planes, int64_t batches, int64_t M, int til
     return FPV_OK;
 }
 
-static int g_sphere_ctas_per_sm = 256;
-static int g_sphere_minb = 8;  // resident CTAs per SM the kernel variant is compiled for (8 -> 64 registers)
+static int g_sphere_ctas_per_sm = 512;
 
 /* Frame chunking of the temporally seeded sphere search: the grid is sized to about ctas_per_sm CTAs per SM
  * (more CTAs = better load balance over the heavy-tailed per-group cost, but every chunk pays one unseeded frame). */
 int fpv_nn_sphere_set_chunking(int ctas_per_sm) {
-    FPV_CHECK_ARG((ctas_per_sm & 0xffff) >= 1 && (ctas_per_sm & 0xffff) <= 4096, "fpv_nn_sphere_set_chunking: ctas_per_sm out of range");
-    g_sphere_ctas_per_sm = ctas_per_sm & 0xffff;
-    g_sphere_minb = ctas_per_sm >> 16;
+    FPV_CHECK_ARG(ctas_per_sm >= 1 && ctas_per_sm <= 4096, "fpv_nn_sphere_set_chunking: ctas_per_sm out of range");
+    g_sphere_ctas_per_sm = ctas_per_sm;
     return FPV_OK;
 }
 
@@ -989,16 +987,10 @@ int fpv_nn_sphere_search(const float *queries, int q_shared, int64_t batches, in
                           (4.0 + idx_bytes) * double(batches * N),
                       double(batches * N) * double(M));
     }
-    if (tile == 16) {
-        if (g_sphere_minb == 8)
-            nn_sphere_kernel<16, 8><<<grid, CU_WARPS * 32, 0, st>>>(p);
-        else if (g_sphere_minb == 6)
-            nn_sphere_kernel<16, 6><<<grid, CU_WARPS * 32, 0, st>>>(p);
-        else
-            nn_sphere_kernel<16, 5><<<grid, CU_WARPS * 32, 0, st>>>(p);
-    } else {
+    if (tile == 16)
+        nn_sphere_kernel<16, 8><<<grid, CU_WARPS * 32, 0, st>>>(p);  // 64 registers, 32 resident warps: latency-bound
+    else
         nn_sphere_kernel<32, 5><<<grid, CU_WARPS * 32, 0, st>>>(p);
-    }
     profile_end(st);
     FPV_LAUNCH_CHECK("nn_sphere_kernel");
     return FPV_OK;

@@ -99,7 +99,7 @@ int fpv_nn_culled_search(const float *queries, int q_shared, int64_t batches, in
                          unsigned long long *tiles_searched, fpv_stream_t stream);
 
 /* Frame chunking of fpv_nn_sphere_search with temporal seeding: size the grid to about ctas_per_sm CTAs per SM
- * (default 256).  More chunks balance the heavy-tailed per-group cost; every chunk pays one unseeded frame. */
+ * (default 512).  More chunks balance the heavy-tailed per-group cost; every chunk pays one unseeded frame. */
 int fpv_nn_sphere_set_chunking(int ctas_per_sm);
 
 /* Sphere-hierarchy variant for moving candidate sets (scene -> body): clusters of `tile` (16 | 32) sorted points
