@@ -135,6 +135,23 @@ def cpu_reference_step(T: int, M: int, budget_s: float = 12.0, seed: int = 1235)
     return 1.0 / t_full, cores, sample, t_ch + t_smplx + t_probe
 
 
+def ncu_traffic(kernel_name, args, world):
+    """DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture (profiles/), or None when
+    the capture does not describe this workload."""
+    try:
+        with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r01_dram_traffic.json")) as f:
+            rec = json.load(f)
+    except (OSError, ValueError):
+        return None
+    w = rec.get("workload", {})
+    if (w.get("frames"), w.get("scene_points"), w.get("n_gpus")) != (args.T, args.M, world):
+        return None
+    for key, val in rec.items():
+        if isinstance(val, (int, float)) and kernel_name.startswith(key):
+            return float(val)
+    return None
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -261,7 +278,7 @@ def run_b200(args):
                     "note": "co-limited by the fp32 min-reduction of the accumulators on the ALU pipe (profiles/r01_nn_tc_ncu.md)"}
     else:
         roofline = {"bound": "hbm", "kernel": dom[0], "achieved": hbm_gbs, "peak": hbm_peak, "unit": "GB/s",
-                    "frac": hbm_gbs / hbm_peak, "traffic": None, "peak_source": peak_src,
+                    "frac": hbm_gbs / hbm_peak, "traffic": ncu_traffic(dom[0], args, world), "peak_source": peak_src,
                     "algorithmic_bytes_per_launch": dbytes, "ms_per_launch": dms}
         if dom[0].startswith("nn_culled") or dom[0].startswith("nn_sphere"):
             ch = importlib.import_module("4dcapture-fpv_b200.chamfer")
