@@ -990,7 +990,7 @@ int fpv_nn_sphere_search(const float *queries, int q_shared, int64_t batches, in
     if (tile == 16)
         nn_sphere_kernel<16, 8><<<grid, CU_WARPS * 32, 0, st>>>(p);  // 64 registers, 32 resident warps: latency-bound
     else
-        nn_sphere_kernel<32, 5><<<grid, CU_WARPS * 32, 0, st>>>(p);
+        nn_sphere_kernel<32, 8><<<grid, CU_WARPS * 32, 0, st>>>(p);
     profile_end(st);
     FPV_LAUNCH_CHECK("nn_sphere_kernel");
     return FPV_OK;

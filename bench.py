@@ -246,6 +246,21 @@ def run_b200(args):
     barrier()
     ms_e2e = max_over_ranks(max(e0.elapsed_time(e1), 0.0))
     wall_e2e = time.perf_counter() - t0
+    # ---- informational: the same step replayed as one CUDA graph (single rank) ----
+    graph_info = None
+    if world == 1 and not args.no_graph:
+        try:
+            prob.capture()
+            prob.step_graph()
+            torch.cuda.synchronize(dev)
+            e0.record()
+            for _ in range(K):
+                prob.step_graph()
+            e1.record()
+            torch.cuda.synchronize(dev)
+            graph_info = {"steps_per_s": K / (e0.elapsed_time(e1) * 1e-3), "ms_per_step": e0.elapsed_time(e1) / K}
+        except Exception as ex:  # capture is an optimisation of the host side, never the measured product path
+            graph_info = {"error": str(ex)[:200]}
     clocks = sampler.stop() if rank == 0 else None
     if rank != 0:
         if world > 1:
@@ -311,7 +326,7 @@ def run_b200(args):
         "roofline": roofline,
         "e2e": {"value": K / (ms_e2e * 1e-3), "unit": "steps/s", "h2d_bytes_per_step": prob.h2d_bytes(),
                 "d2h_bytes_per_step": prob.d2h_bytes(), "wall_s": wall_e2e},
-        "gpu_launches": launches, "clocks": clocks, "fp32_lane_fma_per_s_measured": fma.value,
+        "gpu_launches": launches, "cuda_graph_replay": graph_info, "clocks": clocks, "fp32_lane_fma_per_s_measured": fma.value,
         "nn_kernels_share_of_step": kernel_ms / (ms_total / K),
         "kernels": {k: {"launches_per_step": len(v) / K, "ms_mean": statistics.mean(x[0] for x in v)} for k, v in by.items()},
     }
@@ -334,6 +349,7 @@ def main():
     ap.add_argument("--M", type=int, default=1_000_000)
     ap.add_argument("--idx64", action="store_true", help="reference-faithful int64 index outputs")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="skip the informational CUDA-graph replay leg")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -55,3 +55,24 @@ def test_fit_step_matches_oracle(fpv, cuda_dev):
     assert l2.item() == loss.item()                                   # same inputs -> bitwise same loss
     host = prob.step_e2e()
     assert host[0].item() == pytest.approx(ref_loss, rel=2e-5) and host[1].shape == (6, 106)
+
+
+def test_fit_step_cuda_graph_replay_matches_eager(fpv, cuda_dev):
+    """f1: the whole step captured as one CUDA graph reproduces the eager step bit for bit (the kernels are
+    deterministic), and follows in-place parameter updates between replays."""
+    prob = fpv.FitProblem(T=5, M=12000, device=cuda_dev, seed=1237)
+    loss_e = prob.step().clone()
+    grads_e = [t.grad.clone() for t in prob.leaves()]
+    prob.capture()
+    loss_g = prob.step_graph().clone()
+    assert torch.equal(loss_g, loss_e)
+    for g, t in zip(grads_e, prob.leaves()):
+        assert torch.equal(t.grad, g)
+    with torch.no_grad():
+        prob.params.add_(0.003 * torch.randn_like(prob.params))
+    loss_g2 = prob.step_graph().clone()
+    grads_g2 = [t.grad.clone() for t in prob.leaves()]
+    loss_e2 = prob.step().clone()
+    assert torch.equal(loss_g2, loss_e2)
+    for g, t in zip(grads_g2, prob.leaves()):
+        assert torch.equal(t.grad, g)

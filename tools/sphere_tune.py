@@ -10,6 +10,8 @@ dev = torch.device("cuda:0")
 T = int(sys.argv[1]) if len(sys.argv) > 1 else 300
 M = int(sys.argv[2]) if len(sys.argv) > 2 else 1_000_000
 sweep = [int(x) for x in sys.argv[3].split(",")] if len(sys.argv) > 3 else [16, 32, 64, 128, 256, 512]
+if len(sys.argv) > 4:
+    ch.SPHERE_TILE = int(sys.argv[4])
 prob = fpv.FitProblem(T=T, M=M, device=dev, seed=1235)
 with torch.no_grad():
     p = prob.params
