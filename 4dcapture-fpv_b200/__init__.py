@@ -9,6 +9,8 @@ Public surface (each mirrors a reference signature, see the module docstrings):
     create(...), SMPLXB200                                body_model.py
     verts_transform, body2world, contact_robust_loss,
     second_diff_l1, first_diff_l1                         residuals.py
+    convert_to_3D_rot, convert_to_6D_rot,
+    VPoserDecoderB200, cal_dctloss                        prior.py   
     distChamferSharded, allreduce_grads, shard_range      sharded.py
     FitProblem                                            fit.py
 Everything computes on an sm_100 GPU through libfpv_b200.so; there is no CPU or eager fallback.
@@ -19,6 +21,8 @@ from .chamfer import chamferDist, distChamfer, nn_search, pack_planes, unpack_ke
 from .fit import FitProblem, LOSS_WEIGHTS  # noqa: F401
 from .residuals import (body2world, contact_robust_loss, first_diff_l1, second_diff_l1,  # noqa: F401
                         verts_transform)
+from .prior import (VPoserDecoderB200, aa_to_rot6d, body_params_encapsulate_batch, cal_dctloss,  # noqa: F401
+                    convert_to_3D_rot, convert_to_6D_rot, dct_basis, make_vposer_weights, rot6d_to_aa)
 from .sharded import allreduce_grads, combine_keys, distChamferSharded, shard_range  # noqa: F401
 from . import synthetic  # noqa: F401
 

@@ -27,6 +27,15 @@ class SmplxModelStruct(ctypes.Structure):
     ]
 
 
+class VposerModelStruct(ctypes.Structure):
+    """Mirror of fpv_vposer_model."""
+    _fields_ = [
+        ("w1", c_void_p), ("b1", c_void_p), ("w2", c_void_p), ("b2", c_void_p), ("w3", c_void_p), ("b3", c_void_p),
+        ("w1t", c_void_p), ("w2t", c_void_p), ("w3t", c_void_p),
+        ("latent", c_int), ("hidden", c_int), ("joints", c_int),
+    ]
+
+
 # name -> (restype, argtypes); every symbol include/fpv_b200.h declares
 SIGNATURES = {
     "fpv_last_error": (c_char_p, []),
@@ -82,6 +91,17 @@ SIGNATURES = {
                               c_void_p, c_size_t, c_void_p]),
     "fpv_smplx_bwd": (c_int, [POINTER(SmplxModelStruct), c_int64, c_void_p, c_void_p, c_void_p, c_void_p,
                               c_void_p, c_void_p, c_size_t, c_void_p]),
+    "fpv_rot6d_to_aa_fwd": (c_int, [c_void_p, c_int64, c_void_p, c_void_p]),
+    "fpv_rot6d_to_aa_bwd": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p]),
+    "fpv_aa_to_rot6d": (c_int, [c_void_p, c_int64, c_void_p, c_void_p]),
+    "fpv_vposer_saved_floats": (c_size_t, [POINTER(VposerModelStruct), c_int64]),
+    "fpv_vposer_decode_fwd": (c_int, [POINTER(VposerModelStruct), c_void_p, c_int64, c_void_p, c_void_p, c_void_p]),
+    "fpv_vposer_decode_bwd": (c_int, [POINTER(VposerModelStruct), c_void_p, c_void_p, c_int64, c_void_p, c_void_p]),
+    "fpv_dct_prior_workspace_bytes": (c_size_t, [c_int64, c_int64, c_int64]),
+    "fpv_dct_prior_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int64, c_void_p,
+                                  c_void_p, c_size_t, c_void_p]),
+    "fpv_dct_prior_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int64, c_void_p,
+                                  c_void_p, c_void_p, c_void_p]),
 }
 
 _lib = None

@@ -229,6 +229,36 @@ int fpv_tc_gemm_3xtf32(const float *a_hi, const float *a_lo, int64_t lda, const 
                        const float *b_lo, int64_t ldb, int M, int N, int K, float *C, int64_t ldc,
                        int ksplit, void *workspace, size_t workspace_bytes, fpv_stream_t stream);
 
+/* ---- parameter front-end and trajectory prior -------------------------
+ * rot6d <-> axis-angle: convert_to_3D_rot / convert_to_6D_rot (global_optimization.py:96-115) on n rotations.
+ * in6 / out6 [n][6] = the (3,2) matrix of the first two rotation columns, row-major, as cvae.py:72 views it. */
+int fpv_rot6d_to_aa_fwd(const float *in6, int64_t n, float *aa, fpv_stream_t stream);
+int fpv_rot6d_to_aa_bwd(const float *in6, int64_t n, const float *g_aa, float *g_in6, fpv_stream_t stream);
+int fpv_aa_to_rot6d(const float *aa, int64_t n, float *out6, fpv_stream_t stream);
+
+/* VPoser v1 decoder, output_type='aa' (call site global_optimization.py:270-271).  Device pointers to the three
+ * nn.Linear layers in their own [out][in] layout (w*) and transposed [in][out] copies (w*t). */
+typedef struct fpv_vposer_model {
+    const float *w1, *b1, *w2, *b2, *w3, *b3; /* [hidden][latent], [hidden][hidden], [6*joints][hidden] */
+    const float *w1t, *w2t, *w3t;             /* [latent][hidden], [hidden][hidden], [hidden][6*joints] */
+    int latent, hidden, joints;               /* 32, 512, 21 */
+} fpv_vposer_model;
+size_t fpv_vposer_saved_floats(const fpv_vposer_model *m, int64_t T);
+/* z [T][latent] -> aa [T][joints][3]; saved: fpv_vposer_saved_floats(m, T) floats kept for the backward */
+int fpv_vposer_decode_fwd(const fpv_vposer_model *m, const float *z, int64_t T, float *aa, float *saved,
+                          fpv_stream_t stream);
+int fpv_vposer_decode_bwd(const fpv_vposer_model *m, const float *saved, const float *g_aa, int64_t T, float *g_z,
+                          fpv_stream_t stream);
+
+/* DCT trajectory prior, FittingOP.cal_dctloss (global_optimization.py:232-246): x [NB*F][C] trajectories (C = 23
+ * joints x 3 axes), basis [F][K], coef [NB][C][K]; out = mean over NB*C of sum_f e/(e+1), e = (x - basis.coef)^2.
+ * grad_x / grad_coef may be NULL. */
+size_t fpv_dct_prior_workspace_bytes(int64_t NB, int64_t F, int64_t C);
+int fpv_dct_prior_fwd(const float *x, const float *basis, const float *coef, int64_t NB, int64_t F, int64_t C,
+                      int64_t K, float *out, void *workspace, size_t workspace_bytes, fpv_stream_t stream);
+int fpv_dct_prior_bwd(const float *x, const float *basis, const float *coef, int64_t NB, int64_t F, int64_t C,
+                      int64_t K, const float *g_out, float *grad_x, float *grad_coef, fpv_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -50,7 +50,8 @@ def cuda_dev():
 
 
 def golden_cases():
-    return sorted(f[:-4] for f in os.listdir(GOLDEN) if f.endswith(".npz"))
+    """Chamfer goldens (tests/golden/make_golden.py); the prior_*.npz files belong to test_*prior*.py."""
+    return sorted(f[:-4] for f in os.listdir(GOLDEN) if f.endswith(".npz") and not f.startswith("prior_"))
 
 
 def load_golden(name):
