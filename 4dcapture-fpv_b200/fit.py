@@ -10,8 +10,9 @@ Mirrors FittingOP.cal_loss + loss.backward() of /root/reference/global_optimizat
         vertex 2nd-difference (cal_loss2 :404-405), reconstruction L1 (:259)
     ->  backward to the per-frame parameters, scale and camera_ext.
 
-Out of scope here (SURVEY.md section 8f "next" rows): VPoser decode and the 6D rotation codec (the
-optimised variable is the axis-angle parameter row directly), the DCT prior, the Adam update.
+front_end=True adds the reference's parameter front-end and the `dct` prior (prior.py):
+the optimised variable becomes the 78-D 6D-rotation row with the VPoser latent, decoded every step.  The default
+(front_end=False) optimises the axis-angle parameter row directly.  The Adam update stays outside the step.
 With world_size > 1 the scene is sharded across ranks (sharded.py).
 """
 from __future__ import annotations
@@ -21,7 +22,7 @@ from typing import Dict, Optional
 import torch
 import torch.distributed as dist
 
-from . import chamfer, residuals, sharded
+from . import chamfer, prior, residuals, sharded
 from .body_model import SMPLXB200
 from .synthetic import make_body_constants, make_clip_params, make_scene
 
@@ -30,7 +31,14 @@ from .synthetic import make_body_constants, make_clip_params, make_scene
 P_TRANSL, P_ORIENT, P_BETAS, P_POSE, P_LH, P_RH, P_CAM = (0, 3), (3, 6), (6, 16), (16, 79), (79, 91), (91, 103), (103, 106)
 PARAM_DIM = 106
 
-LOSS_WEIGHTS = dict(rec=1.0, contact=0.1, smoothing=1.0, world_smoothing=1.0, vert_smoothing=0.5, scene2body=0.1)
+LOSS_WEIGHTS = dict(rec=1.0, contact=0.1, smoothing=1.0, world_smoothing=1.0, vert_smoothing=0.5, scene2body=0.1,
+                    vposer=0.001, dct=0.0001)   # vposer: global_optimization.py:683; dct: the weight of the `dct` mode (:620)
+
+# front_end=True: the reference's own optimisation variable (global_optimization.py:96-104, :454): the 78-D row
+#   [transl 0:3 | rot6d 3:9 | betas 9:19 | vposer latent 19:51 | lh 51:63 | rh 63:75 | cam_transl 75:78]
+# decoded every step by convert_to_3D_rot + VPoser.decode before the body model.
+FRONT_END_DIM = 78
+DCT_FRAMES, DCT_NUM = 60, 5   # BATCH_FRAME_NUM, DCT_NUM (global_optimization.py:41-44)
 
 
 def pack_params(p: Dict[str, torch.Tensor]) -> torch.Tensor:
@@ -61,7 +69,8 @@ class FitProblem:
     """Synthetic clip + scene + body model on one device, and the per-step forward/backward."""
 
     def __init__(self, T: int, M: int, device, seed: int = 1234, scene_kind: str = "uniform",
-                 rank: int = 0, world_size: int = 1, group=None, idx_dtype=torch.int64, presort_scene: bool = True):
+                 rank: int = 0, world_size: int = 1, group=None, idx_dtype=torch.int64, presort_scene: bool = True,
+                 front_end: bool = False, dct_frames: int = DCT_FRAMES):
         self.T, self.M, self.device = T, M, torch.device(device)
         self.rank, self.world, self.group = rank, world_size, group
         self.idx_dtype = idx_dtype
@@ -69,7 +78,21 @@ class FitProblem:
         self.constants = constants
         self.model = SMPLXB200(constants, batch_size=T).to(self.device)
         clip = make_clip_params(T, seed)
-        self.host_params = pack_params(clip)                           # [T,106] observed data (CPU)
+        self.front_end = front_end
+        if front_end:
+            self.vposer = prior.VPoserDecoderB200(prior.make_vposer_weights(seed)).to(self.device)
+            g = torch.Generator().manual_seed(seed + 77)
+            latent = torch.clamp(torch.cumsum(torch.randn(T, 32, generator=g) * 0.02, 0), -2.0, 2.0)
+            row75 = torch.cat([clip["transl"], clip["global_orient"], clip["betas"], latent, clip["left_hand_pose"],
+                               clip["right_hand_pose"], clip["cam_transl"]], dim=1)
+            # the observed data in the 6D form, converted once like the reference's loader does (:96-104)
+            self.host_params = prior.convert_to_6D_rot(row75.to(self.device)).cpu().contiguous()      # [T,78]
+            self.dct_batches = T // dct_frames
+            if self.dct_batches:
+                self.dct_mtx = prior.dct_basis(dct_frames, min(DCT_NUM, dct_frames), self.device)
+                self.host_c_dct = torch.randn(self.dct_batches, 23, 3, self.dct_mtx.shape[1], generator=g)   # :186
+        else:
+            self.host_params = pack_params(clip)                       # [T,106] observed data (CPU)
         self.host_scene = make_scene(M, scene_kind, seed)              # [M,3] (CPU)
         self.host_camera_ext = clip["camera_ext"].clone()
         self.host_scale = clip["scale"].clone().reshape(1)
@@ -111,26 +134,42 @@ class FitProblem:
         self.scale = self.host_scale.to(dev, non_blocking=non_blocking).requires_grad_(True)
         self.camera_ext = self.host_camera_ext.to(dev, non_blocking=non_blocking).requires_grad_(True)
         self.scene = self.host_scene[self.begin:self.end].to(dev, non_blocking=non_blocking).unsqueeze(0)
+        if self.front_end and self.dct_batches:
+            if dev.type == "cuda" and not self.host_c_dct.is_pinned():
+                self.host_c_dct = self.host_c_dct.pin_memory()
+            self.c_dct = self.host_c_dct.to(dev, non_blocking=non_blocking).requires_grad_(True)
         return self
 
     def h2d_bytes(self) -> int:
+        extra = self.host_c_dct.numel() if (self.front_end and self.dct_batches) else 0
         return 4 * (self.host_params.numel() * 2 + self.host_scale.numel() + self.host_camera_ext.numel()
-                    + (self.end - self.begin) * 3)
+                    + (self.end - self.begin) * 3 + extra)
 
     def d2h_bytes(self) -> int:
-        return 4 * (1 + self.params.numel() + self.scale.numel() + self.camera_ext.numel())
+        return 4 * (1 + sum(t.numel() for t in self.leaves()))
 
     def leaves(self):
-        return [self.params, self.scale, self.camera_ext]
+        extra = [self.c_dct] if (self.front_end and self.dct_batches) else []
+        return [self.params, self.scale, self.camera_ext] + extra
 
     def forward(self) -> Dict[str, torch.Tensor]:
         p, W = self.params, LOSS_WEIGHTS
         sl = lambda r: p[:, r[0]:r[1]]
         inv_world = 1.0 / self.world
-        b2w = residuals.body2world(sl(P_CAM), self.scale, self.camera_ext)
-        out = self.model(return_verts=True, body_pose=sl(P_POSE), transl=sl(P_TRANSL),
-                         global_orient=sl(P_ORIENT), betas=sl(P_BETAS),
-                         left_hand_pose=sl(P_LH), right_hand_pose=sl(P_RH))
+        extra_losses = {}
+        if self.front_end:
+            # global_optimization.py:261-283: 6D row -> axis-angle row -> VPoser decode -> body model
+            bp = prior.body_params_encapsulate_batch(prior.convert_to_3D_rot(p))
+            z = bp.pop("body_pose_vp")
+            cam_transl = bp.pop("camera_translation")
+            extra_losses["vposer"] = torch.mean(z ** 2) * inv_world
+            b2w = residuals.body2world(cam_transl, self.scale, self.camera_ext)
+            out = self.model(return_verts=True, body_pose=self.vposer.decode(z, output_type="aa").view(self.T, -1), **bp)
+        else:
+            b2w = residuals.body2world(sl(P_CAM), self.scale, self.camera_ext)
+            out = self.model(return_verts=True, body_pose=sl(P_POSE), transl=sl(P_TRANSL),
+                             global_orient=sl(P_ORIENT), betas=sl(P_BETAS),
+                             left_hand_pose=sl(P_LH), right_hand_pose=sl(P_RH))
         verts = residuals.verts_transform(out.vertices * self.scale, b2w)
         joints = residuals.verts_transform(out.joints[:, 0:23, :].contiguous() * self.scale, b2w)
         if self.world > 1:
@@ -145,6 +184,9 @@ class FitProblem:
             "world_smoothing": residuals.first_diff_l1(joints) * inv_world,
             "vert_smoothing": residuals.second_diff_l1(verts) * inv_world,
         }
+        if self.front_end and self.dct_batches:
+            extra_losses["dct"] = prior.cal_dctloss(joints, self.dct_mtx, self.c_dct) * inv_world      # :310
+        losses.update(extra_losses)
         losses["total"] = sum(W[k] * v for k, v in losses.items())
         return losses
 

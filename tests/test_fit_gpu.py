@@ -4,6 +4,7 @@ import pytest
 import torch
 
 from oracle import chamfer_oracle as co
+from oracle import prior_oracle as po
 from oracle import residuals_oracle as ro
 from oracle import smplx_oracle as so
 
@@ -19,10 +20,22 @@ def _oracle_step(fpv, prob):
     cam = prob.camera_ext.detach().cpu().double().requires_grad_(True)
     data = prob.data.cpu().double()
     sl = lambda r: p[:, r[0]:r[1]]
-    b2w = ro.body2world(sl(fit.P_CAM), scale, cam)
-    v, j = so.smplx_forward(prob.constants, betas=sl(fit.P_BETAS), global_orient=sl(fit.P_ORIENT),
-                            body_pose=sl(fit.P_POSE), transl=sl(fit.P_TRANSL), left_hand_pose=sl(fit.P_LH),
-                            right_hand_pose=sl(fit.P_RH), dtype=torch.float64)
+    extra = {}
+    c_dct = None
+    if prob.front_end:
+        r75 = po.convert_to_3D_rot(p)
+        z = r75[:, 16:48]
+        extra["vposer"] = torch.mean(z ** 2)
+        wd = {k: getattr(prob.vposer, k).detach().cpu().double() for k in ("w1", "b1", "w2", "b2", "w3", "b3")}
+        b2w = ro.body2world(r75[:, 72:75], scale, cam)
+        v, j = so.smplx_forward(prob.constants, betas=r75[:, 6:16], global_orient=r75[:, 3:6],
+                                body_pose=po.vposer_decode_aa(wd, z).view(p.shape[0], -1), transl=r75[:, 0:3],
+                                left_hand_pose=r75[:, 48:60], right_hand_pose=r75[:, 60:72], dtype=torch.float64)
+    else:
+        b2w = ro.body2world(sl(fit.P_CAM), scale, cam)
+        v, j = so.smplx_forward(prob.constants, betas=sl(fit.P_BETAS), global_orient=sl(fit.P_ORIENT),
+                                body_pose=sl(fit.P_POSE), transl=sl(fit.P_TRANSL), left_hand_pose=sl(fit.P_LH),
+                                right_hand_pose=sl(fit.P_RH), dtype=torch.float64)
     verts = ro.verts_transform(v * scale, b2w)
     joints = ro.verts_transform(j[:, 0:23] * scale, b2w)
     scene = prob.host_scene.double()
@@ -37,8 +50,14 @@ def _oracle_step(fpv, prob):
     losses = dict(rec=torch.mean(torch.abs(data - p)), smoothing=ro.second_diff_l1(p),
                   contact=ro.contact_robust_loss(d_a2b[:, cid]), scene2body=d_b2a.mean(),
                   world_smoothing=ro.first_diff_l1(joints), vert_smoothing=ro.second_diff_l1(verts))
+    if prob.front_end and prob.dct_batches:
+        c_dct = prob.c_dct.detach().cpu().double().requires_grad_(True)
+        extra["dct"] = po.dct_loss(joints, prob.dct_mtx.cpu().double(), c_dct)
+    losses.update(extra)
     total = sum(W[k] * x for k, x in losses.items())
     total.backward()
+    if c_dct is not None:
+        return total.item(), p.grad, scale.grad, cam.grad, c_dct.grad
     return total.item(), p.grad, scale.grad, cam.grad
 
 
@@ -76,3 +95,21 @@ def test_fit_step_cuda_graph_replay_matches_eager(fpv, cuda_dev):
     assert torch.equal(loss_g2, loss_e2)
     for g, t in zip(grads_g2, prob.leaves()):
         assert torch.equal(t.grad, g)
+
+
+def test_fit_step_with_reference_front_end_matches_oracle(fpv, cuda_dev):
+    """f2 + f3 inside the step: 78-D 6D row -> convert_to_3D_rot -> VPoser decode -> body model, plus the VPoser
+    regulariser (:263) and the DCT prior (:310), against the float64 oracle assembly."""
+    prob = fpv.FitProblem(T=8, M=6000, device=cuda_dev, seed=1238, front_end=True, dct_frames=4)
+    assert prob.params.shape == (8, 78) and prob.dct_batches == 2 and len(prob.leaves()) == 4
+    loss = prob.step()
+    ref_loss, gp, gs, gc, gd = _oracle_step(fpv, prob)
+    assert loss.item() == pytest.approx(ref_loss, rel=2e-5)
+    for got, ref, name in [(prob.params.grad, gp, "params"), (prob.scale.grad, gs, "scale"),
+                           (prob.camera_ext.grad, gc, "camera_ext"), (prob.c_dct.grad, gd, "c_dct")]:
+        err = (got.cpu().double() - ref).abs().max().item()
+        tol = 5e-5 * ref.abs().max().item() + 1e-8
+        assert err <= tol, (name, err, tol)
+    assert prob.step().item() == loss.item()
+    prob.capture()
+    assert torch.equal(prob.step_graph(), loss)

@@ -60,6 +60,6 @@ def test_dct_loss_matches_reference_method():
     c = torch.tensor(d["c_dct"], requires_grad=True)
     loss = po.dct_loss(joints, torch.tensor(d["basis"]), c)
     loss.backward()
-    assert abs(float(loss) - float(d["loss"])) < 1e-12 * max(1.0, abs(float(d["loss"])))
+    assert abs(float(loss.detach()) - float(d["loss"])) < 1e-12 * max(1.0, abs(float(d["loss"])))
     np.testing.assert_allclose(joints.grad.numpy(), d["g_joints"], rtol=1e-10, atol=1e-14)
     np.testing.assert_allclose(c.grad.numpy(), d["g_c"], rtol=1e-10, atol=1e-14)

@@ -83,7 +83,7 @@ def test_dct_loss_matches_reference_golden(fpv, cuda_dev):
     basis = torch.tensor(d["basis"], dtype=torch.float32, device=cuda_dev)
     loss = fpv.cal_dctloss(joints, basis, c)
     loss.backward()
-    assert abs(float(loss) - float(d["loss"])) <= 1e-5 * abs(float(d["loss"]))
+    assert abs(float(loss.detach()) - float(d["loss"])) <= 1e-5 * abs(float(d["loss"]))
     np.testing.assert_allclose(joints.grad.cpu().numpy(), d["g_joints"], rtol=1e-4, atol=1e-5 * np.abs(d["g_joints"]).max())
     np.testing.assert_allclose(c.grad.cpu().numpy(), d["g_c"], rtol=1e-4, atol=1e-5 * np.abs(d["g_c"]).max())
     # repeatable bit for bit (fixed-order reductions)
