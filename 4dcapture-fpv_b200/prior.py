@@ -91,7 +91,9 @@ def body_params_encapsulate_batch(x_body_rec: torch.Tensor) -> Dict[str, torch.T
 # VPoser decoder
 # ---------------------------------------------------------------------------------------------
 def make_vposer_weights(seed: int = 1234, latent: int = 32, hidden: int = 512, joints: int = 21) -> Dict[str, torch.Tensor]:
-    """Random-init decoder weights of the VPoser v1 shapes (the snapshot is licence-gated and absent), nn.Linear init."""
+    """Random-init decoder weights of the VPoser v1 shapes (the snapshot is licence-gated and absent): nn.Linear init,
+    with the output layer damped and biased to the identity rotation so that decoded poses stay in the range of a
+    plausible body (|angle| of a few tenths of a radian), like the axis-angle clips of synthetic.make_clip_params."""
     g = torch.Generator().manual_seed(seed)
 
     def linear(o, i):
@@ -101,6 +103,8 @@ def make_vposer_weights(seed: int = 1234, latent: int = 32, hidden: int = 512, j
     w1, b1 = linear(hidden, latent)
     w2, b2 = linear(hidden, hidden)
     w3, b3 = linear(6 * joints, hidden)
+    w3 = w3 * 0.5
+    b3 = b3 * 0.5 + torch.tensor([1.0, 0.0, 0.0, 1.0, 0.0, 0.0]).repeat(joints)
     return dict(w1=w1, b1=b1, w2=w2, b2=b2, w3=w3, b3=b3)
 
 
