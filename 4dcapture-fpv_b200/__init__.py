@@ -12,6 +12,7 @@ Public surface (each mirrors a reference signature, see the module docstrings):
     convert_to_3D_rot, convert_to_6D_rot,
     VPoserDecoderB200, cal_dctloss                        prior.py   
     distChamferSharded, allreduce_grads, shard_range      sharded.py
+    io_formats (pickles, camerapose.txt, PLY)             io_formats.py  (host-side)
     FitProblem                                            fit.py
 Everything computes on an sm_100 GPU through libfpv_b200.so; there is no CPU or eager fallback.
 """
@@ -24,6 +25,6 @@ from .residuals import (body2world, contact_robust_loss, first_diff_l1, second_d
 from .prior import (VPoserDecoderB200, aa_to_rot6d, body_params_encapsulate_batch, cal_dctloss,  # noqa: F401
                     convert_to_3D_rot, convert_to_6D_rot, dct_basis, make_vposer_weights, rot6d_to_aa)
 from .sharded import allreduce_grads, combine_keys, distChamferSharded, shard_range  # noqa: F401
-from . import synthetic  # noqa: F401
+from . import io_formats, synthetic  # noqa: F401
 
 __version__ = "0.1.0"
