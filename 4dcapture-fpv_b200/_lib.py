@@ -72,6 +72,8 @@ SIGNATURES = {
     "fpv_chamfer_bwd_workspace_bytes": (c_size_t, [c_int64, c_int64, c_int64, c_int, c_int]),
     "fpv_chamfer_bwd": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int, c_void_p, c_void_p,
                                 c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "fpv_chamfer_bwd_bcast": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int, c_void_p, c_void_p, c_int,
+                                      c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "fpv_reduce_workspace_bytes": (c_size_t, [c_int64]),
     "fpv_robust_mean_fwd": (c_int, [c_void_p, c_int64, c_float, c_void_p, c_void_p, c_size_t, c_void_p]),
     "fpv_robust_mean_bwd": (c_int, [c_void_p, c_int64, c_float, c_void_p, c_void_p, c_void_p]),

@@ -14,6 +14,8 @@ Differences from the literal reference, all supersets:
 """
 from __future__ import annotations
 
+import os
+
 import torch
 
 from . import _lib, spatial
@@ -32,10 +34,11 @@ SPATIAL_MIN_POINTS = 4096
 #   "tc"      tensor-core filter over all vertices (nn_tc.cu)
 B2A_ENGINE = "sphere"
 SPHERE_TILE = 16
+BODY_SHARED_ORDER = os.environ.get("FPV_BODY_SHARED_ORDER", "1") != "0"   # one Morton order (of the middle frame) for all frames of the clip; False: per-frame argsort
 LAST_STATS = {}
 
 
-def _forward_spatial(a_c: torch.Tensor, b_c: torch.Tensor, idx_dtype, idx_base: int = 0):
+def _forward_spatial(a_c: torch.Tensor, b_c: torch.Tensor, idx_dtype, idx_base: int = 0, clip: bool = False):
     """Both chamfer directions with the scene held in Morton order.  a_c [T,N,3], b_c [1,M,3].
 
     a -> b (body vertex -> scene): the scene is static, so the box-culled tile search visits ~1 % of it.
@@ -49,12 +52,17 @@ def _forward_spatial(a_c: torch.Tensor, b_c: torch.Tensor, idx_dtype, idx_base: 
     dev = a_c.device
     L = _lib.lib()
     scene = spatial.cached_scene(b_c)                                   # built once per scene tensor
-    body = spatial.SortedCloud(a_c, scene.lo, scene.inv_cell, mode=1,   # per-step [T,N] Morton argsort + cluster table
-                               sphere_tile=SPHERE_TILE if B2A_ENGINE == "sphere" else 0)
+    body = spatial.SortedCloud(a_c, scene.lo, scene.inv_cell, mode=1,   # per-step Morton argsort + cluster table
+                               sphere_tile=SPHERE_TILE if B2A_ENGINE == "sphere" else 0,
+                               shared_perm=clip and BODY_SHARED_ORDER)
     stats = torch.zeros(1, dtype=torch.int64, device=dev)
     d_s, i_s = spatial.culled_search(body.sorted, False, T, scene, idx_dtype, idx_base=idx_base, stats=stats)
-    d_a2b = torch.empty_like(d_s).scatter_(1, body.perm, d_s)
-    i_a2b = torch.empty_like(i_s).scatter_(1, body.perm, i_s)
+    if body.shared_perm:
+        inv_b = body.inv_perm[0]
+        d_a2b, i_a2b = d_s.index_select(1, inv_b), i_s.index_select(1, inv_b)
+    else:
+        d_a2b = torch.empty_like(d_s).scatter_(1, body.perm, d_s)
+        i_a2b = torch.empty_like(i_s).scatter_(1, body.perm, i_s)
     if B2A_ENGINE == "sphere":
         stats2 = torch.zeros(2, dtype=torch.int64, device=dev)
         d_s2, i_s2 = spatial.sphere_search(scene.sorted, True, T, body, cand_orig=a_c, idx_dtype=idx_dtype, stats=stats2)
@@ -109,9 +117,19 @@ def _prep(a: torch.Tensor, b: torch.Tensor):
     return a, b, shared
 
 
+def _weights(g):
+    """(tensor or None, broadcast flag): a gradient that is one value expanded over the whole output (what autograd
+    produces for .sum() / .mean()) is passed as that single float instead of being materialised."""
+    if g is None:
+        return None, 0
+    if g.numel() > 1 and all(st == 0 for st in g.stride()):
+        return g.reshape(-1)[:1].contiguous().float(), 1
+    return g.contiguous().float(), 0
+
+
 class _ChamferFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, a, b, shared: bool, idx_dtype):
+    def forward(ctx, a, b, shared: bool, idx_dtype, clip: bool = False):
         a_c = a.contiguous()
         b_c = b.contiguous()
         bs, N, _ = a_c.shape
@@ -126,7 +144,7 @@ class _ChamferFn(torch.autograd.Function):
         use_spatial = shared and (ENGINE == "spatial" or (ENGINE == "auto" and M >= SPATIAL_MIN_POINTS))
         ctx.sorted = None
         if use_spatial:
-            d_b2a, d_a2b, i_b2a, i_a2b = _forward_spatial(a_c, b_c, idx_dtype)
+            d_b2a, d_a2b, i_b2a, i_a2b = _forward_spatial(a_c, b_c, idx_dtype, clip=clip)
             ctx.sorted = LAST_STATS.pop("sorted", None)
         else:
             with torch.cuda.device(dev):
@@ -148,13 +166,15 @@ class _ChamferFn(torch.autograd.Function):
         a, b, i_b2a, i_a2b = ctx.saved_tensors  # never mutated: backward(retain_graph=True) is safe (:591)
         need_a, need_b = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
         if not (need_a or need_b) or (g_b2a is None and g_a2b is None):
-            return None, None, None, None
+            return None, None, None, None, None
         bs, N, _ = a.shape
         M = b.shape[1]
         dev = a.device
         L = _lib.lib()
-        g1 = g_b2a.contiguous().float() if g_b2a is not None else None
-        g2 = g_a2b.contiguous().float() if g_a2b is not None else None
+        bcast = 0
+        g1, bc1 = _weights(g_b2a)
+        g2, bc2 = _weights(g_a2b)
+        bcast = bc1 | (bc2 << 1)
         grad_a = torch.empty_like(a)
         grad_b = torch.empty_like(b) if need_b else None
         if ctx.sorted is not None and not need_b:
@@ -165,32 +185,34 @@ class _ChamferFn(torch.autograd.Function):
             if not scene.identity:
                 b = scene.sorted
                 i_b2a = i_s2
-                if g1 is not None:
+                if g1 is not None and not bc1:
                     g1 = g1.index_select(1, scene.perm[0])
                 if g2 is not None:
                     i_a2b = scene.inv_perm[0].to(i_a2b.dtype)[i_a2b.long()]
         with torch.cuda.device(dev):
             nbytes = L.fpv_chamfer_bwd_workspace_bytes(bs, N, M, int(ctx.shared), int(need_b))
             ws = _lib.workspace(nbytes, dev)
-            _lib.check(L.fpv_chamfer_bwd(_lib.ptr(a), _lib.ptr(b), bs, N, M, int(ctx.shared),
-                                         _lib.ptr(g1), _lib.ptr(g2), _lib.ptr(i_b2a), _lib.ptr(i_a2b),
-                                         ctx.idx_bytes, _lib.ptr(grad_a), _lib.ptr(grad_b),
-                                         _lib.ptr(ws), ws.numel(), _lib.stream_ptr()),
+            _lib.check(L.fpv_chamfer_bwd_bcast(_lib.ptr(a), _lib.ptr(b), bs, N, M, int(ctx.shared),
+                                               _lib.ptr(g1), _lib.ptr(g2), bcast, _lib.ptr(i_b2a), _lib.ptr(i_a2b),
+                                               ctx.idx_bytes, _lib.ptr(grad_a), _lib.ptr(grad_b),
+                                               _lib.ptr(ws), ws.numel(), _lib.stream_ptr()),
                        "fpv_chamfer_bwd")
-        return (grad_a if need_a else None), grad_b, None, None
+        return (grad_a if need_a else None), grad_b, None, None, None
 
 
-def distChamfer(a: torch.Tensor, b: torch.Tensor, idx_dtype: torch.dtype = torch.int64):
+def distChamfer(a: torch.Tensor, b: torch.Tensor, idx_dtype: torch.dtype = torch.int64, clip: bool = False):
     """chamfer_python.distChamfer: returns (d_b2a [bs,M], d_a2b [bs,N], i_b2a [bs,M], i_a2b [bs,N]).
 
     Squared distances, both directions, lowest index on ties, differentiable w.r.t. a and b through
     the argmin (chamfer_python.py:28).  Indices are int64 as torch.min returns them; pass
-    idx_dtype=torch.int32 to halve the index traffic.
+    idx_dtype=torch.int32 to halve the index traffic.  clip=True declares that the batch entries of `a` are consecutive
+    frames of ONE articulated surface (the fit loop's [T,V,3] body vertices): the spatial engine then orders all
+    frames by one Morton sort instead of T.  A hint only -- results are identical either way.
     """
     if idx_dtype not in (torch.int64, torch.int32):
         raise RuntimeError("distChamfer: idx_dtype must be torch.int64 or torch.int32")
     a, b, shared = _prep(a, b)
-    return _ChamferFn.apply(a, b, shared, idx_dtype)
+    return _ChamferFn.apply(a, b, shared, idx_dtype, bool(clip))
 
 
 class chamferDist(torch.nn.Module):

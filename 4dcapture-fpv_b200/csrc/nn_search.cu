@@ -487,7 +487,7 @@ __global__ void __launch_bounds__(256) bwd_accum_kernel(const float *__restrict_
                                                         const float *__restrict__ y, int64_t y_bstride,
                                                         const float *__restrict__ g, const IdxT *__restrict__ idx,
                                                         const unsigned *__restrict__ cmax_bits, int nb_bits, int to_y,
-                                                        long long *acc, int64_t acc_bstride) {
+                                                        long long *acc, int64_t acc_bstride, int64_t gmul) {
     const int64_t b = blockIdx.y;
     const int lane = threadIdx.x & 31;
     const int64_t row0 = (int64_t(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5)) * (32 * BWD_ROWS);
@@ -506,7 +506,7 @@ __global__ void __launch_bounds__(256) bwd_accum_kernel(const float *__restrict_
             const int64_t j = static_cast<int64_t>(idx[b * N + i]);
             t = to_y ? j : i;
             const float *xi = xb + 3 * i, *yj = yb + 3 * j;
-            const float g2 = __fmul_rn(2.f, g[b * N + i]);
+            const float g2 = __fmul_rn(2.f, g[(b * N + i) * gmul]);  // gmul = 0: one broadcast weight
 #pragma unroll
             for (int k = 0; k < 3; ++k) {
                 float c = __fmul_rn(g2, __fsub_rn(xi[k], yj[k]));
@@ -540,7 +540,7 @@ template <typename IdxT>
 __global__ void bwd_finish_kernel(const float *__restrict__ x, int64_t N, const float *__restrict__ y,
                                   int64_t y_bstride, const float *__restrict__ g, const IdxT *__restrict__ idx,
                                   const unsigned *__restrict__ cmax_bits, int nb_bits, const long long *__restrict__ acc,
-                                  float *__restrict__ grad) {
+                                  float *__restrict__ grad, int64_t gmul) {
     const int64_t b = blockIdx.y;
     const int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
     if (i >= N) return;
@@ -548,7 +548,7 @@ __global__ void bwd_finish_kernel(const float *__restrict__ x, int64_t N, const 
     if (g) {
         const int64_t j = static_cast<int64_t>(idx[b * N + i]);
         const float *xi = x + (b * N + i) * 3, *yj = y + b * y_bstride + 3 * j;
-        const float g2 = __fmul_rn(2.f, g[b * N + i]);
+        const float g2 = __fmul_rn(2.f, g[(b * N + i) * gmul]);
 #pragma unroll
         for (int k = 0; k < 3; ++k) d[k] = __fmul_rn(g2, __fsub_rn(xi[k], yj[k]));
     }
@@ -570,7 +570,11 @@ static int ilog2_ceil(int64_t n) {
 template <typename IdxT>
 static int chamfer_bwd_impl(const float *a, const float *b, int64_t bs, int64_t N, int64_t M, int b_shared,
                             const float *g_b2a, const float *g_a2b, const IdxT *i_b2a, const IdxT *i_a2b,
-                            float *grad_a, float *grad_b, void *workspace, size_t workspace_bytes, cudaStream_t st) {
+                            float *grad_a, float *grad_b, void *workspace, size_t workspace_bytes, cudaStream_t st,
+                            int g_broadcast) {
+    // g_broadcast bit 0 / 1: g_b2a / g_a2b is ONE weight shared by every element (the gradient of a plain sum or
+    // mean arrives as a stride-0 expanded scalar): nothing of size [bs,M] is materialised or re-read
+    const int64_t gm1 = (g_broadcast & 1) ? 0 : 1, gm2 = (g_broadcast & 2) ? 0 : 1;
     Arena ar(workspace, workspace_bytes);
     unsigned *cmax = ar.take<unsigned>(8);  // [0..2] bound triple for grad_a, [4..6] for grad_b
     long long *acc_a = g_b2a ? ar.take<long long>(size_t(bs * N * 3)) : nullptr;
@@ -604,13 +608,13 @@ static int chamfer_bwd_impl(const float *a, const float *b, int64_t bs, int64_t 
     const int nb_a = ilog2_ceil(M) + 1;
     if (g_b2a) {
         FPV_CUDA(cudaMemsetAsync(acc_a, 0, size_t(bs * N * 3) * sizeof(long long), st));
-        absmax(g_b2a, bs * M, cmax);
+        absmax(g_b2a, gm1 ? bs * M : 1, cmax);
         FPV_LAUNCH_CHECK("absmax_kernel");
         bwd_accum_kernel<IdxT><<<gridMr, 256, 0, st>>>(b, b_bstride, M, a, N * 3, g_b2a, i_b2a, cmax, nb_a, 1, acc_a,
-                                                      N * 3);
+                                                      N * 3, gm1);
         FPV_LAUNCH_CHECK("bwd_accum_kernel");
     }
-    bwd_finish_kernel<IdxT><<<gridN, 256, 0, st>>>(a, N, b, b_bstride, g_a2b, i_a2b, cmax, nb_a, acc_a, grad_a);
+    bwd_finish_kernel<IdxT><<<gridN, 256, 0, st>>>(a, N, b, b_bstride, g_a2b, i_a2b, cmax, nb_a, acc_a, grad_a, gm2);
     FPV_LAUNCH_CHECK("bwd_finish_kernel");
 
     // ---- grad_b = 2 g_b2a (b_j - a_idx)  +  sum_{i: i_a2b[i]==j} 2 g_a2b[i] (b_j - a_i)
@@ -618,29 +622,29 @@ static int chamfer_bwd_impl(const float *a, const float *b, int64_t bs, int64_t 
         const int nb_b = ilog2_ceil(b_shared ? bs * (N + 1) : N) + 1;
         if (acc_b) FPV_CUDA(cudaMemsetAsync(acc_b, 0, size_t(gb_batches * M * 3) * sizeof(long long), st));
         if (g_a2b) {
-            absmax(g_a2b, bs * N, cmax + 4);
+            absmax(g_a2b, gm2 ? bs * N : 1, cmax + 4);
             FPV_LAUNCH_CHECK("absmax_kernel");
         }
         if (b_shared && g_b2a) {
-            absmax(g_b2a, bs * M, cmax + 4);
+            absmax(g_b2a, gm1 ? bs * M : 1, cmax + 4);
             FPV_LAUNCH_CHECK("absmax_kernel");
         }
         if (g_a2b) {
             bwd_accum_kernel<IdxT><<<gridNr, 256, 0, st>>>(a, N * 3, N, b, b_bstride, g_a2b, i_a2b, cmax + 4, nb_b, 1,
-                                                          acc_b, b_shared ? 0 : M * 3);
+                                                          acc_b, b_shared ? 0 : M * 3, gm2);
             FPV_LAUNCH_CHECK("bwd_accum_kernel");
         }
         if (b_shared) {
             if (g_b2a) {
                 bwd_accum_kernel<IdxT><<<gridMr, 256, 0, st>>>(b, 0, M, a, N * 3, g_b2a, i_b2a, cmax + 4, nb_b, 0,
-                                                              acc_b, 0);
+                                                              acc_b, 0, gm1);
                 FPV_LAUNCH_CHECK("bwd_accum_kernel");
             }
             dim3 grid1((unsigned)ceil_div(M, 256), 1);
-            bwd_finish_kernel<IdxT><<<grid1, 256, 0, st>>>(b, M, a, 0, nullptr, i_b2a, cmax + 4, nb_b, acc_b, grad_b);
+            bwd_finish_kernel<IdxT><<<grid1, 256, 0, st>>>(b, M, a, 0, nullptr, i_b2a, cmax + 4, nb_b, acc_b, grad_b, 1);
             FPV_LAUNCH_CHECK("bwd_finish_kernel");
         } else {
-            bwd_finish_kernel<IdxT><<<gridM, 256, 0, st>>>(b, M, a, N * 3, g_b2a, i_b2a, cmax + 4, nb_b, acc_b, grad_b);
+            bwd_finish_kernel<IdxT><<<gridM, 256, 0, st>>>(b, M, a, N * 3, g_b2a, i_b2a, cmax + 4, nb_b, acc_b, grad_b, gm1);
             FPV_LAUNCH_CHECK("bwd_finish_kernel");
         }
     }
@@ -759,21 +763,31 @@ size_t fpv_chamfer_bwd_workspace_bytes(int64_t bs, int64_t N, int64_t M, int b_s
     return s + 256;
 }
 
-int fpv_chamfer_bwd(const float *a, const float *b, int64_t bs, int64_t N, int64_t M, int b_shared, const float *g_b2a,
-                    const float *g_a2b, const void *i_b2a, const void *i_a2b, int idx_bytes, float *grad_a,
-                    float *grad_b, void *workspace, size_t workspace_bytes, fpv_stream_t stream) {
+int fpv_chamfer_bwd_bcast(const float *a, const float *b, int64_t bs, int64_t N, int64_t M, int b_shared,
+                          const float *g_b2a, const float *g_a2b, int g_broadcast, const void *i_b2a, const void *i_a2b,
+                          int idx_bytes, float *grad_a, float *grad_b, void *workspace, size_t workspace_bytes,
+                          fpv_stream_t stream) {
     FPV_CHECK_ARG(a && b && i_b2a && i_a2b && grad_a, "fpv_chamfer_bwd: null pointer");
     FPV_CHECK_ARG(bs > 0 && N > 0 && M > 0, "fpv_chamfer_bwd: empty cloud");
     FPV_CHECK_ARG(bs <= 65535, "fpv_chamfer_bwd: more than 65535 batches");
     FPV_CHECK_ARG(idx_bytes == 4 || idx_bytes == 8, "fpv_chamfer_bwd: idx_bytes must be 4 or 8");
+    FPV_CHECK_ARG((g_broadcast & ~3) == 0, "fpv_chamfer_bwd: g_broadcast must be a combination of bits 0 and 1");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (idx_bytes == 8)
         return chamfer_bwd_impl<long long>(a, b, bs, N, M, b_shared, g_b2a, g_a2b,
                                            static_cast<const long long *>(i_b2a),
                                            static_cast<const long long *>(i_a2b), grad_a, grad_b, workspace,
-                                           workspace_bytes, st);
+                                           workspace_bytes, st, g_broadcast);
     return chamfer_bwd_impl<int>(a, b, bs, N, M, b_shared, g_b2a, g_a2b, static_cast<const int *>(i_b2a),
-                                 static_cast<const int *>(i_a2b), grad_a, grad_b, workspace, workspace_bytes, st);
+                                 static_cast<const int *>(i_a2b), grad_a, grad_b, workspace, workspace_bytes, st,
+                                 g_broadcast);
+}
+
+int fpv_chamfer_bwd(const float *a, const float *b, int64_t bs, int64_t N, int64_t M, int b_shared, const float *g_b2a,
+                    const float *g_a2b, const void *i_b2a, const void *i_a2b, int idx_bytes, float *grad_a,
+                    float *grad_b, void *workspace, size_t workspace_bytes, fpv_stream_t stream) {
+    return fpv_chamfer_bwd_bcast(a, b, bs, N, M, b_shared, g_b2a, g_a2b, 0, i_b2a, i_a2b, idx_bytes, grad_a, grad_b,
+                                 workspace, workspace_bytes, stream);
 }
 
 }  // extern "C"

@@ -173,9 +173,9 @@ class FitProblem:
         verts = residuals.verts_transform(out.vertices * self.scale, b2w)
         joints = residuals.verts_transform(out.joints[:, 0:23, :].contiguous() * self.scale, b2w)
         if self.world > 1:
-            d_b2a, d_a2b, _, _ = sharded.distChamferSharded(verts, self.scene, self.begin, self.group)
+            d_b2a, d_a2b, _, _ = sharded.distChamferSharded(verts, self.scene, self.begin, self.group, clip=True)
         else:
-            d_b2a, d_a2b, _, _ = chamfer.distChamfer(verts, self.scene, idx_dtype=self.idx_dtype)
+            d_b2a, d_a2b, _, _ = chamfer.distChamfer(verts, self.scene, idx_dtype=self.idx_dtype, clip=True)
         losses = {
             "rec": torch.mean(torch.abs(self.data - p)) * inv_world,
             "smoothing": residuals.second_diff_l1(p) * inv_world,

@@ -56,7 +56,7 @@ class _ShardedChamferFn(torch.autograd.Function):
     """a [T,N,3] replicated; b_shard [1,Ms,3] this rank's scene range starting at global index idx_base."""
 
     @staticmethod
-    def forward(ctx, a, b_shard, idx_base: int, group, search: Optional[Callable]):
+    def forward(ctx, a, b_shard, idx_base: int, group, search: Optional[Callable], clip: bool = False):
         from . import chamfer
         a_c, b_c = a.contiguous(), b_shard.contiguous()
         T, N, _ = a_c.shape
@@ -65,7 +65,7 @@ class _ShardedChamferFn(torch.autograd.Function):
         if search is None:
             if chamfer.ENGINE != "brute" and Ms >= chamfer.SPATIAL_MIN_POINTS:
                 # shard-local search through the spatial index (global indices via idx_base), then the combine
-                d_b2a, d_loc, i_b2a, i_glob = chamfer._forward_spatial(a_c, b_c, torch.int64, idx_base)
+                d_b2a, d_loc, i_b2a, i_glob = chamfer._forward_spatial(a_c, b_c, torch.int64, idx_base, clip=clip)
                 chamfer.LAST_STATS.pop("sorted", None)
                 keys = pack_keys_torch(d_loc, i_glob)
             else:
@@ -97,7 +97,7 @@ class _ShardedChamferFn(torch.autograd.Function):
     def backward(ctx, g_b2a, g_a2b, _1, _2):
         a, b, i_b2a, i_a2b = ctx.saved_tensors
         if not ctx.needs_input_grad[0] or (g_b2a is None and g_a2b is None):
-            return None, None, None, None, None
+            return None, None, None, None, None, None
         T, N, _ = a.shape
         Ms = b.shape[1]
         g2 = None
@@ -108,7 +108,11 @@ class _ShardedChamferFn(torch.autograd.Function):
             owned = (i_a2b >= ctx.idx_base) & (i_a2b < ctx.idx_base + Ms)
             g2 = torch.where(owned, g_a2b * float(ctx.world), torch.zeros_like(g_a2b)).contiguous()
             i_loc = torch.where(owned, i_a2b - ctx.idx_base, torch.zeros_like(i_a2b)).contiguous()
-        g1 = g_b2a.contiguous() if g_b2a is not None else None
+        if ctx.search is None:
+            from . import chamfer
+            g1, bc1 = chamfer._weights(g_b2a)
+        else:
+            g1, bc1 = (g_b2a.contiguous() if g_b2a is not None else None), 0
         if ctx.search is not None:  # CPU restatement for the gloo tests
             grad_a = torch.zeros_like(a)
             bb = b[0]
@@ -117,21 +121,21 @@ class _ShardedChamferFn(torch.autograd.Function):
             if g1 is not None:
                 contrib = 2 * g1.unsqueeze(-1) * (torch.gather(a, 1, i_b2a.unsqueeze(-1).expand(-1, -1, 3)) - bb.unsqueeze(0))
                 grad_a.scatter_add_(1, i_b2a.unsqueeze(-1).expand(-1, -1, 3), contrib)
-            return grad_a, None, None, None, None
+            return grad_a, None, None, None, None, None
         L = _lib.lib()
         grad_a = torch.empty_like(a)
         if i_loc is None:
             i_loc = torch.zeros(T, N, dtype=torch.int64, device=a.device)
         with torch.cuda.device(a.device):
             wsb = _lib.workspace(L.fpv_chamfer_bwd_workspace_bytes(T, N, Ms, 1, 0), a.device)
-            _lib.check(L.fpv_chamfer_bwd(_lib.ptr(a), _lib.ptr(b), T, N, Ms, 1, _lib.ptr(g1), _lib.ptr(g2),
-                                         _lib.ptr(i_b2a), _lib.ptr(i_loc), 8, _lib.ptr(grad_a), None,
-                                         _lib.ptr(wsb), wsb.numel(), _lib.stream_ptr()), "fpv_chamfer_bwd")
-        return grad_a, None, None, None, None
+            _lib.check(L.fpv_chamfer_bwd_bcast(_lib.ptr(a), _lib.ptr(b), T, N, Ms, 1, _lib.ptr(g1), _lib.ptr(g2), bc1,
+                                               _lib.ptr(i_b2a), _lib.ptr(i_loc), 8, _lib.ptr(grad_a), None,
+                                               _lib.ptr(wsb), wsb.numel(), _lib.stream_ptr()), "fpv_chamfer_bwd")
+        return grad_a, None, None, None, None, None
 
 
 def distChamferSharded(a: torch.Tensor, b_shard: torch.Tensor, idx_base: int, group=None,
-                       _search: Optional[Callable] = None):
+                       _search: Optional[Callable] = None, clip: bool = False):
     """distChamfer with the scene sharded over the ranks of `group`.
 
     Returns (d_b2a [T,Ms] for THIS rank's shard, d_a2b [T,N] combined over all shards,
@@ -142,7 +146,7 @@ def distChamferSharded(a: torch.Tensor, b_shard: torch.Tensor, idx_base: int, gr
     """
     if b_shard.dim() == 2:
         b_shard = b_shard.unsqueeze(0)
-    return _ShardedChamferFn.apply(a, b_shard, int(idx_base), group, _search)
+    return _ShardedChamferFn.apply(a, b_shard, int(idx_base), group, _search, bool(clip))
 
 
 def allreduce_grads(params, group=None) -> None:

@@ -47,7 +47,7 @@ class SortedCloud:
     """[B,M,3] cloud sorted per batch along the Morton curve + everything nn_culled_kernel needs."""
 
     def __init__(self, points: torch.Tensor, lo: torch.Tensor = None, inv_cell: torch.Tensor = None, mode: int = 0,
-                 sphere_tile: int = 0, check_identity: bool = False):
+                 sphere_tile: int = 0, check_identity: bool = False, shared_perm: bool = False):
         """mode 0: 64-point tiles with bounding boxes; mode 1: 32-point tiles with representative + radius.
         sphere_tile (16 | 32): build the three-level bounding-sphere table of nn_sphere_kernel instead."""
         if points.dim() == 2:
@@ -59,14 +59,26 @@ class SortedCloud:
         if lo is None:
             lo, inv_cell = grid_of(points)
         self.lo, self.inv_cell = lo, inv_cell
-        keys = morton_keys(points, lo, inv_cell)
-        self.perm = torch.argsort(keys, dim=1, stable=(B == 1))                  # sorted position -> original index
+        self.shared_perm = bool(shared_perm and B > 1)
+        if self.shared_perm:
+            # One ordering for every batch entry, taken from the middle one: the batch is a clip of ONE articulated
+            # surface, so points that are neighbours in one frame stay neighbours in all of them.  The order only
+            # shapes the clusters (their spheres are rebuilt from the actual points of each frame), never the result.
+            keys = morton_keys(points[B // 2:B // 2 + 1], lo, inv_cell)
+            self.perm = torch.argsort(keys, dim=1).expand(B, -1)
+        else:
+            keys = morton_keys(points, lo, inv_cell)
+            self.perm = torch.argsort(keys, dim=1, stable=(B == 1))              # sorted position -> original index
         # a cloud that already arrives in Morton order (FitProblem pre-sorts its scene once) needs no gather on the
         # way in and no un-permute of the results on the way out; checked once per cached cloud, never per step
         self.identity = bool(check_identity and B == 1 and
                              torch.equal(self.perm[0], torch.arange(M, device=points.device)))
-        self.sorted = points.contiguous() if self.identity else \
-            torch.gather(points, 1, self.perm.unsqueeze(-1).expand(-1, -1, 3)).contiguous()
+        if self.identity:
+            self.sorted = points.contiguous()
+        elif self.shared_perm:
+            self.sorted = points.index_select(1, self.perm[0]).contiguous()
+        else:
+            self.sorted = torch.gather(points, 1, self.perm.unsqueeze(-1).expand(-1, -1, 3)).contiguous()
         Mp = (M + 63) // 64 * 64
         self.oidx = torch.full((B, Mp), INT32_MAX, dtype=torch.int32, device=points.device)
         self.oidx[:, :M] = self.perm.to(torch.int32)
@@ -89,6 +101,10 @@ class SortedCloud:
     @property
     def inv_perm(self) -> torch.Tensor:
         """original index -> sorted position."""
+        if self._inv is None and self.shared_perm:
+            inv = torch.empty(self.M, dtype=self.perm.dtype, device=self.perm.device)
+            inv[self.perm[0]] = torch.arange(self.M, device=self.perm.device)
+            self._inv = inv.unsqueeze(0).expand(self.B, -1)
         if self._inv is None:
             inv = torch.empty_like(self.perm)
             ar = torch.arange(self.M, device=self.perm.device).unsqueeze(0).expand(self.B, -1)

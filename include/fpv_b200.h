@@ -135,6 +135,13 @@ int fpv_chamfer_bwd(const float *a, const float *b, int64_t bs, int64_t N, int64
                     const float *g_b2a, const float *g_a2b, const void *i_b2a, const void *i_a2b,
                     int idx_bytes, float *grad_a, float *grad_b, void *workspace,
                     size_t workspace_bytes, fpv_stream_t stream);
+/* Same, with g_broadcast bit 0 (g_b2a) / bit 1 (g_a2b) set when that weight tensor is ONE value shared by every
+ * element -- what autograd hands back for a plain sum or mean (a stride-0 expanded scalar): the pointer then
+ * addresses a single float and no [bs,M] weight array is materialised or read. */
+int fpv_chamfer_bwd_bcast(const float *a, const float *b, int64_t bs, int64_t N, int64_t M, int b_shared,
+                          const float *g_b2a, const float *g_a2b, int g_broadcast, const void *i_b2a,
+                          const void *i_a2b, int idx_bytes, float *grad_a, float *grad_b, void *workspace,
+                          size_t workspace_bytes, fpv_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * Loss algebra around the chamfer term (global_optimization.py).

@@ -201,3 +201,22 @@ def test_keys_and_unpack(fpv, cuda_dev):
         od, oi = co.nn(x[s], y[0])
         assert np.array_equal(d[s].cpu().numpy(), od) and np.array_equal(i[s].cpu().numpy(), oi + 1000)
     assert int(keys[0, 0]) == co.pack_key(float(d[0, 0]), int(i[0, 0]))
+
+
+def test_backward_broadcast_weights_equal_materialised(fpv, cuda_dev):
+    """sum()/mean() hand the backward a stride-0 expanded scalar: it is passed as one float (fpv_chamfer_bwd_bcast) and
+    must give exactly the gradient of the materialised weights."""
+    rng = np.random.default_rng(77)
+    a = torch.tensor(rng.standard_normal((3, 900, 3)).astype(np.float32), device=cuda_dev)
+    b = torch.tensor(rng.standard_normal((1, 5000, 3)).astype(np.float32), device=cuda_dev)
+    grads = []
+    for materialise in (False, True):
+        ar, br = a.clone().requires_grad_(True), b.clone().requires_grad_(True)
+        d1, d2, _, _ = fpv.distChamfer(ar, br)
+        if materialise:
+            loss = (d1 * torch.full_like(d1, 0.3)).sum() + (d2 * torch.full_like(d2, 1.0 / d2.numel())).sum()
+        else:
+            loss = d1.sum() * 0.3 + d2.mean()
+        loss.backward()
+        grads.append((ar.grad.clone(), br.grad.clone()))
+    assert torch.equal(grads[0][0], grads[1][0]) and torch.equal(grads[0][1], grads[1][1])

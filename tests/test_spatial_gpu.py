@@ -126,3 +126,17 @@ def test_spatial_presorted_scene_identity(fpv, cuda_dev, spatial_engine):
     (out[0] * torch.tensor(g1, device=cuda_dev)).sum().add((out[1] * torch.tensor(g2, device=cuda_dev)).sum()).backward()
     ga, _ = co.dist_chamfer_bwd(a, b.numpy()[None], g1, g2, want[2], want[3])
     np.testing.assert_allclose(at.grad.cpu().numpy(), ga, rtol=1e-5, atol=1e-5 * np.abs(ga).max())
+
+
+def test_spatial_clip_hint_changes_nothing(fpv, cuda_dev, spatial_engine):
+    """clip=True orders every frame by ONE Morton sort; the results must be those of brute force whether the batch really is
+    a coherent clip or a set of unrelated clouds (the hint may only cost speed, never correctness)."""
+    rng = np.random.default_rng(23)
+    b = (rng.random((9000, 3)) * [6, 6, 2]).astype(np.float32)
+    base = (rng.standard_normal((1, 3000, 3)) * 0.3 + [3, 3, 1]).astype(np.float32)
+    clip = (base + np.cumsum(rng.standard_normal((5, 1, 3)) * 0.01, axis=0) + rng.standard_normal((5, 3000, 3)) * 0.002).astype(np.float32)
+    unrelated = (rng.standard_normal((5, 3000, 3)) * 0.5 + [3, 3, 1]).astype(np.float32)
+    for a in (clip, unrelated):
+        want = co.dist_chamfer(a, b)
+        got = fpv.distChamfer(torch.tensor(a, device=cuda_dev), torch.tensor(b, device=cuda_dev), clip=True)
+        _assert_exact([o.cpu().numpy() for o in got], want)
