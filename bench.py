@@ -144,7 +144,7 @@ def ncu_traffic(kernel_name, args, world):
     except (OSError, ValueError):
         return None
     w = rec.get("workload", {})
-    if (w.get("frames"), w.get("scene_points"), w.get("n_gpus")) != (args.T, args.M, world):
+    if (w.get("frames"), w.get("scene_points"), w.get("n_gpus"), w.get("scene")) != (args.T, args.M, world, args.scene):
         return None
     for key, val in rec.items():
         if isinstance(val, (int, float)) and kernel_name.startswith(key):
@@ -201,7 +201,7 @@ def run_b200(args):
     K = max(1, args.steps)
     idx_dtype = torch.int64 if args.idx64 else torch.int32
     prob = pkg.FitProblem(T=args.T, M=args.M, device=dev, seed=1235, rank=rank, world_size=world, idx_dtype=idx_dtype,
-                          front_end=not args.no_front_end)
+                          front_end=not args.no_front_end, scene_kind=args.scene)
 
     def barrier():
         if world > 1:
@@ -319,7 +319,7 @@ def run_b200(args):
         "metric": METRIC, "value": value, "unit": "steps/s", "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"configs[1]: T={args.T} frames, V={V}, M={args.M}-point uniform scene, both chamfer directions, exact",
+        "config": {"workload": f"configs[1]: T={args.T} frames, V={V}, M={args.M}-point {args.scene} scene, both chamfer directions, exact",
                    "frames": args.T, "scene_points": args.M, "scene_sharding": f"{world} shards (contiguous ranges of the stored scene)" if world > 1 else "none",
                    "index_dtype": "int64" if args.idx64 else "int32",
                    "step": ("6D row -> convert_to_3D_rot -> VPoser decode -> " if not args.no_front_end else "") +
@@ -355,6 +355,8 @@ def main():
     ap.add_argument("--idx64", action="store_true", help="reference-faithful int64 index outputs")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="skip the informational CUDA-graph replay leg")
+    ap.add_argument("--scene", default="uniform", choices=["uniform", "surface"],
+                    help="synthetic scene: uniform in the room volume (configs 1, 2, 4) or points on surfaces (configs 3, 5)")
     ap.add_argument("--no-front-end", action="store_true",
                     help="optimise the axis-angle row directly (skip the 6D codec, VPoser decode and DCT prior)")
     args = ap.parse_args()
