@@ -166,7 +166,10 @@ def run_reference(args):
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "steps/s", "n_gpus": args.gpus,
             "steps": n, "warmup": 0, "ms_per_step": 1e3 / value, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"configs[1]: T={args.T} frames, V={V}, M={args.M}-point scene (CPU path, extrapolated from a bounded sample)"},
+            "config": {"workload": f"configs[1]: T={args.T} frames, V={V}, M={args.M}-point {args.scene} scene, both chamfer directions, exact",
+                       "frames": args.T, "scene_points": args.M,
+                       "reference_arm": "the reference's CPU arithmetic (oracle/chamfer_ref_port.py + oracle/smplx_oracle.py) on all "
+                                        "host threads; each step times a bounded sample and extrapolates to the full workload"},
             "cpu_baseline": {"value": value, "unit": "steps/s", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
