@@ -517,13 +517,25 @@ __global__ void __launch_bounds__(256) bwd_accum_kernel(const float *__restrict_
         // runs of equal targets over consecutive lanes: segmented inclusive scan, the last lane of a run owns its sum
         const long long tp = __shfl_up_sync(0xffffffffu, t, 1);
         const unsigned heads = __ballot_sync(0xffffffffu, lane == 0 || tp != t);
-        const int start = 31 - __clz(heads & (0xffffffffu >> (31 - lane)));
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
+        if (heads == 1u) {
+            // the whole row hits one target (the far field): three 21-bit limbs through the integer warp-reduce unit,
+            // v = lo + mid 2^21 + hi 2^42 with hi signed -- exact, like the scan
 #pragma unroll
             for (int k = 0; k < 3; ++k) {
-                const long long u = __shfl_up_sync(0xffffffffu, v[k], o);
-                if (lane - o >= start) v[k] += u;
+                const int lo = int(v[k] & 0x1FFFFF), mid = int((v[k] >> 21) & 0x1FFFFF), hi = int(v[k] >> 42);
+                const long long slo = __reduce_add_sync(0xffffffffu, lo), smid = __reduce_add_sync(0xffffffffu, mid);
+                const long long shi = __reduce_add_sync(0xffffffffu, hi);
+                v[k] = slo + (smid << 21) + (shi << 42);
+            }
+        } else {
+            const int start = 31 - __clz(heads & (0xffffffffu >> (31 - lane)));
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+#pragma unroll
+                for (int k = 0; k < 3; ++k) {
+                    const long long u = __shfl_up_sync(0xffffffffu, v[k], o);
+                    if (lane - o >= start) v[k] += u;
+                }
             }
         }
         const bool tail = lane == 31 || ((heads >> (lane + 1)) & 1u);
