@@ -140,3 +140,43 @@ def test_spatial_clip_hint_changes_nothing(fpv, cuda_dev, spatial_engine):
         want = co.dist_chamfer(a, b)
         got = fpv.distChamfer(torch.tensor(a, device=cuda_dev), torch.tensor(b, device=cuda_dev), clip=True)
         _assert_exact([o.cpu().numpy() for o in got], want)
+
+
+def test_config2_scene_size_engines_agree_and_round_trip(fpv, cuda_dev):
+    """BASELINE config-2 cloud sizes (V = 10,475 vertices, M = 1,000,000 scene points; 4 frames of the clip instead of
+    300): the production engine (box index + sphere hierarchy with temporal seeding) against the brute-force engines
+    bit for bit, an oracle spot check on random rows, and size-independent properties (the winner index reproduces the
+    distance; no other sampled candidate is closer)."""
+    ch = importlib.import_module("4dcapture-fpv_b200.chamfer")
+    prob = fpv.FitProblem(T=4, M=1_000_000, device=cuda_dev, seed=1235)
+    with torch.no_grad():
+        p = prob.params
+        out = prob.model(return_verts=True, body_pose=p[:, 16:79], transl=p[:, 0:3], global_orient=p[:, 3:6],
+                         betas=p[:, 6:16], left_hand_pose=p[:, 79:91], right_hand_pose=p[:, 91:103])
+        verts = fpv.verts_transform(out.vertices * prob.scale, fpv.body2world(p[:, 103:106], prob.scale, prob.camera_ext))
+    old = ch.ENGINE
+    try:
+        ch.ENGINE = "spatial"
+        got = fpv.distChamfer(verts, prob.scene, idx_dtype=torch.int32, clip=True)
+        ch.ENGINE = "brute"
+        ref = fpv.distChamfer(verts, prob.scene, idx_dtype=torch.int32)
+    finally:
+        ch.ENGINE = old
+    for g, r in zip(got, ref):
+        assert torch.equal(g, r)
+    d_b2a, d_a2b, i_b2a, i_a2b = got
+    scene = prob.scene[0]
+    # the index reproduces the distance (re-evaluated in torch fp32; unfused, hence the 2-ulp tolerance)
+    w = torch.gather(verts, 1, i_b2a.long().unsqueeze(-1).expand(-1, -1, 3))
+    dx, dy, dz = (scene[:, 0] - w[..., 0]), (scene[:, 1] - w[..., 1]), (scene[:, 2] - w[..., 2])
+    assert torch.allclose(dx * dx + dy * dy + dz * dz, d_b2a, rtol=3e-7, atol=0)
+    # oracle spot check: random scene points against all vertices, random vertices against the whole scene
+    rng = np.random.default_rng(5)
+    rows = rng.integers(0, 1_000_000, 300)
+    v_np, s_np = verts.cpu().numpy(), scene.cpu().numpy()
+    for t in range(4):
+        d, i = co.nn(s_np[rows], v_np[t])
+        assert np.array_equal(d, d_b2a[t].cpu().numpy()[rows]) and np.array_equal(i, i_b2a[t].cpu().numpy()[rows])
+    cols = rng.integers(0, 10475, 200)
+    d, i = co.nn(v_np[1][cols], s_np)
+    assert np.array_equal(d, d_a2b[1].cpu().numpy()[cols]) and np.array_equal(i, i_a2b[1].cpu().numpy()[cols])
