@@ -64,8 +64,8 @@ SIGNATURES = {
                                      c_int, c_int64, c_void_p, c_void_p, c_int, c_void_p, c_void_p]),
     "fpv_nn_sphere_table_floats": (c_size_t, [c_int64, c_int]),
     "fpv_nn_sphere_table": (c_int, [c_void_p, c_int64, c_int64, c_int, c_void_p, c_void_p]),
-    "fpv_nn_sphere_search": (c_int, [c_void_p, c_int, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_int64,
-                                     c_int, c_int64, c_void_p, c_void_p, c_int, c_void_p, c_void_p]),
+    "fpv_nn_sphere_search": (c_int, [c_void_p, c_int, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                     c_int, c_int64, c_int, c_int64, c_void_p, c_void_p, c_int, c_void_p, c_void_p]),
     "fpv_chamfer_fwd_workspace_bytes": (c_size_t, [c_int64, c_int64, c_int64, c_int]),
     "fpv_chamfer_fwd": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int, c_void_p, c_void_p,
                                 c_void_p, c_void_p, c_int, c_void_p, c_size_t, c_void_p]),

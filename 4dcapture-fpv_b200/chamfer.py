@@ -34,6 +34,7 @@ SPATIAL_MIN_POINTS = 4096
 #   "tc"      tensor-core filter over all vertices (nn_tc.cu)
 B2A_ENGINE = "sphere"
 SPHERE_TILE = 16
+CARRY_SEEDS = os.environ.get("FPV_CARRY_SEEDS", "1") != "0"   # scene->body: start from the previous call's winners
 BODY_SHARED_ORDER = os.environ.get("FPV_BODY_SHARED_ORDER", "1") != "0"   # one Morton order (of the middle frame) for all frames of the clip; False: per-frame argsort
 LAST_STATS = {}
 
@@ -65,7 +66,17 @@ def _forward_spatial(a_c: torch.Tensor, b_c: torch.Tensor, idx_dtype, idx_base: 
         i_a2b = torch.empty_like(i_s).scatter_(1, body.perm, i_s)
     if B2A_ENGINE == "sphere":
         stats2 = torch.zeros(2, dtype=torch.int64, device=dev)
-        d_s2, i_s2 = spatial.sphere_search(scene.sorted, True, T, body, cand_orig=a_c, idx_dtype=idx_dtype, stats=stats2)
+        seed, seed_valid = None, False
+        if CARRY_SEEDS:
+            # winners of the previous call on this scene (an optimiser loop calls with a slowly moving body): every
+            # (frame, scene point) starts from the exact distance to that vertex.  A hint only; kept on the cached scene.
+            seed = scene.seeds.get((T, N))
+            seed_valid = seed is not None and seed.device == dev
+            if not seed_valid:
+                scene.seeds.clear()
+                seed = scene.seeds[(T, N)] = torch.empty((T, M), dtype=torch.int32, device=dev)   # written by this call
+        d_s2, i_s2 = spatial.sphere_search(scene.sorted, True, T, body, cand_orig=a_c, idx_dtype=idx_dtype, stats=stats2,
+                                           seed=seed, seed_valid=seed_valid)
         LAST_STATS["tiles_searched_b2a"] = stats2
     elif B2A_ENGINE == "rep":
         stats2 = torch.zeros(2, dtype=torch.int64, device=dev)

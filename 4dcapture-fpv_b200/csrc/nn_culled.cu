@@ -442,6 +442,8 @@ struct SphereParams {
     const int *oidx;
     int64_t oidx_bstride;
     const float *cand_orig;  // [cand batches][M][3] candidates in ORIGINAL order (temporal seeding), may be null
+    int *seed;               // [batches][N] in/out: last call's winners (original indices; < 0 = none), may be null
+    int seed_read;           // 0: the buffer holds nothing yet, only write it
     int n0, n1, n2;
     int batches, frames_per_cta;
     int64_t idx_base;
@@ -566,8 +568,37 @@ __global__ void __launch_bounds__(CU_WARPS * 32, MINB) nn_sphere_kernel(const Sp
         const float *planes = p.planes + int64_t(b) * p.plane_bstride;
         const float4 *tab = p.table + int64_t(b) * p.table_bstride;
         const int *oidx = p.oidx + int64_t(b) * p.oidx_bstride;
+        // seed, in order of preference: the winner of the previous CALL for this (frame, query) (an optimiser moves the
+        // body by millimetres per step), the winner of the previous FRAME of this call, a coarse pass over the frame
+        bool seeded = false;
+        if (p.seed_read) {
+            int sd[CU_QPT];
+            bool ok = true;
+#pragma unroll
+            for (int k = 0; k < CU_QPT; ++k) {
+                int64_t qi = q0 + k * 32 + lane;
+                if (qi > p.N - 1) qi = p.N - 1;
+                sd[k] = p.seed[int64_t(b) * p.N + qi];
+                ok &= unsigned(sd[k]) < unsigned(p.M);
+            }
+            seeded = __all_sync(0xffffffffu, ok);
+            if (seeded) {
+                const float *co = p.cand_orig + int64_t(b) * p.M * 3;
+#pragma unroll
+                for (int k = 0; k < CU_QPT; ++k) {
+                    const float *y = co + 3 * int64_t(sd[k]);
+                    best[k] = cu_d2(qx[k], qy[k], qz[k], __ldg(y), __ldg(y + 1), __ldg(y + 2));
+                    bidx[k] = sd[k];
+                    if (!(best[k] < CUDART_INF_F)) {
+                        best[k] = CUDART_INF_F;
+                        bidx[k] = 0;
+                    }
+                }
+            }
+        }
         const bool temporal = (b > b0) && p.q_bstride == 0 && p.cand_orig != nullptr;
-        if (temporal) {
+        if (seeded) {
+        } else if (temporal) {
             // seed: exact distance to the previous frame's winner, re-evaluated on this frame's vertices
             const float *co = p.cand_orig + int64_t(b) * p.M * 3;
 #pragma unroll
@@ -695,6 +726,7 @@ __global__ void __launch_bounds__(CU_WARPS * 32, MINB) nn_sphere_kernel(const Sp
                     static_cast<long long *>(p.idx)[o] = gi;
                 else
                     static_cast<int *>(p.idx)[o] = int(gi);
+                if (p.seed != nullptr) p.seed[o] = bidx[k];
             }
         }
     }
@@ -937,10 +969,11 @@ int fpv_nn_sphere_set_chunking(int ctas_per_sm) {
 /* Exact NN through the sphere hierarchy.  cand_orig (optional): the candidates in ORIGINAL order
  * [cand_batches][M][3]; with a shared query set it enables temporal seeding across consecutive batches (frames). */
 int fpv_nn_sphere_search(const float *queries, int q_shared, int64_t batches, int64_t N, const float *planes,
-                         const float *table, const int32_t *orig_idx, const float *cand_orig, int64_t M, int tile,
-                         int64_t idx_base, float *dist, void *idx, int idx_bytes,
+                         const float *table, const int32_t *orig_idx, const float *cand_orig, int32_t *seed_inout,
+                         int seed_valid, int64_t M, int tile, int64_t idx_base, float *dist, void *idx, int idx_bytes,
                          unsigned long long *tiles_searched, fpv_stream_t stream) {
     FPV_CHECK_ARG(queries && planes && table && orig_idx && dist && idx, "fpv_nn_sphere_search: null pointer");
+    FPV_CHECK_ARG(!seed_inout || cand_orig, "fpv_nn_sphere_search: seed_inout needs cand_orig");
     FPV_CHECK_ARG(batches > 0 && N > 0 && M > 0 && batches <= 65535, "fpv_nn_sphere_search: empty input");
     FPV_CHECK_ARG(idx_bytes == 4 || idx_bytes == 8, "fpv_nn_sphere_search: idx_bytes must be 4 or 8");
     FPV_CHECK_ARG(tile == 16 || tile == 32, "fpv_nn_sphere_search: tile must be 16 or 32");
@@ -962,6 +995,8 @@ int fpv_nn_sphere_search(const float *queries, int q_shared, int64_t batches, in
     p.oidx = orig_idx;
     p.oidx_bstride = p.Mp;
     p.cand_orig = cand_orig;
+    p.seed = seed_inout;
+    p.seed_read = (seed_inout && seed_valid) ? 1 : 0;
     p.batches = int(batches);
     p.idx_base = idx_base;
     p.dist = dist;
@@ -971,7 +1006,8 @@ int fpv_nn_sphere_search(const float *queries, int q_shared, int64_t batches, in
     const int64_t ctas_x = ceil_div(ceil_div(N, CU_GROUP), CU_WARPS);
     int64_t nchunks = batches;
     if (q_shared && cand_orig) {  // walk frames inside the warp, but keep >= ~2 resident waves of CTAs
-        nchunks = ceil_div(int64_t(sm_count()) * g_sphere_ctas_per_sm, ctas_x);
+        // with per-call seeds every frame starts seeded: frames need not share a CTA, so the grid can be much finer
+        nchunks = ceil_div(int64_t(sm_count()) * g_sphere_ctas_per_sm * (p.seed_read ? 4 : 1), ctas_x);
         if (nchunks < 1) nchunks = 1;
         if (nchunks > batches) nchunks = batches;
     }

@@ -97,6 +97,7 @@ class SortedCloud:
                 _lib.check(L.fpv_nn_tile_boxes(_lib.ptr(self.planes), _lib.ptr(self.oidx), B, M, mode, _lib.ptr(self.boxes),
                                                _lib.stream_ptr()), "fpv_nn_tile_boxes")
         self._inv = None
+        self.seeds = {}   # (batches, candidates) -> [batches, M] int32 winners of the last search with this cloud as QUERIES
 
     @property
     def inv_perm(self) -> torch.Tensor:
@@ -132,9 +133,11 @@ def culled_search(queries_grouped: torch.Tensor, q_shared: bool, batches: int, c
 
 
 def sphere_search(queries_grouped: torch.Tensor, q_shared: bool, batches: int, cloud: SortedCloud,
-                  cand_orig: torch.Tensor = None, idx_dtype=torch.int32, idx_base: int = 0, stats: torch.Tensor = None):
+                  cand_orig: torch.Tensor = None, idx_dtype=torch.int32, idx_base: int = 0, stats: torch.Tensor = None,
+                  seed: torch.Tensor = None, seed_valid: bool = True):
     """Exact NN through the bounding-sphere hierarchy of `cloud` (built with sphere_tile).  cand_orig [batches,M,3]
-    (the candidates in original order) enables temporal seeding across consecutive batches when q_shared."""
+    (the candidates in original order) enables temporal seeding across consecutive batches when q_shared; seed
+    [batches,N] int32 (in/out) carries the winners from one call to the next (hints only)."""
     L = _lib.lib()
     q = queries_grouped.contiguous()
     N = q.shape[1]
@@ -144,7 +147,7 @@ def sphere_search(queries_grouped: torch.Tensor, q_shared: bool, batches: int, c
     co = cand_orig.contiguous() if cand_orig is not None else None
     with torch.cuda.device(dev):
         _lib.check(L.fpv_nn_sphere_search(_lib.ptr(q), int(q_shared), batches, N, _lib.ptr(cloud.planes),
-                                          _lib.ptr(cloud.boxes), _lib.ptr(cloud.oidx), _lib.ptr(co), cloud.M,
+                                          _lib.ptr(cloud.boxes), _lib.ptr(cloud.oidx), _lib.ptr(co), _lib.ptr(seed), int(seed_valid), cloud.M,
                                           cloud.sphere_tile, idx_base, _lib.ptr(dist), _lib.ptr(idx),
                                           8 if idx_dtype == torch.int64 else 4, _lib.ptr(stats), _lib.stream_ptr()),
                    "fpv_nn_sphere_search")
@@ -156,21 +159,38 @@ _SCENE_CACHE_MAX = 4
 
 
 def cached_scene(scene: torch.Tensor) -> SortedCloud:
-    """Sorted form of a static cloud [1,M,3], rebuilt only when the tensor's storage, version or shape changes.
+    """Sorted form of a static cloud [1,M,3], rebuilt only when its CONTENT changes.
 
-    Each entry keeps a strong reference to the source tensor: while it is cached its memory cannot be freed and
-    handed to another tensor, so (data_ptr, version, shape) identifies the content (the reference keeps one scene
-    tensor alive for the whole fit, global_optimization.py:175-176)."""
+    Fast path: (data_ptr, version, shape) of a tensor we hold a strong reference to (its memory cannot be recycled
+    while cached) -- no device work, capture-safe; this is the reference's situation, one scene tensor alive for the
+    whole fit (global_optimization.py:175-176).  Slow path, for callers that re-create or re-upload the same scene
+    every step: a two-word content checksum finds the candidate entry and torch.equal confirms it (two passes over
+    the cloud and one host sync, ~0.1 ms for 1 M points), so the index and the carried seeds survive."""
     key = (scene.data_ptr(), scene._version, tuple(scene.shape), scene.device.index)
     hit = _scene_cache.get(key)
     if hit is not None:
         return hit[1]
-    while len(_scene_cache) >= _SCENE_CACHE_MAX:
-        _scene_cache.pop(next(iter(_scene_cache)))
     src = scene.detach()
+    if not torch.cuda.is_current_stream_capturing():
+        bits = src.reshape(-1).view(torch.int32).to(torch.int64)
+        w = torch.arange(bits.numel(), device=src.device, dtype=torch.int64) % 65521 + 1
+        h = tuple(torch.stack([bits.sum(), (bits * w).sum()]).tolist())
+        for k, (old_src, sc, old_h) in list(_scene_cache.items()):
+            if old_h == h and old_src.shape == src.shape and old_src.device == src.device and torch.equal(old_src, src):
+                _scene_cache[key] = (src, sc, h)          # alias under the new tensor's key; the old key stays valid
+                _trim_scene_cache()
+                return sc
+    else:
+        h = None
     sc = SortedCloud(src, check_identity=True)
-    _scene_cache[key] = (src, sc)
+    _scene_cache[key] = (src, sc, h)
+    _trim_scene_cache()
     return sc
+
+
+def _trim_scene_cache() -> None:
+    while len(_scene_cache) > _SCENE_CACHE_MAX:
+        _scene_cache.pop(next(iter(_scene_cache)))
 
 
 def clear_scene_cache() -> None:

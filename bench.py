@@ -231,6 +231,9 @@ def run_b200(args):
     barrier()
     e0.record()
     for _ in range(K):
+        if args.jitter > 0:
+            with torch.no_grad():
+                prob.params.add_(torch.randn_like(prob.params) * args.jitter)
         prob.step()
     e1.record()
     barrier()
@@ -328,6 +331,7 @@ def run_b200(args):
                    "step": ("6D row -> convert_to_3D_rot -> VPoser decode -> " if not args.no_front_end else "") +
                            "SMPL-X -> scale/world transform -> chamfer (both directions) -> contact / smoothness" +
                            (" / VPoser / DCT" if not args.no_front_end else "") + " residuals -> full backward",
+                   "param_jitter_per_step": args.jitter,
                    "scene_order": "Morton-sorted once on the host" + (", dealt to ranks in blocks of 2048" if world > 1 else ""),
                    "search": "body->scene: Morton-tiled box-culled exact search; scene->body: per-query bounding-sphere hierarchy over the Morton-sorted body with temporal seeding (exact)",
                    "l2": "per-step working set (>=2.4 GB of [T,M] outputs) exceeds the 126 MB L2; no explicit flush"},
@@ -360,6 +364,9 @@ def main():
     ap.add_argument("--no-graph", action="store_true", help="skip the informational CUDA-graph replay leg")
     ap.add_argument("--scene", default="uniform", choices=["uniform", "surface"],
                     help="synthetic scene: uniform in the room volume (configs 1, 2, 4) or points on surfaces (configs 3, 5)")
+    ap.add_argument("--jitter", type=float, default=0.0,
+                    help="add N(0, jitter^2) to the optimised parameters before every step (an optimiser-like drift; "
+                         "shows that the carried seeds and the scene cache do not depend on identical inputs)")
     ap.add_argument("--no-front-end", action="store_true",
                     help="optimise the axis-angle row directly (skip the 6D codec, VPoser decode and DCT prior)")
     args = ap.parse_args()

@@ -106,15 +106,19 @@ int fpv_nn_sphere_set_chunking(int ctas_per_sm);
  * with bounding spheres on three levels; a query needs a cluster only if |x - c| <= sqrt(best_x) + r.  With a
  * shared query set and cand_orig (the candidates in ORIGINAL order, [batches][M][3]) consecutive batches (frames)
  * seed each other: every query starts from the exact distance to its previous frame's winner.
+ * seed_inout (optional, device, [batches][N] int32, needs cand_orig): the winners of the previous CALL on the same
+ * problem (original candidate indices; any value outside [0,M) = no seed, e.g. -1 on the first call); read as the
+ * starting point of every (batch, query) when seed_valid != 0, and always overwritten with this call's winners.
+ * Seeds are hints: any content yields the same exact result.
  * Table: 8 floats per sphere (expanded-test form, see nn_culled.cu).  tiles_searched (optional, device):
  * += clusters searched by a warp. */
 size_t fpv_nn_sphere_table_floats(int64_t M, int tile);
 int fpv_nn_sphere_table(const float *planes, int64_t batches, int64_t M, int tile, float *table,
                         fpv_stream_t stream);
 int fpv_nn_sphere_search(const float *queries, int q_shared, int64_t batches, int64_t N, const float *planes,
-                         const float *table, const int32_t *orig_idx, const float *cand_orig, int64_t M,
-                         int tile, int64_t idx_base, float *dist, void *idx, int idx_bytes,
-                         unsigned long long *tiles_searched, fpv_stream_t stream);
+                         const float *table, const int32_t *orig_idx, const float *cand_orig,
+                         int32_t *seed_inout, int seed_valid, int64_t M, int tile, int64_t idx_base, float *dist,
+                         void *idx, int idx_bytes, unsigned long long *tiles_searched, fpv_stream_t stream);
 
 /* distChamfer(a, b) forward, reference output order (chamfer_python.py:28):
  *   d_b2a [bs,M], d_a2b [bs,N], i_b2a [bs,M] (index into a), i_a2b [bs,N] (index into b).

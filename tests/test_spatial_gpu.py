@@ -180,3 +180,48 @@ def test_config2_scene_size_engines_agree_and_round_trip(fpv, cuda_dev):
     cols = rng.integers(0, 10475, 200)
     d, i = co.nn(v_np[1][cols], s_np)
     assert np.array_equal(d, d_a2b[1].cpu().numpy()[cols]) and np.array_equal(i, i_a2b[1].cpu().numpy()[cols])
+
+
+def test_seed_carry_between_calls_is_only_a_hint(fpv, cuda_dev):
+    """scene->body starts from the winners of the previous call on the same scene: the second call (seeded), a call after
+    the body moved (stale seeds) and a call with garbage seeds all return exactly what brute force returns."""
+    ch = importlib.import_module("4dcapture-fpv_b200.chamfer")
+    sp = importlib.import_module("4dcapture-fpv_b200.spatial")
+    rng = np.random.default_rng(31)
+    b = (rng.random((20000, 3)) * [6, 6, 2]).astype(np.float32)
+    a0 = (rng.standard_normal((4, 2500, 3)) * 0.35 + [3, 3, 1]).astype(np.float32)
+    a1 = (a0 + rng.standard_normal(a0.shape).astype(np.float32) * 0.01).astype(np.float32)
+    bt = torch.tensor(b, device=cuda_dev).unsqueeze(0)
+    old = ch.ENGINE
+    try:
+        ch.ENGINE = "spatial"
+        for a in (a0, a0, a1):
+            got = fpv.distChamfer(torch.tensor(a, device=cuda_dev), bt, clip=True)
+            _assert_exact([o.cpu().numpy() for o in got], co.dist_chamfer(a, b))
+        seeds = sp.cached_scene(bt).seeds[(4, 2500)]
+        assert seeds.min().item() >= 0 and seeds.max().item() < 2500       # populated by the calls above
+        seeds.copy_(torch.randint(-5, 4000, seeds.shape, device=cuda_dev, dtype=torch.int32))   # garbage, partly invalid
+        got = fpv.distChamfer(torch.tensor(a1, device=cuda_dev), bt, clip=True)
+        _assert_exact([o.cpu().numpy() for o in got], co.dist_chamfer(a1, b))
+    finally:
+        ch.ENGINE = old
+
+
+def test_scene_cache_follows_content_not_identity(fpv, cuda_dev):
+    """A scene that is re-uploaded (new tensor, same content) keeps its index and seeds; changed content does not."""
+    sp = importlib.import_module("4dcapture-fpv_b200.spatial")
+    sp.clear_scene_cache()
+    g = torch.Generator().manual_seed(9)
+    host = torch.rand(1, 50000, 3, generator=g)
+    s1 = host.to(cuda_dev)
+    c1 = sp.cached_scene(s1)
+    assert sp.cached_scene(s1) is c1                                  # pointer fast path
+    s2 = host.to(cuda_dev)
+    assert s2.data_ptr() != s1.data_ptr() and sp.cached_scene(s2) is c1   # content path
+    s3 = host.clone()
+    s3[0, 123, 1] += 1e-3
+    c3 = sp.cached_scene(s3.to(cuda_dev))
+    assert c3 is not c1
+    s1.add_(1.0)                                                      # in-place change bumps the version: rebuilt
+    assert sp.cached_scene(s1) is not c1
+    sp.clear_scene_cache()
