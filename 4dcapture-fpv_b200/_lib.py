@@ -61,7 +61,8 @@ SIGNATURES = {
     "fpv_nn_tile_boxes_floats": (c_size_t, [c_int64, c_int]),
     "fpv_nn_tile_boxes": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int, c_void_p, c_void_p]),
     "fpv_nn_culled_search": (c_int, [c_void_p, c_int, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_int64, c_int64,
-                                     c_int, c_int64, c_void_p, c_void_p, c_int, c_void_p, c_void_p]),
+                                     c_int, c_int64, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int,
+                                     c_void_p]),
     "fpv_nn_sphere_table_floats": (c_size_t, [c_int64, c_int]),
     "fpv_nn_sphere_table": (c_int, [c_void_p, c_int64, c_int64, c_int, c_void_p, c_void_p]),
     "fpv_nn_sphere_search": (c_int, [c_void_p, c_int, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,

@@ -57,7 +57,18 @@ def _forward_spatial(a_c: torch.Tensor, b_c: torch.Tensor, idx_dtype, idx_base: 
                                sphere_tile=SPHERE_TILE if B2A_ENGINE == "sphere" else 0,
                                shared_perm=clip and BODY_SHARED_ORDER)
     stats = torch.zeros(1, dtype=torch.int64, device=dev)
-    d_s, i_s = spatial.culled_search(body.sorted, False, T, scene, idx_dtype, idx_base=idx_base, stats=stats)
+    seed_a, seed_a_valid = None, False
+    if CARRY_SEEDS:
+        # body->scene winners of the previous call, per sorted query position (the order of the body barely changes
+        # between optimiser steps; a misplaced seed is still a nearby scene point)
+        seed_a = scene.seeds.get(("a2b", T, N))
+        seed_a_valid = seed_a is not None and seed_a.device == dev
+        if not seed_a_valid:
+            if len(scene.seeds) >= 4:          # a scene serves one or two problems at a time; do not hoard old buffers
+                scene.seeds.clear()
+            seed_a = scene.seeds[("a2b", T, N)] = torch.empty((T, N), dtype=torch.int32, device=dev)
+    d_s, i_s = spatial.culled_search(body.sorted, False, T, scene, idx_dtype, idx_base=idx_base, stats=stats,
+                                     cand_orig=b_c, seed=seed_a, seed_valid=seed_a_valid)
     if body.shared_perm:
         inv_b = body.inv_perm[0]
         d_a2b, i_a2b = d_s.index_select(1, inv_b), i_s.index_select(1, inv_b)
@@ -70,11 +81,10 @@ def _forward_spatial(a_c: torch.Tensor, b_c: torch.Tensor, idx_dtype, idx_base: 
         if CARRY_SEEDS:
             # winners of the previous call on this scene (an optimiser loop calls with a slowly moving body): every
             # (frame, scene point) starts from the exact distance to that vertex.  A hint only; kept on the cached scene.
-            seed = scene.seeds.get((T, N))
+            seed = scene.seeds.get(("b2a", T, N))
             seed_valid = seed is not None and seed.device == dev
             if not seed_valid:
-                scene.seeds.clear()
-                seed = scene.seeds[(T, N)] = torch.empty((T, M), dtype=torch.int32, device=dev)   # written by this call
+                seed = scene.seeds[("b2a", T, N)] = torch.empty((T, M), dtype=torch.int32, device=dev)   # written by this call
         d_s2, i_s2 = spatial.sphere_search(scene.sorted, True, T, body, cand_orig=a_c, idx_dtype=idx_dtype, stats=stats2,
                                            seed=seed, seed_valid=seed_valid)
         LAST_STATS["tiles_searched_b2a"] = stats2

@@ -53,6 +53,10 @@ struct CulledParams {
     void *idx;
     int idx_bytes;
     unsigned long long *tiles_searched;  // optional statistics counter
+    const float *cand_orig;  // [cand batches][M][3] candidates in ORIGINAL order (needed to re-evaluate seeds), may be null
+    int64_t cand_orig_bstride;
+    int *seed;               // [batches][N] in/out winners of the previous call (original indices), may be null
+    int seed_read;
 };
 
 __device__ __forceinline__ float cu_d2(float x, float y, float z, float rx, float ry, float rz) {
@@ -269,9 +273,40 @@ __global__ void __launch_bounds__(CU_WARPS * 32) nn_culled_kernel(const CulledPa
         seed = smin * 32 + (m ? __ffs(m) - 1 : 0);
         if (seed >= p.ntile) seed = 0;
     }
-    stage_and_search(seed);
+    // seeds carried from the previous call on the same problem: every query starts from the exact distance to its old
+    // winner, the group bound is tight before the first tile and the nearest-tile probe is not needed
+    bool seeded = false;
+    if (p.seed_read) {
+        int sd[CU_QPT];
+        bool ok = true;
+#pragma unroll
+        for (int k = 0; k < CU_QPT; ++k) {
+            int64_t qi = q0 + k * 32 + lane;
+            if (qi > p.N - 1) qi = p.N - 1;
+            sd[k] = p.seed[b * p.N + qi];
+            ok &= unsigned(sd[k]) < unsigned(p.M);
+        }
+        seeded = __all_sync(0xffffffffu, ok);
+        if (seeded) {
+            const float *co = p.cand_orig + b * p.cand_orig_bstride;
+#pragma unroll
+            for (int k = 0; k < CU_QPT; ++k) {
+                const float *y = co + 3 * int64_t(sd[k]);
+                best[k] = cu_d2(qx[k], qy[k], qz[k], __ldg(y), __ldg(y + 1), __ldg(y + 2));
+                bidx[k] = sd[k];
+                if (!(best[k] < CUDART_INF_F)) {
+                    best[k] = CUDART_INF_F;
+                    bidx[k] = 0;
+                }
+            }
+            seed = -1;
+        }
+    }
+    if (!seeded) {
+        stage_and_search(seed);
+        searched = 1;
+    }
     float worst = group_worst();
-    searched = 1;
 
     // ---- phase B: two-level sweep, searching only tiles that can still hold a winner ----
     for (int s0 = 0; s0 < p.nsuper; s0 += 32) {
@@ -327,6 +362,7 @@ __global__ void __launch_bounds__(CU_WARPS * 32) nn_culled_kernel(const CulledPa
                 static_cast<long long *>(p.idx)[o] = gi;
             else
                 static_cast<int *>(p.idx)[o] = int(gi);
+            if (p.seed != nullptr) p.seed[o] = bidx[k];
         }
     }
 }
@@ -884,8 +920,10 @@ int fpv_nn_tile_boxes(const float *planes, const int32_t *orig_idx, int64_t batc
 int fpv_nn_culled_search(const float *queries, int q_shared, int64_t batches, int64_t N, const float *planes,
                          const float *boxes, const int32_t *orig_idx, int64_t cand_batches, int64_t M, int mode,
                          int64_t idx_base, float *dist, void *idx, int idx_bytes,
-                         unsigned long long *tiles_searched, fpv_stream_t stream) {
+                         unsigned long long *tiles_searched, const float *cand_orig, int32_t *seed_inout,
+                         int seed_valid, fpv_stream_t stream) {
     FPV_CHECK_ARG(queries && planes && boxes && orig_idx && dist && idx, "fpv_nn_culled_search: null pointer");
+    FPV_CHECK_ARG(!seed_inout || (cand_orig && mode == 0), "fpv_nn_culled_search: seeds need cand_orig and box mode");
     FPV_CHECK_ARG(batches > 0 && N > 0 && M > 0 && batches <= 65535, "fpv_nn_culled_search: empty input");
     FPV_CHECK_ARG(cand_batches == 1 || cand_batches == batches, "fpv_nn_culled_search: cand_batches must be 1 or batches");
     FPV_CHECK_ARG(idx_bytes == 4 || idx_bytes == 8, "fpv_nn_culled_search: idx_bytes must be 4 or 8");
@@ -914,6 +952,10 @@ int fpv_nn_culled_search(const float *queries, int q_shared, int64_t batches, in
     p.idx = idx;
     p.idx_bytes = idx_bytes;
     p.tiles_searched = tiles_searched;
+    p.cand_orig = cand_orig;
+    p.cand_orig_bstride = cand_batches == 1 ? 0 : M * 3;
+    p.seed = seed_inout;
+    p.seed_read = (seed_inout && seed_valid) ? 1 : 0;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     dim3 grid((unsigned)ceil_div(ceil_div(eN, CU_GROUP), CU_WARPS), (unsigned)eb);
     if (profile_on()) {

@@ -115,7 +115,8 @@ class SortedCloud:
 
 
 def culled_search(queries_grouped: torch.Tensor, q_shared: bool, batches: int, cloud: SortedCloud,
-                  idx_dtype=torch.int32, idx_base: int = 0, stats: torch.Tensor = None):
+                  idx_dtype=torch.int32, idx_base: int = 0, stats: torch.Tensor = None, cand_orig: torch.Tensor = None,
+                  seed: torch.Tensor = None, seed_valid: bool = False):
     """queries_grouped: [batches,N,3] (or [1,N,3] when q_shared) with 128 consecutive queries spatially compact.
     Returns (dist [batches,N], idx [batches,N]) with ORIGINAL candidate indices."""
     L = _lib.lib()
@@ -128,7 +129,8 @@ def culled_search(queries_grouped: torch.Tensor, q_shared: bool, batches: int, c
         _lib.check(L.fpv_nn_culled_search(_lib.ptr(q), int(q_shared), batches, N, _lib.ptr(cloud.planes),
                                           _lib.ptr(cloud.boxes), _lib.ptr(cloud.oidx), cloud.B, cloud.M, cloud.mode, idx_base,
                                           _lib.ptr(dist), _lib.ptr(idx), 8 if idx_dtype == torch.int64 else 4,
-                                          _lib.ptr(stats), _lib.stream_ptr()), "fpv_nn_culled_search")
+                                          _lib.ptr(stats), _lib.ptr(cand_orig.contiguous() if seed is not None else None),
+                                          _lib.ptr(seed), int(seed_valid), _lib.stream_ptr()), "fpv_nn_culled_search")
     return dist, idx
 
 

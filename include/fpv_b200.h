@@ -96,7 +96,11 @@ int fpv_nn_tile_boxes(const float *planes, const int32_t *orig_idx, int64_t batc
 int fpv_nn_culled_search(const float *queries, int q_shared, int64_t batches, int64_t N, const float *planes,
                          const float *boxes, const int32_t *orig_idx, int64_t cand_batches, int64_t M, int mode,
                          int64_t idx_base, float *dist, void *idx, int idx_bytes,
-                         unsigned long long *tiles_searched, fpv_stream_t stream);
+                         unsigned long long *tiles_searched, const float *cand_orig, int32_t *seed_inout,
+                         int seed_valid, fpv_stream_t stream);
+/*   cand_orig / seed_inout / seed_valid (mode 0, optional): the candidates in ORIGINAL order [cand_batches][M][3] and a
+ *   [batches][N] int32 buffer of the previous call's winners (original indices, without idx_base), read as starting
+ *   points when seed_valid and always overwritten -- hints only, see fpv_nn_sphere_search. */
 
 /* Frame chunking of fpv_nn_sphere_search with temporal seeding: size the grid to about ctas_per_sm CTAs per SM
  * (default 512).  More chunks balance the heavy-tailed per-group cost; every chunk pays one unseeded frame. */

@@ -198,9 +198,12 @@ def test_seed_carry_between_calls_is_only_a_hint(fpv, cuda_dev):
         for a in (a0, a0, a1):
             got = fpv.distChamfer(torch.tensor(a, device=cuda_dev), bt, clip=True)
             _assert_exact([o.cpu().numpy() for o in got], co.dist_chamfer(a, b))
-        seeds = sp.cached_scene(bt).seeds[(4, 2500)]
+        seeds = sp.cached_scene(bt).seeds[("b2a", 4, 2500)]
         assert seeds.min().item() >= 0 and seeds.max().item() < 2500       # populated by the calls above
         seeds.copy_(torch.randint(-5, 4000, seeds.shape, device=cuda_dev, dtype=torch.int32))   # garbage, partly invalid
+        seeds_a = sp.cached_scene(bt).seeds[("a2b", 4, 2500)]
+        assert seeds_a.min().item() >= 0 and seeds_a.max().item() < 20000
+        seeds_a.copy_(torch.randint(-5, 30000, seeds_a.shape, device=cuda_dev, dtype=torch.int32))
         got = fpv.distChamfer(torch.tensor(a1, device=cuda_dev), bt, clip=True)
         _assert_exact([o.cpu().numpy() for o in got], co.dist_chamfer(a1, b))
     finally:
