@@ -26,6 +26,8 @@
 //                           over them alone seeds every query with a near-optimal best distance.
 #include <math_constants.h>
 
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace fpv {
@@ -579,7 +581,7 @@ __global__ void __launch_bounds__(CU_WARPS * 32, MINB) nn_sphere_kernel(const Sp
     const int b0 = blockIdx.y * p.frames_per_cta;
     const int b1 = (b0 + p.frames_per_cta < p.batches) ? b0 + p.frames_per_cta : p.batches;
     float *smx = stile[warp][0], *smy = stile[warp][1], *smz = stile[warp][2];
-    float qx[CU_QPT], qy[CU_QPT], qz[CU_QPT], best[CU_QPT], xs[CU_QPT];
+    float qx[CU_QPT], qy[CU_QPT], qz[CU_QPT], best[CU_QPT];
     int bidx[CU_QPT];
     bool canonical = false;  // warp-uniform: a query too large for the expanded forms
     unsigned long long searched = 0;
@@ -597,7 +599,6 @@ __global__ void __launch_bounds__(CU_WARPS * 32, MINB) nn_sphere_kernel(const Sp
                 qz[k] = __ldg(qsrc + 3 * qi + 2);
                 const float x2 = fmaf(qz[k], qz[k], fmaf(qy[k], qy[k], qx[k] * qx[k]));
                 big |= x2 > 1e30f;
-                xs[k] = x2 * (1.0f - SPH_SLACK);
             }
             canonical = __ballot_sync(0xffffffffu, big) != 0;
         }
@@ -680,9 +681,10 @@ __global__ void __launch_bounds__(CU_WARPS * 32, MINB) nn_sphere_kernel(const Sp
             float sq[CU_QPT], a[CU_QPT];
 #pragma unroll
             for (int k = 0; k < CU_QPT; ++k) {
+                const float xs = fmaf(qz[k], qz[k], fmaf(qy[k], qy[k], qx[k] * qx[k])) * (1.0f - SPH_SLACK);
                 sq[k] = sqrtf(best[k]) * 1.000001f;
-                a[k] = fmaf(-sq[k] * sq[k], 1.0f + SPH_SLACK, xs[k]);
-                thrb[k] = best[k] - xs[k];
+                a[k] = fmaf(-sq[k] * sq[k], 1.0f + SPH_SLACK, xs);
+                thrb[k] = best[k] - xs;
             }
             sq2[0] = make_float2(sq[0], sq[1]);
             sq2[1] = make_float2(sq[2], sq[3]);
@@ -693,64 +695,73 @@ __global__ void __launch_bounds__(CU_WARPS * 32, MINB) nn_sphere_kernel(const Sp
         // entry index space: level 0 at [0, n0p), level 1 at [n0p, n0p + n1p), level 2 behind; n0p = 4 n1, n1p = 4 n2
         const int n0p = 4 * p.n1, n1p = 4 * p.n2, n2p = (p.n2 + 3) & ~3;
         const float4 *xp = tab + 2 * (n0p + n1p + n2p);
-        // four sibling spheres at a time (one 128-byte line, independent FMA chains); bit i of the result is warp-uniform
-        auto test4 = [&](int first) -> unsigned {
-            const float4 *g = tab + 2 * first;
-            float4 e[4];
-            float lim[4];
+        // The traversal is instantiated twice: the normal path carries no trace of the canonical fallback (no flag to
+        // keep in a register or reload on the critical path of every test).
+        auto traverse = [&](auto canon_tag) {
+            constexpr bool CANON = decltype(canon_tag)::value;
+            // four sibling spheres at a time (one 128-byte line, independent FMA chains); bit i is warp-uniform
+            auto test4 = [&](int first) -> unsigned {
+                const float4 *g = tab + 2 * first;
+                float4 e[4];
+                float lim[4];
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                e[i] = __ldg(g + 2 * i);
-                lim[i] = __ldg(reinterpret_cast<const float *>(g + 2 * i + 1));
-            }
-            unsigned mask = 0;
+                for (int i = 0; i < 4; ++i) {
+                    e[i] = __ldg(g + 2 * i);
+                    lim[i] = __ldg(reinterpret_cast<const float *>(g + 2 * i + 1));
+                }
+                unsigned mask = 0;
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                // canonical mode asks for everything that is not padding (lim != NaN)
-                const bool need = canonical ? (lim[i] == lim[i]) : sphere_needed(e[i], lim[i], qx2, qy2, qz2, sq2, a2);
-                if (__ballot_sync(0xffffffffu, need)) mask |= 1u << i;
-            }
-            return mask;
-        };
-        for (int u0 = 0; u0 < n2p; u0 += 4) {
-            unsigned m2 = test4(n0p + n1p + u0);
-            while (m2) {
-                const int u = u0 + __ffs(m2) - 1;
-                m2 &= m2 - 1;
-                unsigned m1 = test4(n0p + 4 * u);
-                while (m1) {
-                    const int m = 4 * u + __ffs(m1) - 1;
-                    m1 &= m1 - 1;
-                    unsigned m0 = test4(4 * m);
-                    while (m0) {
-                        const int c = 4 * m + __ffs(m0) - 1;
-                        m0 &= m0 - 1;
-                        const int j0 = c * TILE;
-                        ++searched;
-                        if (!canonical) {
-                            const float cr2s = SPH_SLACK * __ldg(reinterpret_cast<const float *>(tab + 2 * c + 1) + 1);
-                            float thr[CU_QPT];
+                for (int i = 0; i < 4; ++i) {
+                    // canonical mode asks for everything that is not padding (lim != NaN)
+                    const bool need = CANON ? (lim[i] == lim[i]) : sphere_needed(e[i], lim[i], qx2, qy2, qz2, sq2, a2);
+                    if (__ballot_sync(0xffffffffu, need)) mask |= 1u << i;
+                }
+                return mask;
+            };
+            for (int u0 = 0; u0 < n2p; u0 += 4) {
+                unsigned m2 = test4(n0p + n1p + u0);
+                while (m2) {
+                    const int u = u0 + __ffs(m2) - 1;
+                    m2 &= m2 - 1;
+                    unsigned m1 = test4(n0p + 4 * u);
+                    while (m1) {
+                        const int m = 4 * u + __ffs(m1) - 1;
+                        m1 &= m1 - 1;
+                        unsigned m0 = test4(4 * m);
+                        while (m0) {
+                            const int c = 4 * m + __ffs(m0) - 1;
+                            m0 &= m0 - 1;
+                            const int j0 = c * TILE;
+                            ++searched;
+                            if (!CANON) {
+                                const float cr2s = SPH_SLACK * __ldg(reinterpret_cast<const float *>(tab + 2 * c + 1) + 1);
+                                float thr[CU_QPT];
 #pragma unroll
-                            for (int k = 0; k < CU_QPT; ++k) thr[k] = thrb[k] + cr2s;
-                            if (sphere_search_tile<TILE>(xp + j0, planes + j0, p.Mp, oidx + j0, qx, qy, qz, thr, best, bidx))
-                                refresh();
-                        } else {
-                            __syncwarp();
-                            if (TILE >= 32 || lane < TILE) {
+                                for (int k = 0; k < CU_QPT; ++k) thr[k] = thrb[k] + cr2s;
+                                if (sphere_search_tile<TILE>(xp + j0, planes + j0, p.Mp, oidx + j0, qx, qy, qz, thr, best, bidx))
+                                    refresh();
+                            } else {
+                                __syncwarp();
+                                if (TILE >= 32 || lane < TILE) {
 #pragma unroll
-                                for (int cc = 0; cc < TILE; cc += 32) {
-                                    smx[cc + lane] = planes[j0 + cc + lane];
-                                    smy[cc + lane] = planes[p.Mp + j0 + cc + lane];
-                                    smz[cc + lane] = planes[2 * p.Mp + j0 + cc + lane];
+                                    for (int cc = 0; cc < TILE; cc += 32) {
+                                        smx[cc + lane] = planes[j0 + cc + lane];
+                                        smy[cc + lane] = planes[p.Mp + j0 + cc + lane];
+                                        smz[cc + lane] = planes[2 * p.Mp + j0 + cc + lane];
+                                    }
                                 }
+                                __syncwarp();
+                                cu_search_tile<TILE>(smx, smy, smz, oidx + j0, qx, qy, qz, best, bidx);
                             }
-                            __syncwarp();
-                            cu_search_tile<TILE>(smx, smy, smz, oidx + j0, qx, qy, qz, best, bidx);
                         }
                     }
                 }
             }
-        }
+        };
+        if (canonical)
+            traverse(std::true_type{});
+        else
+            traverse(std::false_type{});
 #pragma unroll
         for (int k = 0; k < CU_QPT; ++k) {
             const int64_t qi = q0 + k * 32 + lane;
