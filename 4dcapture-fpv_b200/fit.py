@@ -201,21 +201,26 @@ class FitProblem:
         return losses["total"].detach()
 
     def capture(self, warmup: int = 3):
-        """Capture zero_grad -> forward -> backward as ONE CUDA graph: ~280 kernel
-        launches, no host synchronisation, no allocation at replay.  Returns self; step_graph() replays.
+        """Capture zero_grad -> forward -> backward as ONE CUDA graph (SURVEY.md section
+        8f, row f1): ~250 kernel launches, no host synchronisation, no allocation at replay.  Returns self;
+        step_graph() replays.
 
         Everything the step touches is capture-safe by construction: the library entry points only enqueue work
-        on the caller's stream into caller-provided workspaces, the scene index is cached (built during warm-up),
-        and the per-step tensors come from torch's graph-private pool.  Single-rank only: the sharded step keeps
-        its NCCL combine outside a graph."""
+        on the caller's stream into caller-provided workspaces, the scene index and the seed buffers are cached (built
+        during warm-up; the kernels update the seeds in place), the per-step tensors come from torch's graph-private
+        pool.  After capture the leaves, the observed data and the scene are STATIC buffers: change them in place
+        (copy_), never rebind them -- and the scene must stay what it was (its index is not part of the graph).
+        Single-rank only: capturing the sharded step together with its NCCL collectives deadlocked on 2 GPUs in round 1
+        (both ranks blocked inside the capture), so the sharded step stays eager."""
         if self.world != 1:
-            raise RuntimeError("FitProblem.capture: single-rank only")
+            raise RuntimeError("FitProblem.capture: single-rank only (the sharded step keeps its NCCL combine outside a graph)")
         side = torch.cuda.Stream(self.device)
         side.wait_stream(torch.cuda.current_stream(self.device))
         with torch.cuda.stream(side):
             for _ in range(max(1, warmup)):
                 self.step()
         torch.cuda.current_stream(self.device).wait_stream(side)
+        torch.cuda.synchronize(self.device)
         for t in self.leaves():
             t.grad = None
         self._graph = torch.cuda.CUDAGraph()
@@ -226,10 +231,29 @@ class FitProblem:
         return self
 
     def step_graph(self) -> torch.Tensor:
-        """Replay the captured step: gradients land in the leaves' .grad (static buffers), returns the loss tensor
-        (static; overwritten by the next replay)."""
+        """Replay the captured step: gradients land in the leaves' .grad (static buffers), returns the (global) loss
+        tensor (static; overwritten by the next replay)."""
         self._graph.replay()
         return self._graph_loss
+
+    def step_e2e_graph(self):
+        """End to end through the captured step: every per-step input goes from pinned host memory into the static
+        device buffers, the graph is replayed, loss + gradients come back to the host.  The scene is resident, as in
+        the reference (uploaded once before the loop, global_optimization.py:173-176)."""
+        with torch.no_grad():
+            self.data.copy_(self.host_params, non_blocking=True)
+            self.params.copy_(self._host_init, non_blocking=True)
+            self.scale.copy_(self.host_scale, non_blocking=True)
+            self.camera_ext.copy_(self.host_camera_ext, non_blocking=True)
+            if self.front_end and self.dct_batches:
+                self.c_dct.copy_(self.host_c_dct, non_blocking=True)
+        loss = self.step_graph()
+        host = [loss.to("cpu", non_blocking=True)] + [t.grad.to("cpu", non_blocking=True) for t in self.leaves()]
+        torch.cuda.synchronize(self.device)
+        return host
+
+    def h2d_bytes_graph(self) -> int:
+        return self.h2d_bytes() - 4 * (self.end - self.begin) * 3
 
     def step_e2e(self):
         """The same step from HOST buffers: pinned inputs -> device, step, loss + gradients -> host."""

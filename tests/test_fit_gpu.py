@@ -113,3 +113,15 @@ def test_fit_step_with_reference_front_end_matches_oracle(fpv, cuda_dev):
     assert prob.step().item() == loss.item()
     prob.capture()
     assert torch.equal(prob.step_graph(), loss)
+
+
+def test_fit_e2e_graph_matches_eager(fpv, cuda_dev):
+    """The end-to-end path through the captured step (host inputs -> static buffers -> replay -> host results) returns
+    what the eager step returns."""
+    prob = fpv.FitProblem(T=5, M=9000, device=cuda_dev, seed=1239, front_end=True, dct_frames=2)
+    eager = prob.step_e2e()
+    prob.capture()
+    graph = prob.step_e2e_graph()
+    assert len(graph) == len(eager)
+    for g, e in zip(graph, eager):
+        assert torch.equal(g, e)

@@ -38,10 +38,11 @@ def _worker(rank, world, init_file, out_dir):
     prob = fpv.FitProblem(T=4, M=30_000, device=dev, seed=1236, rank=rank, world_size=world)
     fl = prob.step().clone()
     dist.all_reduce(fl)
+    fit_grad, fit_scale = prob.params.grad.clone(), prob.scale.grad.clone()
     np.savez(os.path.join(out_dir, f"r{rank}.npz"), d_a2b=d_a2b.detach().cpu().numpy(), i_a2b=i_a2b.cpu().numpy(),
              d_b2a=d_b2a.detach().cpu().numpy(), i_b2a=i_b2a.cpu().numpy(), grad=a.grad.cpu().numpy(),
              a=a0.numpy(), scene=scene.numpy(), w1=w1.numpy(), w2=w2.numpy(), lo=lo, hi=hi,
-             fit_loss=fl.cpu().numpy(), fit_grad=prob.params.grad.cpu().numpy(), fit_scale=prob.scale.grad.cpu().numpy())
+             fit_loss=fl.cpu().numpy(), fit_grad=fit_grad.cpu().numpy(), fit_scale=fit_scale.cpu().numpy())
     dist.destroy_process_group()
 
 
