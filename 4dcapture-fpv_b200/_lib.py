@@ -63,6 +63,8 @@ SIGNATURES = {
     "fpv_nn_culled_search": (c_int, [c_void_p, c_int, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_int64, c_int64,
                                      c_int, c_int64, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int,
                                      c_void_p]),
+    "fpv_morton_keys": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "fpv_nn_gather_pack": (c_int, [c_void_p, c_void_p, c_int, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_void_p]),
     "fpv_nn_sphere_table_floats": (c_size_t, [c_int64, c_int]),
     "fpv_nn_sphere_table": (c_int, [c_void_p, c_int64, c_int64, c_int, c_void_p, c_void_p]),
     "fpv_nn_sphere_search": (c_int, [c_void_p, c_int, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,

@@ -884,6 +884,62 @@ __global__ void sphere_expand_kernel(const float *__restrict__ planes, int64_t M
     out[3] = make_float4(w[0], w[1], w[2], w[3]);
 }
 
+// ---- ordering helpers: one launch each instead of dozens of elementwise torch ops per step -------------------
+__device__ __forceinline__ unsigned spread10(unsigned v) {
+    v &= 0x3FFu;
+    v = (v | (v << 16)) & 0x030000FFu;
+    v = (v | (v << 8)) & 0x0300F00Fu;
+    v = (v | (v << 4)) & 0x030C30C3u;
+    v = (v | (v << 2)) & 0x09249249u;
+    return v;
+}
+
+// 30-bit Morton code on the grid (lo, inv_cell); non-finite coordinates go to the ends of the axis (they never win a
+// search, their position in the order is irrelevant).  Same arithmetic as spatial.morton_keys.
+__global__ void morton_keys_kernel(const float *__restrict__ pts, int64_t n, const float *__restrict__ lo,
+                                   const float *__restrict__ inv_cell, long long *__restrict__ keys) {
+    const int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    unsigned q[3];
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        float v = (pts[3 * i + a] - lo[a]) * inv_cell[a];
+        if (v != v || v == CUDART_INF_F) v = 1023.0f;   // nan_to_num(nan=1023, posinf=1023, neginf=0)
+        if (v == -CUDART_INF_F) v = 0.0f;
+        v = fminf(fmaxf(v, 0.0f), 1023.0f);
+        q[a] = unsigned(v);                             // truncation, like .to(int64)
+    }
+    keys[i] = (long long)(spread10(q[0]) | (spread10(q[1]) << 1) | (spread10(q[2]) << 2));
+}
+
+// sorted[b][j] = pts[b][perm[j]], SoA planes (+inf padded) and the original-index table (INT32_MAX padded) in one pass
+__global__ void gather_pack_kernel(const float *__restrict__ pts, const long long *__restrict__ perm, int64_t perm_bstride,
+                                   int64_t M, int64_t Mp, float *__restrict__ sorted, float *__restrict__ planes,
+                                   int *__restrict__ oidx) {
+    const int64_t b = blockIdx.y;
+    const int64_t j = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (j >= Mp) return;
+    float x = CUDART_INF_F, y = CUDART_INF_F, z = CUDART_INF_F;
+    int o = 0x7fffffff;
+    if (j < M) {
+        const long long src = perm[b * perm_bstride + j];
+        const float *s = pts + (b * M + src) * 3;
+        x = s[0];
+        y = s[1];
+        z = s[2];
+        o = int(src);
+        float *d = sorted + (b * M + j) * 3;
+        d[0] = x;
+        d[1] = y;
+        d[2] = z;
+    }
+    float *pl = planes + b * 3 * Mp;
+    pl[j] = x;
+    pl[Mp + j] = y;
+    pl[2 * Mp + j] = z;
+    oidx[b * Mp + j] = o;
+}
+
 }  // namespace fpv
 
 using namespace fpv;
@@ -1082,6 +1138,28 @@ int fpv_nn_sphere_search(const float *queries, int q_shared, int64_t batches, in
         nn_sphere_kernel<32, 8><<<grid, CU_WARPS * 32, 0, st>>>(p);
     profile_end(st);
     FPV_LAUNCH_CHECK("nn_sphere_kernel");
+    return FPV_OK;
+}
+
+/* 30-bit Morton keys of n points on the grid (lo[3], inv_cell[3] device pointers). */
+int fpv_morton_keys(const float *pts, int64_t n, const float *lo, const float *inv_cell, long long *keys, fpv_stream_t stream) {
+    FPV_CHECK_ARG(pts && lo && inv_cell && keys && n > 0, "fpv_morton_keys: bad arguments");
+    morton_keys_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(pts, n, lo, inv_cell, keys);
+    FPV_LAUNCH_CHECK("morton_keys_kernel");
+    return FPV_OK;
+}
+
+/* Apply an ordering: sorted [B][M][3], planes (fpv_nn_planes_bytes) and orig_idx [B][Mp] from pts [B][M][3] and
+ * perm ([M] shared by every batch entry when perm_shared, else [B][M]; int64 sorted position -> original index). */
+int fpv_nn_gather_pack(const float *pts, const long long *perm, int perm_shared, int64_t batches, int64_t M, float *sorted,
+                       float *planes, int32_t *orig_idx, fpv_stream_t stream) {
+    FPV_CHECK_ARG(pts && perm && sorted && planes && orig_idx, "fpv_nn_gather_pack: null pointer");
+    FPV_CHECK_ARG(batches > 0 && batches <= 65535 && M > 0, "fpv_nn_gather_pack: bad sizes");
+    const int64_t Mp = ceil_div(M, 64) * 64;
+    dim3 grid((unsigned)ceil_div(Mp, 256), (unsigned)batches);
+    gather_pack_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(pts, perm, perm_shared ? 0 : M, M, Mp, sorted,
+                                                                            planes, orig_idx);
+    FPV_LAUNCH_CHECK("gather_pack_kernel");
     return FPV_OK;
 }
 

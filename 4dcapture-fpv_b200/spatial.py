@@ -60,32 +60,35 @@ class SortedCloud:
             lo, inv_cell = grid_of(points)
         self.lo, self.inv_cell = lo, inv_cell
         self.shared_perm = bool(shared_perm and B > 1)
-        if self.shared_perm:
-            # One ordering for every batch entry, taken from the middle one: the batch is a clip of ONE articulated
-            # surface, so points that are neighbours in one frame stay neighbours in all of them.  The order only
-            # shapes the clusters (their spheres are rebuilt from the actual points of each frame), never the result.
-            keys = morton_keys(points[B // 2:B // 2 + 1], lo, inv_cell)
-            self.perm = torch.argsort(keys, dim=1).expand(B, -1)
-        else:
-            keys = morton_keys(points, lo, inv_cell)
-            self.perm = torch.argsort(keys, dim=1, stable=(B == 1))              # sorted position -> original index
-        # a cloud that already arrives in Morton order (FitProblem pre-sorts its scene once) needs no gather on the
-        # way in and no un-permute of the results on the way out; checked once per cached cloud, never per step
-        self.identity = bool(check_identity and B == 1 and
-                             torch.equal(self.perm[0], torch.arange(M, device=points.device)))
-        if self.identity:
-            self.sorted = points.contiguous()
-        elif self.shared_perm:
-            self.sorted = points.index_select(1, self.perm[0]).contiguous()
-        else:
-            self.sorted = torch.gather(points, 1, self.perm.unsqueeze(-1).expand(-1, -1, 3)).contiguous()
+        dev = points.device
+        pts = points.contiguous()
+        lo_c, ic_c = lo.to(torch.float32).contiguous(), inv_cell.to(torch.float32).contiguous()
         Mp = (M + 63) // 64 * 64
-        self.oidx = torch.full((B, Mp), INT32_MAX, dtype=torch.int32, device=points.device)
-        self.oidx[:, :M] = self.perm.to(torch.int32)
-        with torch.cuda.device(points.device):
-            self.planes = torch.empty(L.fpv_nn_planes_bytes(B, M) // 4, dtype=torch.float32, device=points.device)
-            _lib.check(L.fpv_nn_pack_planes(_lib.ptr(self.sorted), B, M, _lib.ptr(self.planes), _lib.stream_ptr()),
-                       "fpv_nn_pack_planes")
+        with torch.cuda.device(dev):
+            if self.shared_perm:
+                # One ordering for every batch entry, taken from the middle one: the batch is a clip of ONE articulated
+                # surface, so points that are neighbours in one frame stay neighbours in all of them.  The order only
+                # shapes the clusters (their spheres are rebuilt from the actual points of each frame), never the result.
+                keys = torch.empty(M, dtype=torch.int64, device=dev)
+                _lib.check(L.fpv_morton_keys(_lib.ptr(pts[B // 2]), M, _lib.ptr(lo_c), _lib.ptr(ic_c), _lib.ptr(keys),
+                                             _lib.stream_ptr()), "fpv_morton_keys")
+                perm_c = torch.argsort(keys)                                         # sorted position -> original index
+                self.perm = perm_c.unsqueeze(0).expand(B, -1)
+            else:
+                keys = torch.empty(B, M, dtype=torch.int64, device=dev)
+                _lib.check(L.fpv_morton_keys(_lib.ptr(pts), B * M, _lib.ptr(lo_c), _lib.ptr(ic_c), _lib.ptr(keys),
+                                             _lib.stream_ptr()), "fpv_morton_keys")
+                self.perm = perm_c = torch.argsort(keys, dim=1, stable=(B == 1))
+            # a cloud that already arrives in Morton order (FitProblem pre-sorts its scene once) needs no gather on the
+            # way in and no un-permute of the results on the way out; checked once per cached cloud, never per step
+            self.identity = bool(check_identity and B == 1 and torch.equal(self.perm[0], torch.arange(M, device=dev)))
+            # sorted points, padded SoA planes and the original-index table in one pass
+            self.sorted = torch.empty_like(pts)
+            self.planes = torch.empty(L.fpv_nn_planes_bytes(B, M) // 4, dtype=torch.float32, device=dev)
+            self.oidx = torch.empty((B, Mp), dtype=torch.int32, device=dev)
+            _lib.check(L.fpv_nn_gather_pack(_lib.ptr(pts), _lib.ptr(perm_c), int(self.shared_perm), B, M, _lib.ptr(self.sorted),
+                                            _lib.ptr(self.planes), _lib.ptr(self.oidx), _lib.stream_ptr()),
+                       "fpv_nn_gather_pack")
             self.sphere_tile = sphere_tile
             if sphere_tile:
                 self.boxes = torch.empty(B * L.fpv_nn_sphere_table_floats(M, sphere_tile), dtype=torch.float32,

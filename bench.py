@@ -230,11 +230,13 @@ def run_b200(args):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     e0.record()
+    t_host = time.perf_counter()
     for _ in range(K):
         if args.jitter > 0:
             with torch.no_grad():
                 prob.params.add_(torch.randn_like(prob.params) * args.jitter)
         prob.step()
+    host_ms_per_step = (time.perf_counter() - t_host) * 1e3 / K     # host time to ENQUEUE a step (no sync inside)
     e1.record()
     barrier()
     ms_total = max_over_ranks(e0.elapsed_time(e1))
@@ -361,7 +363,7 @@ def run_b200(args):
                 "d2h_bytes_per_step": prob.d2h_bytes(), "wall_s": wall_e2e,
                 "inputs": "every step: observed data, parameters, scale, camera_ext, DCT coefficients AND the scene shard "
                           "from pinned host memory; loss + all gradients back"},
-        "launch": "eager",
+        "launch": "eager", "host_enqueue_ms_per_step_eager": host_ms_per_step,
         "gpu_launches": launches, "cuda_graph_replay": graph_info, "clocks": clocks, "fp32_lane_fma_per_s_measured": fma.value,
         "nn_kernels_share_of_step": kernel_ms / (ms_total / K),
         "kernels": {k: {"launches_per_step": len(v) / K, "ms_mean": statistics.mean(x[0] for x in v)} for k, v in by.items()},

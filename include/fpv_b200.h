@@ -102,6 +102,14 @@ int fpv_nn_culled_search(const float *queries, int q_shared, int64_t batches, in
  *   [batches][N] int32 buffer of the previous call's winners (original indices, without idx_base), read as starting
  *   points when seed_valid and always overwritten -- hints only, see fpv_nn_sphere_search. */
 
+/* Ordering helpers of the spatial engines (one launch each): 30-bit Morton keys of n points on the grid
+ * (lo[3], inv_cell[3] are DEVICE pointers), and the application of an ordering -- sorted points, padded SoA planes
+ * and the original-index table in one pass (perm: int64, [M] when perm_shared, else [batches][M]). */
+int fpv_morton_keys(const float *pts, int64_t n, const float *lo, const float *inv_cell, long long *keys,
+                    fpv_stream_t stream);
+int fpv_nn_gather_pack(const float *pts, const long long *perm, int perm_shared, int64_t batches, int64_t M,
+                       float *sorted, float *planes, int32_t *orig_idx, fpv_stream_t stream);
+
 /* Frame chunking of fpv_nn_sphere_search with temporal seeding: size the grid to about ctas_per_sm CTAs per SM
  * (default 512).  More chunks balance the heavy-tailed per-group cost; every chunk pays one unseeded frame. */
 int fpv_nn_sphere_set_chunking(int ctas_per_sm);
