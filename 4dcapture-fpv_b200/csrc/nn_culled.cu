@@ -709,14 +709,14 @@ __global__ void __launch_bounds__(CU_WARPS * 32, MINB) nn_sphere_kernel(const Sp
                     e[i] = __ldg(g + 2 * i);
                     lim[i] = __ldg(reinterpret_cast<const float *>(g + 2 * i + 1));
                 }
-                unsigned mask = 0;
+                unsigned mine = 0;
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
                     // canonical mode asks for everything that is not padding (lim != NaN)
                     const bool need = CANON ? (lim[i] == lim[i]) : sphere_needed(e[i], lim[i], qx2, qy2, qz2, sq2, a2);
-                    if (__ballot_sync(0xffffffffu, need)) mask |= 1u << i;
+                    mine |= unsigned(need) << i;
                 }
-                return mask;
+                return __reduce_or_sync(0xffffffffu, mine);   // one warp-wide OR instead of four votes
             };
             for (int u0 = 0; u0 < n2p; u0 += 4) {
                 unsigned m2 = test4(n0p + n1p + u0);
