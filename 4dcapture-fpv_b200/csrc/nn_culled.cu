@@ -1129,7 +1129,7 @@ int fpv_nn_sphere_search(const float *queries, int q_shared, int64_t batches, in
         snprintf(nm, sizeof(nm), "nn_sphere<%d> Q=%lld M=%lld", tile, (long long)(batches * N), (long long)M);
         profile_begin(nm, st,
                       12.0 * double(q_shared ? N : batches * N) + 24.0 * double(M) * double(batches) +
-                          (4.0 + idx_bytes) * double(batches * N),
+                          (4.0 + idx_bytes + (seed_inout ? 4.0 : 0.0) + (p.seed_read ? 4.0 : 0.0)) * double(batches * N),
                       double(batches * N) * double(M));
     }
     if (tile == 16)
