@@ -512,9 +512,8 @@ __device__ __forceinline__ bool sphere_needed(const float4 e, const float lim, c
 // Search one cluster, read as expanded groups (-2y, |y|^2) straight from L1, for the warp's 128 queries; returns true when a query of this lane
 // improved.  thr[q] = best[q] - |x_q|^2 (1 - s) + s (|c| + r)^2.
 template <int TILE>
-__device__ __forceinline__ bool sphere_search_tile(const float4 *__restrict__ xp_tile,
-                                                   const float *__restrict__ planes_tile, int64_t Mp,
-                                                   const int *__restrict__ oidx_tile, const float (&qx)[CU_QPT],
+__device__ __forceinline__ bool sphere_search_tile(const float4 *__restrict__ xp_tile, const SphereParams &p, int b, int j0,
+                                                   const float (&qx)[CU_QPT],
                                                    const float (&qy)[CU_QPT], const float (&qz)[CU_QPT],
                                                    const float (&thr)[CU_QPT], float (&best)[CU_QPT],
                                                    int (&bidx)[CU_QPT]) {
@@ -542,6 +541,10 @@ __device__ __forceinline__ bool sphere_search_tile(const float4 *__restrict__ xp
             any |= hit[q];
         }
         if (any) {  // rare: canonical re-evaluation of the four candidates, lexicographic update
+            // (the plane / index addresses are formed here, not on the hot path)
+            const float *planes_tile = p.planes + int64_t(b) * p.plane_bstride + j0;
+            const int *oidx_tile = p.oidx + int64_t(b) * p.oidx_bstride + j0;
+            const int64_t Mp = p.Mp;
             float rx[4], ry[4], rz[4];
             int o[4];
 #pragma unroll
@@ -738,7 +741,7 @@ __global__ void __launch_bounds__(CU_WARPS * 32, MINB) nn_sphere_kernel(const Sp
                                 float thr[CU_QPT];
 #pragma unroll
                                 for (int k = 0; k < CU_QPT; ++k) thr[k] = thrb[k] + cr2s;
-                                if (sphere_search_tile<TILE>(xp + j0, planes + j0, p.Mp, oidx + j0, qx, qy, qz, thr, best, bidx))
+                                if (sphere_search_tile<TILE>(xp + j0, p, b, j0, qx, qy, qz, thr, best, bidx))
                                     refresh();
                             } else {
                                 __syncwarp();
