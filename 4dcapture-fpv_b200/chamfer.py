@@ -28,7 +28,7 @@ from . import _lib, spatial
 ENGINE = "auto"
 SPATIAL_MIN_POINTS = 4096
 # scene -> body inside the spatial path:
-#   "sphere"  three-level bounding-sphere hierarchy over the per-frame Morton-sorted body, per-query triangle-inequality
+#   "sphere"  four-level bounding-sphere hierarchy over the per-frame Morton-sorted body, per-query triangle-inequality
 #             tests, temporal seeding from the previous frame's winner (nn_culled.cu nn_sphere_kernel)   [default]
 #   "rep"     single-level representative/radius culling over 32-vertex clusters (nn_culled.cu rep mode)
 #   "tc"      tensor-core filter over all vertices (nn_tc.cu)

@@ -448,7 +448,7 @@ __global__ void super_boxes_kernel(const float *__restrict__ planes, int64_t M, 
 
 // =====================================================================================================
 // Sphere-hierarchy mode (scene -> body): candidates are per-frame Morton-sorted body vertices cut into
-// clusters of TILE points with a 3-level hierarchy of bounding spheres (TILE, 4*TILE, 16*TILE points).
+// clusters of TILE points with a 4-level hierarchy of bounding spheres (TILE, 4*TILE, 16*TILE, 64*TILE points).
 // A query needs a cluster only if |x - c| <= sqrt(best_x) + r  (triangle inequality, PER QUERY; the warp
 // searches a cluster when any of its 128 spatially adjacent queries needs it).  When the query set is shared
 // by consecutive frames of a clip, a warp walks a chunk of frames and seeds every query with the exact distance
@@ -482,7 +482,7 @@ struct SphereParams {
     const float *cand_orig;  // [cand batches][M][3] candidates in ORIGINAL order (temporal seeding), may be null
     int *seed;               // [batches][N] in/out: last call's winners (original indices; < 0 = none), may be null
     int seed_read;           // 0: the buffer holds nothing yet, only write it
-    int n0, n1, n2;
+    int n0, n1, n2, n3;
     int batches, frames_per_cta;
     int64_t idx_base;
     float *dist;
@@ -695,9 +695,10 @@ __global__ void __launch_bounds__(CU_WARPS * 32, MINB) nn_sphere_kernel(const Sp
             a2[1] = make_float2(a[2], a[3]);
         };
         refresh();
-        // entry index space: level 0 at [0, n0p), level 1 at [n0p, n0p + n1p), level 2 behind; n0p = 4 n1, n1p = 4 n2
-        const int n0p = 4 * p.n1, n1p = 4 * p.n2, n2p = (p.n2 + 3) & ~3;
-        const float4 *xp = tab + 2 * (n0p + n1p + n2p);
+        // entry index space: level 0 at [0, n0p), level 1 behind it, then level 2, then level 3 (TILE*64 points per
+        // sphere); n0p = 4 n1, n1p = 4 n2, n2p = 4 n3: every sphere's four children are one aligned sibling group
+        const int n0p = 4 * p.n1, n1p = 4 * p.n2, n2p = 4 * p.n3, n3p = (p.n3 + 3) & ~3;
+        const float4 *xp = tab + 2 * (n0p + n1p + n2p + n3p);
         // The traversal is instantiated twice: the normal path carries no trace of the canonical fallback (no flag to
         // keep in a register or reload on the critical path of every test).
         auto traverse = [&](auto canon_tag) {
@@ -721,10 +722,14 @@ __global__ void __launch_bounds__(CU_WARPS * 32, MINB) nn_sphere_kernel(const Sp
                 }
                 return __reduce_or_sync(0xffffffffu, mine);   // one warp-wide OR instead of four votes
             };
-            for (int u0 = 0; u0 < n2p; u0 += 4) {
-                unsigned m2 = test4(n0p + n1p + u0);
+            for (int w0 = 0; w0 < n3p; w0 += 4) {
+              unsigned m3 = test4(n0p + n1p + n2p + w0);
+              while (m3) {
+                const int w = w0 + __ffs(m3) - 1;
+                m3 &= m3 - 1;
+                unsigned m2 = test4(n0p + n1p + 4 * w);
                 while (m2) {
-                    const int u = u0 + __ffs(m2) - 1;
+                    const int u = 4 * w + __ffs(m2) - 1;
                     m2 &= m2 - 1;
                     unsigned m1 = test4(n0p + 4 * u);
                     while (m1) {
@@ -759,6 +764,7 @@ __global__ void __launch_bounds__(CU_WARPS * 32, MINB) nn_sphere_kernel(const Sp
                         }
                     }
                 }
+              }
             }
         };
         if (canonical)
@@ -785,16 +791,18 @@ __global__ void __launch_bounds__(CU_WARPS * 32, MINB) nn_sphere_kernel(const Sp
 
 // Padded level sizes of the sphere table (whole sibling groups of 4 on every level).
 struct SphereLayout {
-    int n0, n1, n2, n0p, n1p, n2p;
+    int n0, n1, n2, n3, n0p, n1p, n2p, n3p;
     __host__ __device__ SphereLayout(int64_t M, int tile) {
         n0 = int((M + tile - 1) / tile);
         n1 = (n0 + 3) / 4;
         n2 = (n1 + 3) / 4;
+        n3 = (n2 + 3) / 4;
         n0p = 4 * n1;
         n1p = 4 * n2;
-        n2p = (n2 + 3) & ~3;
+        n2p = 4 * n3;
+        n3p = (n3 + 3) & ~3;
     }
-    __host__ __device__ int entries() const { return n0p + n1p + n2p; }
+    __host__ __device__ int entries() const { return n0p + n1p + n2p + n3p; }
     __host__ __device__ int64_t float4s(int tile) const { return 2 * int64_t(entries()) + int64_t(n0p) * tile; }
 };
 
@@ -808,7 +816,11 @@ __global__ void sphere_table_kernel(const float *__restrict__ planes, int64_t M,
     if (e >= L.entries()) return;
     int64_t span = tile, first = e;
     int real = L.n0;
-    if (e >= L.n0p + L.n1p) {
+    if (e >= L.n0p + L.n1p + L.n2p) {
+        span = int64_t(tile) * 64;
+        first = e - L.n0p - L.n1p - L.n2p;
+        real = L.n3;
+    } else if (e >= L.n0p + L.n1p) {
         span = int64_t(tile) * 16;
         first = e - L.n0p - L.n1p;
         real = L.n2;
@@ -1102,6 +1114,7 @@ int fpv_nn_sphere_search(const float *queries, int q_shared, int64_t batches, in
     p.n0 = L.n0;
     p.n1 = L.n1;
     p.n2 = L.n2;
+    p.n3 = L.n3;
     p.table = reinterpret_cast<const float4 *>(table);
     p.table_bstride = L.float4s(tile);
     p.oidx = orig_idx;

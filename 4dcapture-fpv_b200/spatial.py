@@ -49,7 +49,7 @@ class SortedCloud:
     def __init__(self, points: torch.Tensor, lo: torch.Tensor = None, inv_cell: torch.Tensor = None, mode: int = 0,
                  sphere_tile: int = 0, check_identity: bool = False, shared_perm: bool = False):
         """mode 0: 64-point tiles with bounding boxes; mode 1: 32-point tiles with representative + radius.
-        sphere_tile (16 | 32): build the three-level bounding-sphere table of nn_sphere_kernel instead."""
+        sphere_tile (16 | 32): build the four-level bounding-sphere table of nn_sphere_kernel instead."""
         if points.dim() == 2:
             points = points.unsqueeze(0)
         _lib.require_cuda(points)

@@ -115,7 +115,7 @@ int fpv_nn_gather_pack(const float *pts, const long long *perm, int perm_shared,
 int fpv_nn_sphere_set_chunking(int ctas_per_sm);
 
 /* Sphere-hierarchy variant for moving candidate sets (scene -> body): clusters of `tile` (16 | 32) sorted points
- * with bounding spheres on three levels; a query needs a cluster only if |x - c| <= sqrt(best_x) + r.  With a
+ * with bounding spheres on four levels (tile, x4, x16, x64 points); a query needs a cluster only if |x - c| <= sqrt(best_x) + r.  With a
  * shared query set and cand_orig (the candidates in ORIGINAL order, [batches][M][3]) consecutive batches (frames)
  * seed each other: every query starts from the exact distance to its previous frame's winner.
  * seed_inout (optional, device, [batches][N] int32, needs cand_orig): the winners of the previous CALL on the same
