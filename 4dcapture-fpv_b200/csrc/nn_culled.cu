@@ -518,7 +518,7 @@ __device__ __forceinline__ bool sphere_search_tile(const float4 *__restrict__ xp
                                                    const float (&thr)[CU_QPT], float (&best)[CU_QPT],
                                                    int (&bidx)[CU_QPT]) {
     bool improved = false;
-#pragma unroll 2
+#pragma unroll
     for (int j4 = 0; j4 < TILE / 4; ++j4) {
         // warp-uniform addresses: every load is one broadcast request served by L1
         const float4 mx = __ldg(xp_tile + 4 * j4), my = __ldg(xp_tile + 4 * j4 + 1), mz = __ldg(xp_tile + 4 * j4 + 2),
