@@ -35,18 +35,21 @@ SPATIAL_MIN_POINTS = 4096
 B2A_ENGINE = "sphere"
 SPHERE_TILE = 16
 CARRY_SEEDS = os.environ.get("FPV_CARRY_SEEDS", "1") != "0"   # scene->body: start from the previous call's winners
-BODY_SHARED_ORDER = os.environ.get("FPV_BODY_SHARED_ORDER", "1") != "0"   # one Morton order (of the middle frame) for all frames of the clip; False: per-frame argsort
+# clip=True batches: one Morton order (of the middle frame) for all frames; "0": per-frame argsort
+BODY_SHARED_ORDER = os.environ.get("FPV_BODY_SHARED_ORDER", "1") != "0"
 LAST_STATS = {}
 
 
 def _forward_spatial(a_c: torch.Tensor, b_c: torch.Tensor, idx_dtype, idx_base: int = 0, clip: bool = False):
     """Both chamfer directions with the scene held in Morton order.  a_c [T,N,3], b_c [1,M,3].
 
-    a -> b (body vertex -> scene): the scene is static, so the box-culled tile search visits ~1 % of it.
-    b -> a (scene point -> body): far-field queries defeat box culling (SURVEY/DESIGN section 6), so this
-    direction stays brute force -- but its queries are issued in the scene's Morton order, which makes the rows of
-    a warp spatial neighbours: their running minima improve on the same candidate tiles and the tensor-core
-    filter's divergent exact re-checks collapse (profiles/r01_nn_tune6_tc_vs_simt.txt).
+    a -> b (body vertex -> scene): the scene is static; its Morton tiles + boxes are built once (spatial.cached_scene)
+    and the box-culled search with a per-query box test visits well under 1 % of it.
+    b -> a (scene point -> body): group-level box culling fails here (far points see near-equidistant vertices), so the
+    body is re-clustered every call and searched through a bounding-sphere hierarchy with PER-QUERY tests
+    (B2A_ENGINE="sphere"); the queries are issued in the scene's Morton order so that a warp's 128 queries are spatial
+    neighbours.  Both searches start from the winners of the previous call on the same scene (CARRY_SEEDS) -- hints
+    that never change the result.  DESIGN.md sections 4.3, 4.3b.
     """
     T, N, _ = a_c.shape
     M = b_c.shape[1]
