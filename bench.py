@@ -356,7 +356,7 @@ def run_b200(args):
                            (" / VPoser / DCT" if not args.no_front_end else "") + " residuals -> full backward",
                    "param_jitter_per_step": args.jitter,
                    "scene_order": "Morton-sorted once on the host" + (", dealt to ranks in blocks of 2048" if world > 1 else ""),
-                   "search": "body->scene: Morton-tiled box-culled exact search; scene->body: per-query bounding-sphere hierarchy over the Morton-sorted body with temporal seeding (exact)",
+                   "search": "body->scene: Morton-tiled box-culled exact search; scene->body: per-query bounding-sphere hierarchy over the Morton-sorted body; both seeded with the previous step's winners (hints; results exact)",
                    "l2": "per-step working set (>=2.4 GB of [T,M] outputs) exceeds the 126 MB L2; no explicit flush"},
         "roofline": roofline,
         "e2e": {"value": K / (ms_e2e * 1e-3), "unit": "steps/s", "h2d_bytes_per_step": prob.h2d_bytes(),
