@@ -224,7 +224,9 @@ class FitProblem:
         for t in self.leaves():
             t.grad = None
         self._graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self._graph):
+        # capture on the stream the warm-up ran on: the leaves' AccumulateGrad nodes then live on the capture stream and
+        # autograd inserts no dependency on the legacy default stream (illegal while a stream is capturing)
+        with torch.cuda.graph(self._graph, stream=side):
             losses = self.forward()
             losses["total"].backward()
             self._graph_loss = losses["total"].detach()
