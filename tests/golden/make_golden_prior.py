@@ -75,4 +75,19 @@ loss = go.FittingOP.cal_dctloss(fake, joints)
 loss.backward()
 np.savez(os.path.join(out, "prior_dct.npz"), basis=basis.numpy(), joints=joints.detach().numpy(), c_dct=c_dct.detach().numpy(),
          loss=loss.detach().numpy(), g_joints=joints.grad.numpy(), g_c=c_dct.grad.numpy())
-print("wrote prior_codec.npz, prior_dct.npz; loss_dct =", float(loss))
+print("wrote prior_codec.npz, prior_dct.npz; loss_dct =", float(loss.detach()))
+
+# ---- the world placement: the literal verts_transform (:119-127) and FittingOP.body2world (:191-206) ----
+torch.Tensor.cuda = lambda self, *a, **k: self                        # CPU shim for the per-frame `.cuda()` of :200
+T = 9
+verts = torch.randn(T, 57, 3, generator=g, dtype=torch.float32)
+cam_ext = torch.eye(4).repeat(T, 1, 1) + 0.05 * torch.randn(T, 4, 4, generator=g)
+cam_ext[:, 3, :] = torch.tensor([0.0, 0.0, 0.0, 1.0])
+rec = torch.randn(T, 78, generator=g)
+scale = torch.tensor([1.3])
+fake = types.SimpleNamespace(body_rotation_rec=rec, num_body=T, scale=scale, camera_ext=cam_ext)
+b2w = go.FittingOP.body2world(fake)
+vt = go.verts_transform(verts * scale, b2w)
+np.savez(os.path.join(out, "prior_world.npz"), verts=verts.numpy(), cam_ext=cam_ext.numpy(), rec=rec.numpy(), scale=scale.numpy(),
+         b2w=b2w.numpy(), vt=vt.numpy())
+print("wrote prior_world.npz")

@@ -63,3 +63,14 @@ def test_dct_loss_matches_reference_method():
     assert abs(float(loss.detach()) - float(d["loss"])) < 1e-12 * max(1.0, abs(float(d["loss"])))
     np.testing.assert_allclose(joints.grad.numpy(), d["g_joints"], rtol=1e-10, atol=1e-14)
     np.testing.assert_allclose(c.grad.numpy(), d["g_c"], rtol=1e-10, atol=1e-14)
+
+
+def test_world_placement_oracle_matches_reference_functions():
+    """oracle/residuals_oracle.py against the literal verts_transform and FittingOP.body2world of the reference."""
+    from oracle import residuals_oracle as ro
+    d = np.load(os.path.join(G, "prior_world.npz"))
+    rec, scale, cam = torch.tensor(d["rec"]), torch.tensor(d["scale"]), torch.tensor(d["cam_ext"])
+    b2w = ro.body2world(rec[:, -3:], scale, cam)
+    assert np.array_equal(b2w.numpy(), d["b2w"])
+    vt = ro.verts_transform(torch.tensor(d["verts"]) * scale, b2w)
+    assert np.array_equal(vt.numpy(), d["vt"])
