@@ -91,3 +91,14 @@ vt = go.verts_transform(verts * scale, b2w)
 np.savez(os.path.join(out, "prior_world.npz"), verts=verts.numpy(), cam_ext=cam_ext.numpy(), rec=rec.numpy(), scale=scale.numpy(),
          b2w=b2w.numpy(), vt=vt.numpy())
 print("wrote prior_world.npz")
+
+# ---- host-side formats: the literal qvec2rotmat (:51-61) and body_params_parse (:64-76) ----
+q = torch.randn(6, 4, generator=g, dtype=torch.float64)
+q = (q / q.norm(dim=1, keepdim=True)).numpy()
+Rq = np.stack([go.qvec2rotmat(v) for v in q])
+keys = ["transl", "global_orient", "betas", "body_pose", "left_hand_pose", "right_hand_pose", "camera_translation"]
+dims = [3, 3, 10, 32, 12, 12, 3]
+frame = {k: torch.randn(1, n, generator=g).numpy() for k, n in zip(keys, dims)}
+row = go.body_params_parse(frame)
+np.savez(os.path.join(out, "prior_formats.npz"), q=q, Rq=Rq, row=row, **{"frame_" + k: v for k, v in frame.items()})
+print("wrote prior_formats.npz")

@@ -91,3 +91,13 @@ def test_result_pickles_round_trip_and_reader_keys(tmp_path):
     assert torch.equal(rows, rec)
     with pytest.raises(FileNotFoundError):
         io.load_smplifyx_results(str(tmp_path / "nothing" / "*.pkl"))
+
+
+def test_formats_match_reference_functions():
+    """qvec2rotmat and body_params_parse against outputs of the reference's own functions
+    (tests/golden/prior_formats.npz, made by tests/golden/make_golden_prior.py)."""
+    d = np.load(os.path.join(os.path.dirname(__file__), "golden", "prior_formats.npz"))
+    for q, R in zip(d["q"], d["Rq"]):
+        assert np.array_equal(io.qvec2rotmat(q), R)
+    frame = {k[len("frame_"):]: d[k] for k in d.files if k.startswith("frame_")}
+    assert np.array_equal(io.body_params_parse(frame), d["row"])
