@@ -1,5 +1,6 @@
 """CPU: the C-ABI library loads, exports every symbol include/fpv_b200.h declares, answers its size
 queries without a GPU, and the product refuses CPU tensors instead of falling back."""
+import numpy as np
 import ctypes
 import os
 import re
@@ -99,3 +100,41 @@ def test_shard_ranges_partition_the_scene():
         assert r[0][0] == 0 and r[-1][1] == M and all(r[k][1] == r[k + 1][0] for k in range(G - 1))
         sizes = [e - b for b, e in r]
         assert max(sizes) - min(sizes) <= 1
+
+
+def test_morton_keys_and_scene_presort_host_logic():
+    """The host-side ordering helpers (pure torch, CPU): bit interleave against a plain Python reference, and the
+    pre-sorted scene is a permutation of the input that is sorted by its own keys."""
+    import importlib
+    sp = importlib.import_module("4dcapture-fpv_b200.spatial")
+    fit = importlib.import_module("4dcapture-fpv_b200.fit")
+    g = torch.Generator().manual_seed(3)
+    pts = torch.rand(500, 3, generator=g) * torch.tensor([8.0, 8.0, 3.0]) - torch.tensor([4.0, 4.0, 0.0])
+    pts[7] = torch.tensor([float("nan"), 0.0, 0.0])
+    pts[9] = torch.tensor([float("inf"), -float("inf"), 1.0])
+    lo, inv = sp.grid_of(pts)
+    keys = sp.morton_keys(pts, lo, inv)
+
+    def ref_key(p):
+        q = []
+        for a in range(3):
+            v = (float(p[a]) - float(lo[a])) * float(inv[a])
+            v = np.float32(p[a].item() - lo[a].item()) * np.float32(inv[a].item()) if np.isfinite(p[a].item()) else v
+            if v != v or v == float("inf"):
+                v = 1023.0
+            if v == -float("inf"):
+                v = 0.0
+            q.append(int(min(max(float(v), 0.0), 1023.0)))
+        k = 0
+        for bit in range(10):
+            for a in range(3):
+                k |= ((q[a] >> bit) & 1) << (3 * bit + a)
+        return k
+
+    assert [int(k) for k in keys] == [ref_key(p) for p in pts]
+    clean = pts[torch.isfinite(pts).all(dim=1)]
+    srt = fit._morton_sorted(clean)
+    assert sorted(map(tuple, srt.tolist())) == sorted(map(tuple, clean.tolist()))
+    lo2, inv2 = sp.grid_of(srt)
+    k2 = sp.morton_keys(srt, lo2, inv2)
+    assert bool((k2[1:] >= k2[:-1]).all())
