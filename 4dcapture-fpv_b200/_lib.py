@@ -63,6 +63,27 @@ SIGNATURES = {
     "fpv_nn_culled_search": (c_int, [c_void_p, c_int, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_int64, c_int64,
                                      c_int, c_int64, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int,
                                      c_void_p]),
+    "fpv_nn_culled_search_keys": (c_int, [c_void_p, c_int, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_int64, c_int64,
+                                          c_int64, c_void_p, POINTER(c_void_p), c_int, c_void_p, c_int64, c_void_p,
+                                          c_void_p, c_void_p, c_int, c_void_p]),
+    "fpv_nn_sphere_fused_workspace_bytes": (c_size_t, [c_int64, c_int64]),
+    "fpv_fix_shift_for": (c_int, [c_float, c_int64]),
+    "fpv_nn_sphere_fused": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int,
+                                    c_int64, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "fpv_scene2body_grad": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int64, c_int64, c_void_p, c_int, c_void_p]),
+    "fpv_adam_tick": (c_int, [c_void_p, c_void_p]),
+    "fpv_adam_update": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_float, c_float, c_float, c_float,
+                                c_void_p, c_void_p]),
+    "fpv_p2p_alloc": (c_int, [c_size_t, POINTER(c_void_p)]),
+    "fpv_p2p_free": (c_int, [c_void_p]),
+    "fpv_p2p_export": (c_int, [c_void_p, POINTER(ctypes.c_ubyte)]),
+    "fpv_p2p_open": (c_int, [POINTER(ctypes.c_ubyte), POINTER(c_void_p)]),
+    "fpv_p2p_close": (c_int, [c_void_p]),
+    "fpv_p2p_barrier": (c_int, [POINTER(c_void_p), c_int, c_int, c_void_p, c_void_p, ctypes.c_double, c_void_p]),
+    "fpv_p2p_min_unpack": (c_int, [c_void_p, c_int, c_int64, c_int64, c_void_p, c_int, c_int64, c_int64, c_void_p, c_int,
+                                   c_void_p, c_void_p, c_int, c_void_p, c_void_p]),
+    "fpv_p2p_push": (c_int, [c_void_p, c_int64, POINTER(c_void_p), c_int, c_void_p, c_int64, c_void_p]),
+    "fpv_p2p_sum": (c_int, [c_void_p, c_int, c_int64, c_int64, c_void_p, c_int, c_int64, c_void_p, c_void_p]),
     "fpv_morton_keys": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p]),
     "fpv_nn_gather_pack": (c_int, [c_void_p, c_void_p, c_int, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_void_p]),
     "fpv_nn_sphere_table_floats": (c_size_t, [c_int64, c_int]),

@@ -1,100 +1,160 @@
 """Drop-in chamfer operators backed by the sm_100a nearest-neighbour kernels.
 
-Signatures kept (SURVEY.md section 8b):
-  distChamfer(a, b)            /root/reference/chamfer_python.py:18-28, imported at
-                               global_optimization.py:34
-  chamferDist()(xyz1, xyz2)    [3P] ChamferDistancePytorch @ 719b0f1c, called at
-                               global_optimization.py:292-294 and :349-353
+Signatures kept (SURVEY.md section 8a/8b):
+  distChamfer(a, b)            /root/reference/chamfer_python.py:18-28, imported at global_optimization.py:34
+  pairwise_dist(x, y)          chamfer_python.py:4-9        NN_loss(x, y, dim=0)   chamfer_python.py:12-15
+  chamferDist()(xyz1, xyz2)    [3P] ChamferDistancePytorch @ 719b0f1c, called at global_optimization.py:292-294, :349-353
 
 Differences from the literal reference, all supersets:
   * N != M is accepted (chamfer_python.py:24-27 only works for N == M);
-  * `b` may be a single cloud shared by every batch -- [M,3], [1,M,3] or a stride-0 .expand() view --
-    so the T-fold scene copy of global_optimization.py:176 need not exist (a real [bs,M,3] works too);
+  * `b` may be a single cloud shared by every batch -- [M,3], [1,M,3], a stride-0 .expand() view, or the materialised
+    T-fold copy the reference makes (global_optimization.py:176: detected once per tensor and routed to the shared path);
   * distances use the canonical direct-difference arithmetic (never negative).
+
+Beyond the reference signatures (used by fit.FitProblem; the reference's loss only ever consumes reductions):
+  body_to_scene(a, b)          one direction, a -> b: (dist [bs,N], idx [bs,N])
+  scene_to_body_sum(a, b)      the b -> a direction reduced in the kernel: per-batch sum of the min distances [bs],
+                               never materialising anything of size [bs,M] (SURVEY.md section 7 "hard parts")
+
+No module-level mutable state takes part in a call: strategy is an argument (SearchOptions) and everything carried from
+one call to the next -- seeds, the frozen body ordering, statistics -- lives in a SearchState handle (one per problem; a
+default one per cached scene and shape for callers that pass none).
 """
 from __future__ import annotations
 
-import os
+import dataclasses
+import weakref
+from typing import Dict, Optional, Tuple
 
 import torch
 
 from . import _lib, spatial
 
-# Search strategy of distChamfer when `b` is one cloud shared by every batch (the scene):
-#   "auto"    spatially indexed exact search (nn_culled.cu) for scenes of >= SPATIAL_MIN_POINTS points,
-#             brute force (SIMT / tensor-core filter, chosen inside the library) otherwise
-#   "brute"   always the brute-force kernels          "spatial"  always the indexed search
-# Every strategy returns bit-identical results.
-ENGINE = "auto"
-SPATIAL_MIN_POINTS = 4096
-# scene -> body inside the spatial path:
-#   "sphere"  four-level bounding-sphere hierarchy over the per-frame Morton-sorted body, per-query triangle-inequality
-#             tests, temporal seeding from the previous frame's winner (nn_culled.cu nn_sphere_kernel)   [default]
-#   "rep"     single-level representative/radius culling over 32-vertex clusters (nn_culled.cu rep mode)
-#   "tc"      tensor-core filter over all vertices (nn_tc.cu)
-B2A_ENGINE = "sphere"
-SPHERE_TILE = 16
-CARRY_SEEDS = os.environ.get("FPV_CARRY_SEEDS", "1") != "0"   # scene->body: start from the previous call's winners
-# clip=True batches: one Morton order (of the middle frame) for all frames; "0": per-frame argsort
-BODY_SHARED_ORDER = os.environ.get("FPV_BODY_SHARED_ORDER", "1") != "0"
-LAST_STATS = {}
+
+@dataclasses.dataclass(frozen=True)
+class SearchOptions:
+    """How distChamfer searches when `b` is one cloud shared by every batch (the scene).  Every choice returns
+    bit-identical results.
+      engine      "auto"    spatially indexed exact search (nn_culled.cu) for scenes of >= spatial_min_points points,
+                            brute force (SIMT / tensor-core filter, chosen inside the library) otherwise
+                  "brute"   always the brute-force kernels          "spatial"  always the indexed search
+      b2a_engine  scene -> body inside the spatial path:
+                  "sphere"  four-level bounding-sphere hierarchy over the Morton-sorted body, per-query triangle-inequality
+                            tests, seeded from the previous call / previous frame (nn_sphere_kernel)   [default]
+                  "rep"     single-level representative/radius culling over 32-vertex clusters
+                  "tc"      tensor-core filter over all vertices (nn_tc.cu)
+      carry_seeds start both searches from the previous call's winners (hints; never change a result)
+      body_shared_order  clip=True batches: one Morton order for all frames, computed once and kept in the SearchState"""
+    engine: str = "auto"
+    b2a_engine: str = "sphere"
+    sphere_tile: int = 16
+    carry_seeds: bool = True
+    body_shared_order: bool = True
+    spatial_min_points: int = 4096
+
+    def __post_init__(self):
+        if self.engine not in ("auto", "brute", "spatial"):
+            raise RuntimeError(f"SearchOptions: unknown engine {self.engine!r}")
+        if self.b2a_engine not in ("sphere", "rep", "tc"):
+            raise RuntimeError(f"SearchOptions: unknown b2a_engine {self.b2a_engine!r}")
+        if self.sphere_tile not in (16, 32):
+            raise RuntimeError("SearchOptions: sphere_tile must be 16 or 32")
 
 
-def _forward_spatial(a_c: torch.Tensor, b_c: torch.Tensor, idx_dtype, idx_base: int = 0, clip: bool = False):
-    """Both chamfer directions with the scene held in Morton order.  a_c [T,N,3], b_c [1,M,3].
+DEFAULT_OPTIONS = SearchOptions()
 
-    a -> b (body vertex -> scene): the scene is static; its Morton tiles + boxes are built once (spatial.cached_scene)
-    and the box-culled search with a per-query box test visits well under 1 % of it.
-    b -> a (scene point -> body): group-level box culling fails here (far points see near-equidistant vertices), so the
-    body is re-clustered every call and searched through a bounding-sphere hierarchy with PER-QUERY tests
-    (B2A_ENGINE="sphere"); the queries are issued in the scene's Morton order so that a warp's 128 queries are spatial
-    neighbours.  Both searches start from the winners of the previous call on the same scene (CARRY_SEEDS) -- hints
-    that never change the result.  DESIGN.md sections 4.3, 4.3b.
-    """
+
+class SearchState:
+    """What one problem carries from call to call.  Nothing in here can change a result.
+      seeds      (direction, T, N) -> int32 winners of the last search (in/out buffers of the kernels)
+      body_perm  (N, device) -> frozen Morton ordering of a clip's body (the clusters are fixed vertex sets, their
+                 spheres are rebuilt from the actual positions every call)
+      stats      device counters of the last call (tiles / clusters searched)"""
+
+    def __init__(self):
+        self.seeds: Dict[tuple, torch.Tensor] = {}
+        self.body_perm: Dict[tuple, torch.Tensor] = {}
+        self.stats: Dict[str, torch.Tensor] = {}
+
+    def seed_buffer(self, direction: str, T: int, n: int, device, enabled: bool) -> Tuple[Optional[torch.Tensor], bool]:
+        """(buffer, valid): the in/out seed buffer of one search direction; valid = it holds a previous call's winners."""
+        if not enabled:
+            return None, False
+        key = (direction, T, n, device.index)
+        buf = self.seeds.get(key)
+        if buf is not None:
+            return buf, True
+        buf = self.seeds[key] = torch.empty((T, n), dtype=torch.int32, device=device)
+        return buf, False
+
+    def reset(self):
+        self.seeds.clear()
+        self.body_perm.clear()
+        self.stats.clear()
+
+
+def _default_state(scene: spatial.SortedCloud, T: int, N: int) -> SearchState:
+    """Callers that pass no handle (the plain reference signature) get one per (cached scene, batch shape); a scene
+    serves one or two problems at a time, so old ones are dropped rather than hoarded."""
+    st = scene.states.get((T, N))
+    if st is None:
+        if len(scene.states) >= 2:
+            scene.states.pop(next(iter(scene.states)))
+        st = scene.states[(T, N)] = SearchState()
+    return st
+
+
+def _body_cloud(a_c: torch.Tensor, scene: spatial.SortedCloud, opts: SearchOptions, state: SearchState, clip: bool,
+                spheres: bool) -> spatial.SortedCloud:
+    """The body in Morton order with its cluster table.  clip=True: ONE ordering for every frame, computed on the first
+    call (middle frame) and frozen in the state -- no sort on the per-step path."""
     T, N, _ = a_c.shape
-    M = b_c.shape[1]
+    shared = clip and opts.body_shared_order and T > 1
+    perm = None
+    if shared:
+        key = (N, a_c.device.index)
+        perm = state.body_perm.get(key)
+        if perm is None:
+            perm = state.body_perm[key] = spatial.morton_order(a_c[T // 2], scene.lo, scene.inv_cell)
+    return spatial.SortedCloud(a_c, scene.lo, scene.inv_cell, mode=1,
+                               sphere_tile=opts.sphere_tile if (spheres and opts.b2a_engine == "sphere") else 0,
+                               shared_perm=shared, perm=perm, tables=spheres)
+
+
+def _search_a2b(a_c, b_c, scene, body, idx_dtype, idx_base, opts, state):
+    """body vertex -> scene point: the scene is static; its Morton tiles + boxes are built once and the box-culled search
+    with a per-query box test visits well under 1 % of it.  Returns (d [T,N], i [T,N]) in the ORIGINAL vertex order."""
+    T, N, _ = a_c.shape
+    dev = a_c.device
+    stats = torch.zeros(1, dtype=torch.int64, device=dev)
+    # winners of the previous call, per sorted query position (the order of the body is frozen for a clip; otherwise a
+    # misplaced seed is still a nearby scene point)
+    seed, seed_valid = state.seed_buffer("a2b", T, N, dev, opts.carry_seeds)
+    keys = spatial.culled_search_keys(body.sorted, T, scene, idx_base=idx_base, stats=stats, cand_orig=b_c, seed=seed,
+                                      seed_valid=seed_valid)
+    d, i = spatial.min_unpack(keys, 1, T * N, N, body.perm_row(), idx_dtype)
+    state.stats["tiles_searched"] = stats
+    return d.view(T, N), i.view(T, N)
+
+
+def _search_b2a(a_c, scene, body, idx_dtype, opts, state):
+    """scene point -> body vertex.  Returns (d, i) in the scene's SORTED order ([T,M]); the caller un-permutes."""
+    T, N, _ = a_c.shape
+    M = scene.M
     dev = a_c.device
     L = _lib.lib()
-    scene = spatial.cached_scene(b_c)                                   # built once per scene tensor
-    body = spatial.SortedCloud(a_c, scene.lo, scene.inv_cell, mode=1,   # per-step Morton argsort + cluster table
-                               sphere_tile=SPHERE_TILE if B2A_ENGINE == "sphere" else 0,
-                               shared_perm=clip and BODY_SHARED_ORDER)
-    stats = torch.zeros(1, dtype=torch.int64, device=dev)
-    seed_a, seed_a_valid = None, False
-    if CARRY_SEEDS:
-        # body->scene winners of the previous call, per sorted query position (the order of the body barely changes
-        # between optimiser steps; a misplaced seed is still a nearby scene point)
-        seed_a = scene.seeds.get(("a2b", T, N))
-        seed_a_valid = seed_a is not None and seed_a.device == dev
-        if not seed_a_valid:
-            if len(scene.seeds) >= 4:          # a scene serves one or two problems at a time; do not hoard old buffers
-                scene.seeds.clear()
-            seed_a = scene.seeds[("a2b", T, N)] = torch.empty((T, N), dtype=torch.int32, device=dev)
-    d_s, i_s = spatial.culled_search(body.sorted, False, T, scene, idx_dtype, idx_base=idx_base, stats=stats,
-                                     cand_orig=b_c, seed=seed_a, seed_valid=seed_a_valid)
-    if body.shared_perm:
-        inv_b = body.inv_perm[0]
-        d_a2b, i_a2b = d_s.index_select(1, inv_b), i_s.index_select(1, inv_b)
-    else:
-        d_a2b = torch.empty_like(d_s).scatter_(1, body.perm, d_s)
-        i_a2b = torch.empty_like(i_s).scatter_(1, body.perm, i_s)
-    if B2A_ENGINE == "sphere":
+    if opts.b2a_engine == "sphere":
         stats2 = torch.zeros(2, dtype=torch.int64, device=dev)
-        seed, seed_valid = None, False
-        if CARRY_SEEDS:
-            # winners of the previous call on this scene (an optimiser loop calls with a slowly moving body): every
-            # (frame, scene point) starts from the exact distance to that vertex.  A hint only; kept on the cached scene.
-            seed = scene.seeds.get(("b2a", T, N))
-            seed_valid = seed is not None and seed.device == dev
-            if not seed_valid:
-                seed = scene.seeds[("b2a", T, N)] = torch.empty((T, M), dtype=torch.int32, device=dev)   # written by this call
+        # winners of the previous call on this scene (an optimiser loop calls with a slowly moving body): every
+        # (frame, scene point) starts from the exact distance to that vertex.  A hint only.
+        seed, seed_valid = state.seed_buffer("b2a", T, M, dev, opts.carry_seeds)
         d_s2, i_s2 = spatial.sphere_search(scene.sorted, True, T, body, cand_orig=a_c, idx_dtype=idx_dtype, stats=stats2,
                                            seed=seed, seed_valid=seed_valid)
-        LAST_STATS["tiles_searched_b2a"] = stats2
-    elif B2A_ENGINE == "rep":
+        state.stats["tiles_searched_b2a"] = stats2
+    elif opts.b2a_engine == "rep":
         stats2 = torch.zeros(2, dtype=torch.int64, device=dev)
         d_s2, i_s2 = spatial.culled_search(scene.sorted, True, T, body, idx_dtype, stats=stats2)
-        LAST_STATS["tiles_searched_b2a"] = stats2
+        state.stats["tiles_searched_b2a"] = stats2
     else:
         planes_a = pack_planes(a_c)                                     # candidates in ORIGINAL order: native tie-break
         d_s2 = torch.empty(T, M, dtype=torch.float32, device=dev)
@@ -104,40 +164,84 @@ def _forward_spatial(a_c: torch.Tensor, b_c: torch.Tensor, idx_dtype, idx_base: 
             _lib.check(L.fpv_nn_search(_lib.ptr(scene.sorted), 1, T, M, _lib.ptr(planes_a), T, N, 0, _lib.ptr(d_s2),
                                        _lib.ptr(i_s2), 8 if idx_dtype == torch.int64 else 4, None, _lib.ptr(ws),
                                        ws.numel(), _lib.stream_ptr()), "fpv_nn_search")
-    if scene.identity:
-        d_b2a, i_b2a = d_s2, i_s2
-    else:
-        inv = scene.inv_perm[0]
-        d_b2a = d_s2.index_select(1, inv)
-        i_b2a = i_s2.index_select(1, inv)
-    LAST_STATS["tiles_searched"] = stats
-    LAST_STATS["sorted"] = (scene, i_s2)      # picked up by _ChamferFn.forward for the spatially ordered backward
-    return d_b2a, d_a2b, i_b2a, i_a2b
+    return d_s2, i_s2
 
 
-def _prep(a: torch.Tensor, b: torch.Tensor):
+def _forward_spatial(a_c: torch.Tensor, b_c: torch.Tensor, idx_dtype, idx_base: int, clip: bool, opts: SearchOptions,
+                     state: Optional[SearchState], want_a2b: bool = True, want_b2a: bool = True):
+    """The requested chamfer directions with the scene held in Morton order.  a_c [T,N,3], b_c [1,M,3].
+    Returns (d_b2a, d_a2b, i_b2a, i_a2b, sorted_info): absent directions are None; sorted_info = (scene, i_b2a in the
+    scene's sorted order) feeds the spatially ordered backward.  DESIGN.md sections 4.3, 4.3b."""
+    T, N, _ = a_c.shape
+    scene = spatial.cached_scene(b_c)                                   # built once per scene tensor
+    if state is None:
+        state = _default_state(scene, T, N)
+    body = _body_cloud(a_c, scene, opts, state, clip, spheres=want_b2a)
+    d_a2b = i_a2b = d_b2a = i_b2a = None
+    sorted_info = None
+    if want_a2b:
+        d_a2b, i_a2b = _search_a2b(a_c, b_c, scene, body, idx_dtype, idx_base, opts, state)
+    if want_b2a:
+        d_s2, i_s2 = _search_b2a(a_c, scene, body, idx_dtype, opts, state)
+        if scene.identity:
+            d_b2a, i_b2a = d_s2, i_s2
+        else:
+            inv = scene.inv_perm[0]
+            d_b2a = d_s2.index_select(1, inv)
+            i_b2a = i_s2.index_select(1, inv)
+        sorted_info = (scene, i_s2)
+    return d_b2a, d_a2b, i_b2a, i_a2b, sorted_info
+
+
+# verdicts of _is_repeated_scene, keyed on the tensor OBJECT (weak reference) and its version: a recycled address can
+# never inherit another tensor's verdict
+_repeat_verdicts: Dict[int, tuple] = {}
+
+
+def _is_repeated_scene(b: torch.Tensor) -> bool:
+    """True when every batch entry of b [bs,M,3] equals b[0] -- the materialised T-fold scene copy of
+    global_optimization.py:176.  One pass over the tensor and one host sync, once per tensor object and version (the
+    reference keeps that tensor alive for the whole fit; `.contiguous()` on it returns the same object every step)."""
+    hit = _repeat_verdicts.get(id(b))
+    if hit is not None and hit[0]() is b and hit[1] == b._version:
+        return hit[2]
+    if torch.cuda.is_current_stream_capturing():
+        return False                           # cannot sync inside a capture: the general path is still correct
+    verdict = bool(torch.equal(b, b[0:1].expand_as(b)))
+    for k in [k for k, v in _repeat_verdicts.items() if v[0]() is None]:
+        del _repeat_verdicts[k]
+    _repeat_verdicts[id(b)] = (weakref.ref(b), b._version, verdict)
+    return verdict
+
+
+def _prep(a: torch.Tensor, b: torch.Tensor, what: str = "distChamfer"):
     if a.dim() != 3 or a.shape[-1] != 3:
-        raise RuntimeError(f"distChamfer: expected a of shape [bs,N,3], got {tuple(a.shape)}")
+        raise RuntimeError(f"{what}: expected a of shape [bs,N,3], got {tuple(a.shape)}")
     if b.dim() == 2:
         b = b.unsqueeze(0)
     if b.dim() != 3 or b.shape[-1] != 3:
-        raise RuntimeError(f"distChamfer: expected b of shape [bs,M,3], got {tuple(b.shape)}")
+        raise RuntimeError(f"{what}: expected b of shape [bs,M,3], got {tuple(b.shape)}")
     if a.dtype != torch.float32 or b.dtype != torch.float32:
-        raise RuntimeError("distChamfer: float32 inputs required")
+        raise RuntimeError(f"{what}: float32 inputs required")
     _lib.require_cuda(a, b)
     if a.device != b.device:
-        raise RuntimeError("distChamfer: a and b are on different devices")
+        raise RuntimeError(f"{what}: a and b are on different devices")
     bs = a.shape[0]
+    if a.shape[1] == 0 or b.shape[1] == 0 or bs == 0:
+        raise RuntimeError(f"{what}: empty cloud (torch.min over an empty dimension)")
     shared = False
     if b.shape[0] != bs:
         if b.shape[0] != 1:
-            raise RuntimeError(f"distChamfer: batch mismatch {bs} vs {b.shape[0]}")
+            raise RuntimeError(f"{what}: batch mismatch {bs} vs {b.shape[0]}")
         shared = True
-    elif bs > 1 and b.stride(0) == 0:
+    elif bs == 1:
+        shared = True                          # one frame: the two layouts are the same thing
+    elif b.stride(0) == 0:
         b = b[0:1]
         shared = True
-    if a.shape[1] == 0 or b.shape[1] == 0 or bs == 0:
-        raise RuntimeError("distChamfer: empty cloud (torch.min over an empty dimension)")
+    elif not b.requires_grad and _is_repeated_scene(b):
+        b = b[0:1]                             # the reference's .repeat(T,1,1) scene: search it once, not T times
+        shared = True
     return a, b, shared
 
 
@@ -152,25 +256,27 @@ def _weights(g):
 
 
 class _ChamferFn(torch.autograd.Function):
+    """distChamfer, or one of its directions (want = 3: both, 1: b->a only, 2: a->b only; absent outputs are None)."""
+
     @staticmethod
-    def forward(ctx, a, b, shared: bool, idx_dtype, clip: bool = False):
+    def forward(ctx, a, b, shared: bool, idx_dtype, clip: bool, opts: SearchOptions, state, want: int):
         a_c = a.contiguous()
         b_c = b.contiguous()
         bs, N, _ = a_c.shape
         M = b_c.shape[1]
         dev = a_c.device
         L = _lib.lib()
-        d_b2a = torch.empty(bs, M, dtype=torch.float32, device=dev)
-        d_a2b = torch.empty(bs, N, dtype=torch.float32, device=dev)
-        i_b2a = torch.empty(bs, M, dtype=idx_dtype, device=dev)
-        i_a2b = torch.empty(bs, N, dtype=idx_dtype, device=dev)
         idx_bytes = 8 if idx_dtype == torch.int64 else 4
-        use_spatial = shared and (ENGINE == "spatial" or (ENGINE == "auto" and M >= SPATIAL_MIN_POINTS))
+        use_spatial = shared and (opts.engine == "spatial" or (opts.engine == "auto" and M >= opts.spatial_min_points))
         ctx.sorted = None
         if use_spatial:
-            d_b2a, d_a2b, i_b2a, i_a2b = _forward_spatial(a_c, b_c, idx_dtype, clip=clip)
-            ctx.sorted = LAST_STATS.pop("sorted", None)
-        else:
+            d_b2a, d_a2b, i_b2a, i_a2b, ctx.sorted = _forward_spatial(a_c, b_c, idx_dtype, 0, clip, opts, state,
+                                                                      want_a2b=bool(want & 2), want_b2a=bool(want & 1))
+        elif want == 3:
+            d_b2a = torch.empty(bs, M, dtype=torch.float32, device=dev)
+            d_a2b = torch.empty(bs, N, dtype=torch.float32, device=dev)
+            i_b2a = torch.empty(bs, M, dtype=idx_dtype, device=dev)
+            i_a2b = torch.empty(bs, N, dtype=idx_dtype, device=dev)
             with torch.cuda.device(dev):
                 nbytes = L.fpv_chamfer_fwd_workspace_bytes(bs, N, M, int(shared))
                 ws = _lib.workspace(nbytes, dev)
@@ -178,10 +284,19 @@ class _ChamferFn(torch.autograd.Function):
                                              _lib.ptr(d_b2a), _lib.ptr(d_a2b), _lib.ptr(i_b2a), _lib.ptr(i_a2b),
                                              idx_bytes, _lib.ptr(ws), ws.numel(), _lib.stream_ptr()),
                            "fpv_chamfer_fwd")
+        else:
+            d_b2a = d_a2b = i_b2a = i_a2b = None
+            if want & 2:      # a -> b
+                planes_b = pack_planes(b_c)
+                d_a2b, i_a2b = nn_search(a_c, planes_b, M, ref_batches=b_c.shape[0], idx_dtype=idx_dtype)
+            else:             # b -> a
+                planes_a = pack_planes(a_c)
+                d_b2a, i_b2a = _nn_search_raw(b_c, shared, bs, M, planes_a, bs, N, idx_dtype)
         ctx.save_for_backward(a_c, b_c, i_b2a, i_a2b)
         ctx.shared = shared
         ctx.idx_bytes = idx_bytes
-        ctx.mark_non_differentiable(i_b2a, i_a2b)
+        ctx.idx_dtype = idx_dtype
+        ctx.mark_non_differentiable(*[t for t in (i_b2a, i_a2b) if t is not None])
         ctx.set_materialize_grads(False)
         return d_b2a, d_a2b, i_b2a, i_a2b
 
@@ -189,19 +304,25 @@ class _ChamferFn(torch.autograd.Function):
     def backward(ctx, g_b2a, g_a2b, _g1, _g2):
         a, b, i_b2a, i_a2b = ctx.saved_tensors  # never mutated: backward(retain_graph=True) is safe (:591)
         need_a, need_b = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
+        none = (None,) * 8
         if not (need_a or need_b) or (g_b2a is None and g_a2b is None):
-            return None, None, None, None, None
+            return none
         bs, N, _ = a.shape
         M = b.shape[1]
         dev = a.device
         L = _lib.lib()
-        bcast = 0
-        g1, bc1 = _weights(g_b2a)
-        g2, bc2 = _weights(g_a2b)
+        g1, bc1 = _weights(g_b2a if i_b2a is not None else None)
+        g2, bc2 = _weights(g_a2b if i_a2b is not None else None)
         bcast = bc1 | (bc2 << 1)
+        # a direction that was not computed has no gradient: give the kernel a valid dummy index array (never read
+        # with a NULL weight pointer, but the ABI wants non-null pointers)
+        if i_b2a is None:
+            i_b2a = torch.zeros(1, dtype=ctx.idx_dtype, device=dev)
+        if i_a2b is None:
+            i_a2b = torch.zeros(1, dtype=ctx.idx_dtype, device=dev)
         grad_a = torch.empty_like(a)
         grad_b = torch.empty_like(b) if need_b else None
-        if ctx.sorted is not None and not need_b:
+        if ctx.sorted is not None and not need_b and g1 is not None:
             # Spatially ordered scatter: walk the scene in Morton order so that consecutive scene points hit the same
             # body vertex and merge in registers (bwd_accum_kernel).  The fixed-point integer sum is order-independent,
             # so grad_a is bit-identical to the original-order evaluation.
@@ -209,7 +330,7 @@ class _ChamferFn(torch.autograd.Function):
             if not scene.identity:
                 b = scene.sorted
                 i_b2a = i_s2
-                if g1 is not None and not bc1:
+                if not bc1:
                     g1 = g1.index_select(1, scene.perm[0])
                 if g2 is not None:
                     i_a2b = scene.inv_perm[0].to(i_a2b.dtype)[i_a2b.long()]
@@ -221,36 +342,228 @@ class _ChamferFn(torch.autograd.Function):
                                                ctx.idx_bytes, _lib.ptr(grad_a), _lib.ptr(grad_b),
                                                _lib.ptr(ws), ws.numel(), _lib.stream_ptr()),
                        "fpv_chamfer_bwd")
-        return (grad_a if need_a else None), grad_b, None, None, None
+        return ((grad_a if need_a else None), grad_b) + (None,) * 6
 
 
-def distChamfer(a: torch.Tensor, b: torch.Tensor, idx_dtype: torch.dtype = torch.int64, clip: bool = False):
+def _check_idx_dtype(idx_dtype, what):
+    if idx_dtype not in (torch.int64, torch.int32):
+        raise RuntimeError(f"{what}: idx_dtype must be torch.int64 or torch.int32")
+
+
+def distChamfer(a: torch.Tensor, b: torch.Tensor, idx_dtype: torch.dtype = torch.int64, clip: bool = False,
+                options: Optional[SearchOptions] = None, state: Optional[SearchState] = None):
     """chamfer_python.distChamfer: returns (d_b2a [bs,M], d_a2b [bs,N], i_b2a [bs,M], i_a2b [bs,N]).
 
     Squared distances, both directions, lowest index on ties, differentiable w.r.t. a and b through
     the argmin (chamfer_python.py:28).  Indices are int64 as torch.min returns them; pass
     idx_dtype=torch.int32 to halve the index traffic.  clip=True declares that the batch entries of `a` are consecutive
     frames of ONE articulated surface (the fit loop's [T,V,3] body vertices): the spatial engine then orders all
-    frames by one Morton sort instead of T.  A hint only -- results are identical either way.
+    frames by one Morton sort, done once.  A hint only -- results are identical either way.  options / state: see
+    SearchOptions / SearchState (strategy and call-to-call carry-over; neither can change a result).
     """
-    if idx_dtype not in (torch.int64, torch.int32):
-        raise RuntimeError("distChamfer: idx_dtype must be torch.int64 or torch.int32")
+    _check_idx_dtype(idx_dtype, "distChamfer")
     a, b, shared = _prep(a, b)
-    return _ChamferFn.apply(a, b, shared, idx_dtype, bool(clip))
+    return _ChamferFn.apply(a, b, shared, idx_dtype, bool(clip), options or DEFAULT_OPTIONS, state, 3)
+
+
+def body_to_scene(a: torch.Tensor, b: torch.Tensor, idx_dtype: torch.dtype = torch.int32, clip: bool = False,
+                  options: Optional[SearchOptions] = None, state: Optional[SearchState] = None):
+    """The a -> b direction of distChamfer alone: (dist [bs,N], idx [bs,N]) -- what the reference loop consumes
+    (`contact_dist, _ = ...`, global_optimization.py:292-294).  Differentiable w.r.t. a and b."""
+    _check_idx_dtype(idx_dtype, "body_to_scene")
+    a, b, shared = _prep(a, b, "body_to_scene")
+    _, d, _, i = _ChamferFn.apply(a, b, shared, idx_dtype, bool(clip), options or DEFAULT_OPTIONS, state, 2)
+    return d, i
+
+
+def scene_to_body(a: torch.Tensor, b: torch.Tensor, idx_dtype: torch.dtype = torch.int32, clip: bool = False,
+                  options: Optional[SearchOptions] = None, state: Optional[SearchState] = None):
+    """The b -> a direction of distChamfer alone: (dist [bs,M], idx [bs,M])."""
+    _check_idx_dtype(idx_dtype, "scene_to_body")
+    a, b, shared = _prep(a, b, "scene_to_body")
+    d, _, i, _ = _ChamferFn.apply(a, b, shared, idx_dtype, bool(clip), options or DEFAULT_OPTIONS, state, 1)
+    return d, i
+
+
+def pairwise_dist(x: torch.Tensor, y: torch.Tensor) -> torch.Tensor:
+    """chamfer_python.pairwise_dist (:4-9): the [N,M] matrix of squared distances P[i,j] = |x_i - y_j|^2, for
+    unbatched clouds x [N,3], y [M,3] (the literal function only works for N == M).  Canonical direct-difference
+    arithmetic; meant for small clouds -- the searches never build this matrix."""
+    if x.dim() != 2 or y.dim() != 2 or x.shape[1] != 3 or y.shape[1] != 3:
+        raise RuntimeError("pairwise_dist: expected x [N,3] and y [M,3]")
+    _lib.require_cuda(x, y)
+    if x.dtype != torch.float32 or y.dtype != torch.float32:
+        raise RuntimeError("pairwise_dist: float32 inputs required")
+    d = x.unsqueeze(1) - y.unsqueeze(0)
+    return torch.addcmul(torch.addcmul(d[..., 0] * d[..., 0], d[..., 1], d[..., 1]), d[..., 2], d[..., 2])
+
+
+def NN_loss(x: torch.Tensor, y: torch.Tensor, dim: int = 0) -> torch.Tensor:
+    """chamfer_python.NN_loss (:12-15): mean over the points of one cloud of the squared distance to their nearest
+    neighbour in the other -- `torch.min(pairwise_dist(x, y), dim)[0].mean()`: dim=0 reduces over x (one value per
+    y_j), dim=1 over y (one value per x_i).  Computed by the exact search, never through the [N,M] matrix."""
+    if x.dim() != 2 or y.dim() != 2 or x.shape[1] != 3 or y.shape[1] != 3:
+        raise RuntimeError("NN_loss: expected x [N,3] and y [M,3]")
+    if dim not in (0, 1, -1, -2):
+        raise RuntimeError("NN_loss: dim must be 0 or 1")
+    if dim in (0, -2):
+        d, _ = scene_to_body(x.unsqueeze(0), y.unsqueeze(0))      # for every y_j the nearest x_i
+    else:
+        d, _ = body_to_scene(x.unsqueeze(0), y.unsqueeze(0))      # for every x_i the nearest y_j
+    return d.mean()
 
 
 class chamferDist(torch.nn.Module):
-    """[3P] dist_chamfer.chamferDist as used at global_optimization.py:292-294:
-    forward(xyz1 [bs,N,3], xyz2 [bs,M,3]) -> (dist1 [bs,N], dist2 [bs,M])."""
+    """[3P] dist_chamfer.chamferDist as used at global_optimization.py:292-294 and :349-353:
+    forward(xyz1 [bs,N,3], xyz2 [bs,M,3]) -> (dist1 [bs,N], dist2 [bs,M]).
+
+    directions: "dist1" (default) computes only xyz1 -> xyz2 and returns (dist1, None) -- every call site of the
+    reference discards dist2 (`contact_dist, _ = ...`), and against a scene cloud dist2 is the expensive direction;
+    "both" restores the [3P] op's full result, "dist2" the other half."""
+
+    def __init__(self, directions: str = "dist1", options: Optional[SearchOptions] = None,
+                 state: Optional[SearchState] = None):
+        super().__init__()
+        if directions not in ("dist1", "dist2", "both"):
+            raise RuntimeError("chamferDist: directions must be 'dist1', 'dist2' or 'both'")
+        self.directions, self.options, self.state = directions, options, state
 
     def forward(self, xyz1: torch.Tensor, xyz2: torch.Tensor):
-        d_2to1, d_1to2, _, _ = distChamfer(xyz1, xyz2, idx_dtype=torch.int32)
+        if self.directions == "dist1":
+            d1, _ = body_to_scene(xyz1, xyz2, options=self.options, state=self.state)
+            return d1, None
+        if self.directions == "dist2":
+            d2, _ = scene_to_body(xyz1, xyz2, options=self.options, state=self.state)
+            return None, d2
+        d_2to1, d_1to2, _, _ = distChamfer(xyz1, xyz2, idx_dtype=torch.int32, options=self.options, state=self.state)
         return d_1to2, d_2to1
+
+
+# --------------------------------------------------------------------------------------------------------------
+# fused scene -> body sum
+# --------------------------------------------------------------------------------------------------------------
+class _FusedTermsFn(torch.autograd.Function):
+    """scene -> body reduced in the kernel (sum_d [T]) and, optionally, the body -> scene direction (d, i [T,N]) from
+    the same sorted body -- the two chamfer terms of one fit step with one ordering / table build."""
+
+    @staticmethod
+    def forward(ctx, a, b, clip: bool, opts: SearchOptions, state, want_a2b: bool, idx_dtype):
+        a_c = a.contiguous()
+        b_c = b.contiguous()
+        T, N, _ = a_c.shape
+        dev = a_c.device
+        L = _lib.lib()
+        scene = spatial.cached_scene(b_c)
+        if state is None:
+            state = _default_state(scene, T, N)
+        if opts.b2a_engine != "sphere":
+            raise RuntimeError("scene_to_body_sum runs on the sphere engine only")
+        body = _body_cloud(a_c, scene, opts, state, clip, spheres=True)
+        M = scene.M
+        d_a2b = i_a2b = None
+        if want_a2b:
+            d_a2b, i_a2b = _search_a2b(a_c, b_c, scene, body, idx_dtype, 0, opts, state)
+        seed, seed_valid = state.seed_buffer("b2a", T, M, dev, True)     # the seeds are this op's only [T,M] array
+        stats = torch.zeros(2, dtype=torch.int64, device=dev)
+        sum_d = torch.empty(T, dtype=torch.float32, device=dev)
+        acc = torch.zeros(T, N, 4, dtype=torch.int64, device=dev)
+        fix_shift = scene.fix_shift()
+        with torch.cuda.device(dev):
+            ws = _lib.workspace(L.fpv_nn_sphere_fused_workspace_bytes(T, M), dev)
+            _lib.check(L.fpv_nn_sphere_fused(_lib.ptr(scene.sorted), T, M, _lib.ptr(body.planes), _lib.ptr(body.boxes),
+                                             _lib.ptr(body.oidx), _lib.ptr(a_c), _lib.ptr(seed), int(seed_valid), N,
+                                             body.sphere_tile, fix_shift, _lib.ptr(sum_d), _lib.ptr(acc), _lib.ptr(stats),
+                                             _lib.ptr(ws), ws.numel(), _lib.stream_ptr()), "fpv_nn_sphere_fused")
+        state.stats["tiles_searched_b2a"] = stats
+        ctx.save_for_backward(a_c, b_c, acc, i_a2b)
+        ctx.fix_shift = fix_shift
+        ctx.idx_bytes = 8 if idx_dtype == torch.int64 else 4
+        if i_a2b is not None:
+            ctx.mark_non_differentiable(i_a2b)
+        ctx.set_materialize_grads(False)
+        return sum_d, d_a2b, i_a2b
+
+    @staticmethod
+    def backward(ctx, g_sum, g_a2b, _gi):
+        a, b, acc, i_a2b = ctx.saved_tensors
+        none = (None,) * 7
+        if not ctx.needs_input_grad[0] or (g_sum is None and g_a2b is None):
+            return none
+        T, N, _ = a.shape
+        M = b.shape[1]
+        dev = a.device
+        L = _lib.lib()
+        grad = torch.empty_like(a)
+        have = False
+        with torch.cuda.device(dev):
+            if g_a2b is not None and i_a2b is not None:
+                # direct term 2 g (a_i - b_idx): a gather, no scatter (the scene gets no gradient here)
+                g2, bc2 = _weights(g_a2b)
+                dummy = torch.zeros(1, dtype=i_a2b.dtype, device=dev)
+                ws = _lib.workspace(L.fpv_chamfer_bwd_workspace_bytes(T, N, M, 1, 0), dev)
+                _lib.check(L.fpv_chamfer_bwd_bcast(_lib.ptr(a), _lib.ptr(b), T, N, M, 1, None, _lib.ptr(g2), bc2 << 1,
+                                                   _lib.ptr(dummy), _lib.ptr(i_a2b), ctx.idx_bytes, _lib.ptr(grad), None,
+                                                   _lib.ptr(ws), ws.numel(), _lib.stream_ptr()), "fpv_chamfer_bwd")
+                have = True
+            if g_sum is not None:
+                gc = g_sum.contiguous().float()
+                _lib.check(L.fpv_scene2body_grad(_lib.ptr(a), _lib.ptr(acc), ctx.fix_shift, _lib.ptr(gc), T, N,
+                                                 _lib.ptr(grad), int(have), _lib.stream_ptr()), "fpv_scene2body_grad")
+            elif not have:
+                grad.zero_()
+        return (grad,) + (None,) * 6
+
+
+def _prep_shared(a, b, what):
+    a, b, shared = _prep(a, b, what)
+    if not shared:
+        raise RuntimeError(f"{what}: b must be ONE cloud shared by every batch entry")
+    if b.requires_grad:
+        raise RuntimeError(f"{what}: no gradient w.r.t. the scene (use distChamfer)")
+    return a, b
+
+
+def scene_to_body_sum(a: torch.Tensor, b: torch.Tensor, clip: bool = False, options: Optional[SearchOptions] = None,
+                      state: Optional[SearchState] = None) -> torch.Tensor:
+    """sum_j min_i |b_j - a_t,i|^2 per batch entry t: the b -> a direction of distChamfer reduced inside the search
+    kernel ([bs] float32).  Equal to distChamfer(a, b)[0].sum(1) up to the summation order (double accumulation in a
+    fixed order: deterministic), but nothing of size [bs,M] is written: no distances, no indices -- the backward
+    w.r.t. `a` comes from per-vertex integer accumulators (count and coordinate sum of the scene points each vertex
+    won) filled by the same kernel.  `b` must be one cloud shared by the batch ([M,3], [1,M,3], expand or repeat);
+    no gradient flows to it."""
+    a, b = _prep_shared(a, b, "scene_to_body_sum")
+    return _FusedTermsFn.apply(a, b, bool(clip), options or DEFAULT_OPTIONS, state, False, torch.int32)[0]
+
+
+def fit_chamfer_terms(a: torch.Tensor, b: torch.Tensor, clip: bool = True, options: Optional[SearchOptions] = None,
+                      state: Optional[SearchState] = None, idx_dtype: torch.dtype = torch.int32):
+    """Both chamfer terms of one fit step from one sorted body:
+        (sum_b2a [bs], d_a2b [bs,N], i_a2b [bs,N]) = (scene_to_body_sum(a, b), *body_to_scene(a, b))."""
+    _check_idx_dtype(idx_dtype, "fit_chamfer_terms")
+    a, b = _prep_shared(a, b, "fit_chamfer_terms")
+    return _FusedTermsFn.apply(a, b, bool(clip), options or DEFAULT_OPTIONS, state, True, idx_dtype)
+
+
+# --------------------------------------------------------------------------------------------------------------
+# building blocks
+# --------------------------------------------------------------------------------------------------------------
+def _nn_search_raw(q, q_shared, B, N, planes, ref_batches, M, idx_dtype, idx_base: int = 0):
+    dev = q.device
+    L = _lib.lib()
+    qc = q.contiguous()
+    dist = torch.empty(B, N, dtype=torch.float32, device=dev)
+    idx = torch.empty(B, N, dtype=idx_dtype, device=dev)
+    with torch.cuda.device(dev):
+        ws = _lib.workspace(L.fpv_nn_search_workspace_bytes(B, N, M), dev)
+        _lib.check(L.fpv_nn_search(_lib.ptr(qc), int(bool(q_shared)), B, N, _lib.ptr(planes), ref_batches, M, idx_base,
+                                   _lib.ptr(dist), _lib.ptr(idx), 8 if idx_dtype == torch.int64 else 4,
+                                   None, _lib.ptr(ws), ws.numel(), _lib.stream_ptr()), "fpv_nn_search")
+    return dist, idx
 
 
 def nn_search(queries: torch.Tensor, planes: torch.Tensor, M: int, *, ref_batches: int = 1,
               idx_base: int = 0, want_keys: bool = False, idx_dtype: torch.dtype = torch.int32):
-    """One-direction search against pre-packed candidate planes (see pack_planes).
+    """One-direction brute-force search against pre-packed candidate planes (see pack_planes).
 
     queries [B,N,3] -> (dist [B,N], idx [B,N]) or, with want_keys, the packed uint64 combine keys
     (returned as int64: the sign bit is never set because canonical distances are non-negative).
@@ -260,20 +573,15 @@ def nn_search(queries: torch.Tensor, planes: torch.Tensor, M: int, *, ref_batche
     B, N, _ = q.shape
     dev = q.device
     L = _lib.lib()
-    with torch.cuda.device(dev):
-        ws = _lib.workspace(L.fpv_nn_search_workspace_bytes(B, N, M), dev)
-        if want_keys:
+    if want_keys:
+        with torch.cuda.device(dev):
+            ws = _lib.workspace(L.fpv_nn_search_workspace_bytes(B, N, M), dev)
             keys = torch.empty(B, N, dtype=torch.int64, device=dev)
             _lib.check(L.fpv_nn_search(_lib.ptr(q), 0, B, N, _lib.ptr(planes), ref_batches, M, idx_base,
                                        None, None, 0, _lib.ptr(keys), _lib.ptr(ws), ws.numel(),
                                        _lib.stream_ptr()), "fpv_nn_search")
-            return keys
-        dist = torch.empty(B, N, dtype=torch.float32, device=dev)
-        idx = torch.empty(B, N, dtype=idx_dtype, device=dev)
-        _lib.check(L.fpv_nn_search(_lib.ptr(q), 0, B, N, _lib.ptr(planes), ref_batches, M, idx_base,
-                                   _lib.ptr(dist), _lib.ptr(idx), 8 if idx_dtype == torch.int64 else 4,
-                                   None, _lib.ptr(ws), ws.numel(), _lib.stream_ptr()), "fpv_nn_search")
-    return dist, idx
+        return keys
+    return _nn_search_raw(q, False, B, N, planes, ref_batches, M, idx_dtype, idx_base)
 
 
 def pack_planes(points: torch.Tensor) -> torch.Tensor:

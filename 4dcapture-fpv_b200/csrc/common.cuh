@@ -59,6 +59,21 @@ struct Arena {
 int sm_count();
 void count_launch();
 
+// One-time per-DEVICE configuration flag: function attributes such as MaxDynamicSharedMemorySize are per device, so a
+// process that uses cuda:1 after cuda:0 must set them again there.  slot() returns the flag of the current device.
+struct PerDeviceOnce {
+    bool done[64] = {};
+    bool *slot() {
+        static bool overflow;
+        int d = 0;
+        if (cudaGetDevice(&d) != cudaSuccess || d < 0 || d >= 64) {
+            overflow = false;  // unknown device: configure every time (cheap)
+            return &overflow;
+        }
+        return &done[d];
+    }
+};
+
 // Optional per-kernel timing (bench.py's roofline leg): when enabled, instrumented launch sites bracket
 // the kernel with CUDA events on the launching stream and record its algorithmic work.
 bool profile_on();

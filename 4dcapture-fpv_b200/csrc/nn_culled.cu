@@ -59,6 +59,15 @@ struct CulledParams {
     int64_t cand_orig_bstride;
     int *seed;               // [batches][N] in/out winners of the previous call (original indices), may be null
     int seed_read;
+    // packed-key epilogue (multi-GPU combine): when `keys` is set the kernel writes
+    // (float_bits(d) << 32 | idx_base + idx) per query instead of dist / idx, and stores the same key into every
+    // peer's mailbox slot (push_n remote buffers of the same layout, reached over NVLink) -- the transfer overlaps
+    // the search warp by warp.  push_parity (device, may be null) selects the half of a double-buffered mailbox.
+    unsigned long long *keys;
+    unsigned long long *push[FPV_MAX_PEERS];
+    int push_n;
+    const unsigned *push_parity;
+    int64_t push_half;       // elements between the two halves of a mailbox slot
 };
 
 __device__ __forceinline__ float cu_d2(float x, float y, float z, float rx, float ry, float rz) {
@@ -353,6 +362,22 @@ __global__ void __launch_bounds__(CU_WARPS * 32) nn_culled_kernel(const CulledPa
     }
     if (p.tiles_searched && lane == 0) atomicAdd(p.tiles_searched, searched);
 
+    if (p.keys != nullptr) {
+        const int64_t half = (p.push_parity != nullptr && (__ldg(p.push_parity) & 1u)) ? p.push_half : 0;
+#pragma unroll
+        for (int k = 0; k < CU_QPT; ++k) {
+            const int64_t qi = q0 + k * 32 + lane;
+            if (qi < p.N) {
+                const int64_t o = b * p.N + qi;
+                const unsigned long long key =
+                    (static_cast<unsigned long long>(__float_as_uint(best[k])) << 32) | unsigned(p.idx_base + bidx[k]);
+                p.keys[o + half] = key;
+                for (int r = 0; r < p.push_n; ++r) p.push[r][o + half] = key;  // coalesced 8-byte stores into peer memory
+                if (p.seed != nullptr) p.seed[o] = bidx[k];
+            }
+        }
+        return;
+    }
 #pragma unroll
     for (int k = 0; k < CU_QPT; ++k) {
         const int64_t qi = q0 + k * 32 + lane;
@@ -489,6 +514,14 @@ struct SphereParams {
     void *idx;
     int idx_bytes;
     unsigned long long *tiles_searched;
+    // fused-loss mode (template FUSED): nothing of size [batches][N] is written except the seeds.  Per batch the kernel
+    // accumulates the winners' distances (per-warp partial sums in double, reduced in fixed order afterwards) and, per
+    // winning candidate, the number of queries it won and the fixed-point sum of their coordinates -- everything the
+    // backward of  sum_j d(x_j, y_win(j))  needs:  d/dy_i = 2 (n_i y_i - S_i).  Integer atomics: order-independent.
+    double *sum_partial;          // [batches][groups]
+    int64_t groups;               // query groups (warps) per batch
+    unsigned long long *acc;      // [batches][M][4]: S_x, S_y, S_z (x * 2^fix_shift, two's complement), count
+    float fix_scale;              // 2^fix_shift
 };
 
 // does any of this lane's 4 queries (two packed pairs) need the sphere?  a2 = |x|^2(1-s) - sq^2(1+s), sq2 = sq
@@ -573,10 +606,59 @@ __device__ __forceinline__ bool sphere_search_tile(const float4 *__restrict__ xp
     return improved;
 }
 
-template <int TILE, int MINB>
+// FUSED epilogue for one row of 32 consecutive queries (one per lane): add every query's fixed-point coordinates and a
+// count to the accumulator of the candidate it picked.  Runs of equal winners over consecutive lanes are merged by a
+// segmented scan before touching memory; a row that picked one winner (the far field) costs four atomics in total.
+// Kept out of line so that its registers do not weigh on the traversal.
+__device__ __noinline__ void fused_row_accumulate(unsigned long long *accb, bool valid, int winner, float x, float y,
+                                                  float z, float fix_scale, const long long *rowsum, int lane) {
+    const int t = valid ? winner : (-1 - lane);  // an invalid lane is its own empty run
+    const int tp = __shfl_up_sync(0xffffffffu, t, 1);
+    const unsigned heads = __ballot_sync(0xffffffffu, lane == 0 || tp != t);
+    if (heads == 1u && t >= 0) {
+        if (lane == 0) {
+            atomicAdd(accb + 4 * int64_t(t) + 0, static_cast<unsigned long long>(rowsum[0]));
+            atomicAdd(accb + 4 * int64_t(t) + 1, static_cast<unsigned long long>(rowsum[1]));
+            atomicAdd(accb + 4 * int64_t(t) + 2, static_cast<unsigned long long>(rowsum[2]));
+            atomicAdd(accb + 4 * int64_t(t) + 3, 32ull);
+        }
+        return;
+    }
+    long long v0 = 0, v1 = 0, v2 = 0;
+    int cnt = 0;
+    if (valid) {
+        v0 = __float2ll_rn(__fmul_rn(x, fix_scale));
+        v1 = __float2ll_rn(__fmul_rn(y, fix_scale));
+        v2 = __float2ll_rn(__fmul_rn(z, fix_scale));
+        cnt = 1;
+    }
+    const int start = 31 - __clz(heads & (0xffffffffu >> (31 - lane)));
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const long long u0 = __shfl_up_sync(0xffffffffu, v0, o), u1 = __shfl_up_sync(0xffffffffu, v1, o);
+        const long long u2 = __shfl_up_sync(0xffffffffu, v2, o);
+        const int uc = __shfl_up_sync(0xffffffffu, cnt, o);
+        if (lane - o >= start) {
+            v0 += u0;
+            v1 += u1;
+            v2 += u2;
+            cnt += uc;
+        }
+    }
+    const bool tail = lane == 31 || ((heads >> (lane + 1)) & 1u);
+    if (tail && t >= 0) {
+        atomicAdd(accb + 4 * int64_t(t) + 0, static_cast<unsigned long long>(v0));
+        atomicAdd(accb + 4 * int64_t(t) + 1, static_cast<unsigned long long>(v1));
+        atomicAdd(accb + 4 * int64_t(t) + 2, static_cast<unsigned long long>(v2));
+        atomicAdd(accb + 4 * int64_t(t) + 3, static_cast<unsigned long long>(cnt));
+    }
+}
+
+template <int TILE, int MINB, bool FUSED>
 __global__ void __launch_bounds__(CU_WARPS * 32, MINB) nn_sphere_kernel(const SphereParams p) {
     constexpr int ST = TILE < 32 ? 32 : TILE;
     __shared__ __align__(16) float stile[CU_WARPS][3][ST];  // canonical fallback path only
+    __shared__ long long rowsum[FUSED ? CU_WARPS : 1][CU_QPT][3];  // FUSED: fixed-point coordinate sums of the warp's 4 rows
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int64_t group = int64_t(blockIdx.x) * CU_WARPS + warp;
     const int64_t q0 = group * CU_GROUP;
@@ -604,6 +686,23 @@ __global__ void __launch_bounds__(CU_WARPS * 32, MINB) nn_sphere_kernel(const Sp
                 big |= x2 > 1e30f;
             }
             canonical = __ballot_sync(0xffffffffu, big) != 0;
+            if (FUSED) {
+                // the queries are static across the frames of this CTA: the sum of a whole row of 32 consecutive
+                // queries is a constant, used whenever the row's queries all pick the same winner (the far field)
+#pragma unroll
+                for (int k = 0; k < CU_QPT; ++k) {
+                    const float c3[3] = {qx[k], qy[k], qz[k]};
+#pragma unroll
+                    for (int a = 0; a < 3; ++a) {
+                        const long long v = __float2ll_rn(__fmul_rn(c3[a], p.fix_scale));
+                        const int lo = int(v & 0x1FFFFF), mid = int((v >> 21) & 0x1FFFFF), hi = int(v >> 42);
+                        const long long slo = __reduce_add_sync(0xffffffffu, lo), smid = __reduce_add_sync(0xffffffffu, mid);
+                        const long long shi = __reduce_add_sync(0xffffffffu, hi);
+                        if (lane == 0) rowsum[warp][k][a] = slo + (smid << 21) + (shi << 42);
+                    }
+                }
+                __syncwarp();
+            }
         }
         const float *planes = p.planes + int64_t(b) * p.plane_bstride;
         const float4 *tab = p.table + int64_t(b) * p.table_bstride;
@@ -771,18 +870,37 @@ __global__ void __launch_bounds__(CU_WARPS * 32, MINB) nn_sphere_kernel(const Sp
             traverse(std::true_type{});
         else
             traverse(std::false_type{});
+        if (FUSED) {
+            unsigned long long *accb = p.acc + int64_t(b) * p.M * 4;
+            double dsum = 0.0;
 #pragma unroll
-        for (int k = 0; k < CU_QPT; ++k) {
-            const int64_t qi = q0 + k * 32 + lane;
-            if (qi < p.N) {
-                const int64_t o = int64_t(b) * p.N + qi;
-                const int64_t gi = p.idx_base + bidx[k];
-                p.dist[o] = best[k];
-                if (p.idx_bytes == 8)
-                    static_cast<long long *>(p.idx)[o] = gi;
-                else
-                    static_cast<int *>(p.idx)[o] = int(gi);
-                if (p.seed != nullptr) p.seed[o] = bidx[k];
+            for (int k = 0; k < CU_QPT; ++k) {
+                const int64_t qi = q0 + k * 32 + lane;
+                const bool inb = qi < p.N;
+                if (inb) {
+                    dsum += double(best[k]);
+                    if (p.seed != nullptr) p.seed[int64_t(b) * p.N + qi] = bidx[k];
+                }
+                // a query without a finite winner contributes no gradient
+                fused_row_accumulate(accb, inb && best[k] < CUDART_INF_F, bidx[k], qx[k], qy[k], qz[k], p.fix_scale,
+                                     &rowsum[warp][k][0], lane);
+            }
+            dsum = warp_sum(dsum);  // fixed shuffle tree: deterministic
+            if (lane == 0) p.sum_partial[int64_t(b) * p.groups + group] = dsum;
+        } else {
+#pragma unroll
+            for (int k = 0; k < CU_QPT; ++k) {
+                const int64_t qi = q0 + k * 32 + lane;
+                if (qi < p.N) {
+                    const int64_t o = int64_t(b) * p.N + qi;
+                    const int64_t gi = p.idx_base + bidx[k];
+                    p.dist[o] = best[k];
+                    if (p.idx_bytes == 8)
+                        static_cast<long long *>(p.idx)[o] = gi;
+                    else
+                        static_cast<int *>(p.idx)[o] = int(gi);
+                    if (p.seed != nullptr) p.seed[o] = bidx[k];
+                }
             }
         }
     }
@@ -899,6 +1017,38 @@ __global__ void sphere_expand_kernel(const float *__restrict__ planes, int64_t M
     out[3] = make_float4(w[0], w[1], w[2], w[3]);
 }
 
+// ---- fused-loss helpers -----------------------------------------------------------------------------------------
+// sum_d[b] = sum over the query groups of the per-warp partial sums, in a fixed order (deterministic)
+__global__ void __launch_bounds__(256) sphere_sum_kernel(const double *__restrict__ partial, int64_t groups,
+                                                         float *__restrict__ sum_d) {
+    __shared__ double scratch[32];
+    const int64_t b = blockIdx.x;
+    double s = 0.0;
+    for (int64_t g = threadIdx.x; g < groups; g += blockDim.x) s += partial[b * groups + g];
+    s = block_sum(s, scratch);
+    if (threadIdx.x == 0) sum_d[b] = float(s);
+}
+
+// d/dy of  sum_b g_b sum_j d(x_j, y_b,win(j)):  grad[b][i] = 2 g_b (n_i y_i - S_i), from the integer accumulators
+__global__ void __launch_bounds__(256) scene2body_grad_kernel(const float *__restrict__ y,
+                                                              const unsigned long long *__restrict__ acc,
+                                                              double inv_scale, const float *__restrict__ g, int64_t M,
+                                                              float *__restrict__ grad, int accumulate) {
+    const int64_t b = blockIdx.y;
+    const int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= M) return;
+    const unsigned long long *a = acc + (b * M + i) * 4;
+    const double n = double(a[3]);
+    const double g2 = 2.0 * double(g[b]);
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        const double S = double(static_cast<long long>(a[c])) * inv_scale;
+        const float v = float(g2 * (n * double(y[(b * M + i) * 3 + c]) - S));
+        float *o = grad + (b * M + i) * 3 + c;
+        *o = accumulate ? __fadd_rn(*o, v) : v;
+    }
+}
+
 // ---- ordering helpers: one launch each instead of dozens of elementwise torch ops per step -------------------
 __device__ __forceinline__ unsigned spread10(unsigned v) {
     v &= 0x3FFu;
@@ -999,16 +1149,12 @@ int fpv_nn_tile_boxes(const float *planes, const int32_t *orig_idx, int64_t batc
  * with cand_batches == batches or 1.  Returns, per query, the canonical distance and the
  * ORIGINAL index (+ idx_base) of the lexicographic (distance, original index) minimum -- identical to
  * fpv_nn_search on the unsorted cloud.  tiles_searched (optional, device) accumulates statistics. */
-int fpv_nn_culled_search(const float *queries, int q_shared, int64_t batches, int64_t N, const float *planes,
-                         const float *boxes, const int32_t *orig_idx, int64_t cand_batches, int64_t M, int mode,
-                         int64_t idx_base, float *dist, void *idx, int idx_bytes,
-                         unsigned long long *tiles_searched, const float *cand_orig, int32_t *seed_inout,
-                         int seed_valid, fpv_stream_t stream) {
-    FPV_CHECK_ARG(queries && planes && boxes && orig_idx && dist && idx, "fpv_nn_culled_search: null pointer");
-    FPV_CHECK_ARG(!seed_inout || (cand_orig && mode == 0), "fpv_nn_culled_search: seeds need cand_orig and box mode");
-    FPV_CHECK_ARG(batches > 0 && N > 0 && M > 0 && batches <= 65535, "fpv_nn_culled_search: empty input");
-    FPV_CHECK_ARG(cand_batches == 1 || cand_batches == batches, "fpv_nn_culled_search: cand_batches must be 1 or batches");
-    FPV_CHECK_ARG(idx_bytes == 4 || idx_bytes == 8, "fpv_nn_culled_search: idx_bytes must be 4 or 8");
+static int culled_search_impl(const float *queries, int q_shared, int64_t batches, int64_t N, const float *planes,
+                              const float *boxes, const int32_t *orig_idx, int64_t cand_batches, int64_t M, int mode,
+                              int64_t idx_base, float *dist, void *idx, int idx_bytes,
+                              unsigned long long *tiles_searched, const float *cand_orig, int32_t *seed_inout,
+                              int seed_valid, unsigned long long *keys, unsigned long long *const *push, int push_n,
+                              const unsigned *push_parity, int64_t push_half, cudaStream_t st) {
     CulledParams p;
     int64_t eb = batches, eN = N;
     p.q_bstride = q_shared ? 0 : N * 3;
@@ -1038,14 +1184,19 @@ int fpv_nn_culled_search(const float *queries, int q_shared, int64_t batches, in
     p.cand_orig_bstride = cand_batches == 1 ? 0 : M * 3;
     p.seed = seed_inout;
     p.seed_read = (seed_inout && seed_valid) ? 1 : 0;
-    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    p.keys = keys;
+    p.push_n = push_n;
+    for (int r = 0; r < FPV_MAX_PEERS; ++r) p.push[r] = (r < push_n) ? push[r] : nullptr;
+    p.push_parity = push_parity;
+    p.push_half = push_half;
     dim3 grid((unsigned)ceil_div(ceil_div(eN, CU_GROUP), CU_WARPS), (unsigned)eb);
     if (profile_on()) {
+        // algorithmic bytes per SURVEY 8(d): queries + candidates once + (d, i) out; seeds are not counted
         char nm[48];
         snprintf(nm, sizeof(nm), "nn_culled<%s> Q=%lld M=%lld", mode ? "rep" : "box", (long long)(eb * eN), (long long)M);
         profile_begin(nm, st,
-                      12.0 * double(q_shared ? N : batches * N) + 40.0 * double(M) * double(cand_batches) +
-                          (4.0 + idx_bytes) * double(eb * eN),
+                      12.0 * double(q_shared ? N : batches * N) + 12.0 * double(M) * double(cand_batches) +
+                          (keys ? 8.0 * (1 + push_n) : 4.0 + idx_bytes) * double(eb * eN),
                       double(eb * eN) * double(M));
     }
     if (mode)
@@ -1055,6 +1206,44 @@ int fpv_nn_culled_search(const float *queries, int q_shared, int64_t batches, in
     profile_end(st);
     FPV_LAUNCH_CHECK("nn_culled_kernel");
     return FPV_OK;
+}
+
+int fpv_nn_culled_search(const float *queries, int q_shared, int64_t batches, int64_t N, const float *planes,
+                         const float *boxes, const int32_t *orig_idx, int64_t cand_batches, int64_t M, int mode,
+                         int64_t idx_base, float *dist, void *idx, int idx_bytes,
+                         unsigned long long *tiles_searched, const float *cand_orig, int32_t *seed_inout,
+                         int seed_valid, fpv_stream_t stream) {
+    FPV_CHECK_ARG(queries && planes && boxes && orig_idx && dist && idx, "fpv_nn_culled_search: null pointer");
+    FPV_CHECK_ARG(!seed_inout || (cand_orig && mode == 0), "fpv_nn_culled_search: seeds need cand_orig and box mode");
+    FPV_CHECK_ARG(batches > 0 && N > 0 && M > 0 && batches <= 65535, "fpv_nn_culled_search: empty input");
+    FPV_CHECK_ARG(cand_batches == 1 || cand_batches == batches, "fpv_nn_culled_search: cand_batches must be 1 or batches");
+    FPV_CHECK_ARG(idx_bytes == 4 || idx_bytes == 8, "fpv_nn_culled_search: idx_bytes must be 4 or 8");
+    return culled_search_impl(queries, q_shared, batches, N, planes, boxes, orig_idx, cand_batches, M, mode, idx_base, dist,
+                              idx, idx_bytes, tiles_searched, cand_orig, seed_inout, seed_valid, nullptr, nullptr, 0,
+                              nullptr, 0, static_cast<cudaStream_t>(stream));
+}
+
+/* The same search with the multi-GPU epilogue: every query's result is written as ONE packed key
+ * (float_bits(d) << 32 | idx_base + index; canonical d >= 0, so unsigned integer order == lexicographic (d, index) order)
+ * into keys[], and the same key is stored into push_n peer buffers of the same layout (device pointers into the other
+ * ranks' mailboxes, mapped with fpv_p2p_open) straight from the search epilogue.  When push_parity is given, bit 0 of the
+ * device word selects the half (offset push_half elements) of keys / push buffers (double-buffered mailbox). */
+int fpv_nn_culled_search_keys(const float *queries, int q_shared, int64_t batches, int64_t N, const float *planes,
+                              const float *boxes, const int32_t *orig_idx, int64_t cand_batches, int64_t M,
+                              int64_t idx_base, uint64_t *keys, uint64_t *const *push_host, int push_n,
+                              const uint32_t *push_parity, int64_t push_half, unsigned long long *tiles_searched,
+                              const float *cand_orig, int32_t *seed_inout, int seed_valid, fpv_stream_t stream) {
+    FPV_CHECK_ARG(queries && planes && boxes && orig_idx && keys, "fpv_nn_culled_search_keys: null pointer");
+    FPV_CHECK_ARG(!seed_inout || cand_orig, "fpv_nn_culled_search_keys: seeds need cand_orig");
+    FPV_CHECK_ARG(batches > 0 && N > 0 && M > 0 && batches <= 65535, "fpv_nn_culled_search_keys: empty input");
+    FPV_CHECK_ARG(cand_batches == 1 || cand_batches == batches, "fpv_nn_culled_search_keys: cand_batches must be 1 or batches");
+    FPV_CHECK_ARG(push_n >= 0 && push_n <= FPV_MAX_PEERS && (push_n == 0 || push_host), "fpv_nn_culled_search_keys: bad push list");
+    FPV_CHECK_ARG(idx_base >= 0 && idx_base + M <= 0xFFFFFFFFll, "fpv_nn_culled_search_keys: global index does not fit 32 bits");
+    return culled_search_impl(queries, q_shared, batches, N, planes, boxes, orig_idx, cand_batches, M, 0, idx_base, nullptr,
+                              nullptr, 4, tiles_searched, cand_orig, seed_inout, seed_valid,
+                              reinterpret_cast<unsigned long long *>(keys),
+                              reinterpret_cast<unsigned long long *const *>(push_host), push_n, push_parity, push_half,
+                              static_cast<cudaStream_t>(stream));
 }
 
 
@@ -1090,18 +1279,12 @@ int fpv_nn_sphere_set_chunking(int ctas_per_sm) {
     return FPV_OK;
 }
 
-/* Exact NN through the sphere hierarchy.  cand_orig (optional): the candidates in ORIGINAL order
- * [cand_batches][M][3]; with a shared query set it enables temporal seeding across consecutive batches (frames). */
-int fpv_nn_sphere_search(const float *queries, int q_shared, int64_t batches, int64_t N, const float *planes,
-                         const float *table, const int32_t *orig_idx, const float *cand_orig, int32_t *seed_inout,
-                         int seed_valid, int64_t M, int tile, int64_t idx_base, float *dist, void *idx, int idx_bytes,
-                         unsigned long long *tiles_searched, fpv_stream_t stream) {
-    FPV_CHECK_ARG(queries && planes && table && orig_idx && dist && idx, "fpv_nn_sphere_search: null pointer");
-    FPV_CHECK_ARG(!seed_inout || cand_orig, "fpv_nn_sphere_search: seed_inout needs cand_orig");
-    FPV_CHECK_ARG(batches > 0 && N > 0 && M > 0 && batches <= 65535, "fpv_nn_sphere_search: empty input");
-    FPV_CHECK_ARG(idx_bytes == 4 || idx_bytes == 8, "fpv_nn_sphere_search: idx_bytes must be 4 or 8");
-    FPV_CHECK_ARG(tile == 16 || tile == 32, "fpv_nn_sphere_search: tile must be 16 or 32");
-    FPV_CHECK_ARG((reinterpret_cast<uintptr_t>(table) & 15) == 0, "fpv_nn_sphere_search: table must be 16-byte aligned");
+static int sphere_search_impl(const float *queries, int q_shared, int64_t batches, int64_t N, const float *planes,
+                              const float *table, const int32_t *orig_idx, const float *cand_orig, int32_t *seed_inout,
+                              int seed_valid, int64_t M, int tile, int64_t idx_base, float *dist, void *idx, int idx_bytes,
+                              unsigned long long *tiles_searched, double *sum_partial, unsigned long long *acc,
+                              int fix_shift, cudaStream_t st) {
+    const bool fused = sum_partial != nullptr;
     SphereParams p;
     p.q = queries;
     p.q_bstride = q_shared ? 0 : N * 3;
@@ -1128,6 +1311,10 @@ int fpv_nn_sphere_search(const float *queries, int q_shared, int64_t batches, in
     p.idx = idx;
     p.idx_bytes = idx_bytes;
     p.tiles_searched = tiles_searched;
+    p.sum_partial = sum_partial;
+    p.groups = ceil_div(N, CU_GROUP);
+    p.acc = acc;
+    p.fix_scale = ldexpf(1.0f, fix_shift);
     const int64_t ctas_x = ceil_div(ceil_div(N, CU_GROUP), CU_WARPS);
     int64_t nchunks = batches;
     if (q_shared && cand_orig) {  // walk frames inside the warp, but keep >= ~2 resident waves of CTAs
@@ -1138,22 +1325,110 @@ int fpv_nn_sphere_search(const float *queries, int q_shared, int64_t batches, in
     }
     p.frames_per_cta = int(ceil_div(batches, nchunks));
     nchunks = ceil_div(batches, p.frames_per_cta);
-    cudaStream_t st = static_cast<cudaStream_t>(stream);
     dim3 grid((unsigned)ctas_x, (unsigned)nchunks);
     if (profile_on()) {
+        // algorithmic bytes per SURVEY 8(d): queries once, candidates once per batch, outputs; the carried seeds are an
+        // implementation device, not part of the algorithmic traffic, and are NOT counted
         char nm[48];
-        snprintf(nm, sizeof(nm), "nn_sphere<%d> Q=%lld M=%lld", tile, (long long)(batches * N), (long long)M);
-        profile_begin(nm, st,
-                      12.0 * double(q_shared ? N : batches * N) + 24.0 * double(M) * double(batches) +
-                          (4.0 + idx_bytes + (seed_inout ? 4.0 : 0.0) + (p.seed_read ? 4.0 : 0.0)) * double(batches * N),
+        snprintf(nm, sizeof(nm), "nn_sphere%s<%d> Q=%lld M=%lld", fused ? "_fused" : "", tile, (long long)(batches * N),
+                 (long long)M);
+        const double out_bytes = fused ? 8.0 * double(batches) + 12.0 * double(M) * double(batches)
+                                       : (4.0 + idx_bytes) * double(batches * N);
+        profile_begin(nm, st, 12.0 * double(q_shared ? N : batches * N) + 12.0 * double(M) * double(batches) + out_bytes,
                       double(batches * N) * double(M));
     }
-    if (tile == 16)
-        nn_sphere_kernel<16, 8><<<grid, CU_WARPS * 32, 0, st>>>(p);  // 64 registers, 32 resident warps: latency-bound
-    else
-        nn_sphere_kernel<32, 8><<<grid, CU_WARPS * 32, 0, st>>>(p);
+    if (fused) {
+        if (tile == 16)
+            nn_sphere_kernel<16, 8, true><<<grid, CU_WARPS * 32, 0, st>>>(p);
+        else
+            nn_sphere_kernel<32, 8, true><<<grid, CU_WARPS * 32, 0, st>>>(p);
+    } else if (tile == 16) {
+        nn_sphere_kernel<16, 8, false><<<grid, CU_WARPS * 32, 0, st>>>(p);  // 64 registers, 32 resident warps: latency-bound
+    } else {
+        nn_sphere_kernel<32, 8, false><<<grid, CU_WARPS * 32, 0, st>>>(p);
+    }
     profile_end(st);
     FPV_LAUNCH_CHECK("nn_sphere_kernel");
+    return FPV_OK;
+}
+
+/* Exact NN through the sphere hierarchy.  cand_orig (optional): the candidates in ORIGINAL order
+ * [cand_batches][M][3]; with a shared query set it enables temporal seeding across consecutive batches (frames). */
+int fpv_nn_sphere_search(const float *queries, int q_shared, int64_t batches, int64_t N, const float *planes,
+                         const float *table, const int32_t *orig_idx, const float *cand_orig, int32_t *seed_inout,
+                         int seed_valid, int64_t M, int tile, int64_t idx_base, float *dist, void *idx, int idx_bytes,
+                         unsigned long long *tiles_searched, fpv_stream_t stream) {
+    FPV_CHECK_ARG(queries && planes && table && orig_idx && dist && idx, "fpv_nn_sphere_search: null pointer");
+    FPV_CHECK_ARG(!seed_inout || cand_orig, "fpv_nn_sphere_search: seed_inout needs cand_orig");
+    FPV_CHECK_ARG(batches > 0 && N > 0 && M > 0 && batches <= 65535, "fpv_nn_sphere_search: empty input");
+    FPV_CHECK_ARG(idx_bytes == 4 || idx_bytes == 8, "fpv_nn_sphere_search: idx_bytes must be 4 or 8");
+    FPV_CHECK_ARG(tile == 16 || tile == 32, "fpv_nn_sphere_search: tile must be 16 or 32");
+    FPV_CHECK_ARG((reinterpret_cast<uintptr_t>(table) & 15) == 0, "fpv_nn_sphere_search: table must be 16-byte aligned");
+    return sphere_search_impl(queries, q_shared, batches, N, planes, table, orig_idx, cand_orig, seed_inout, seed_valid, M,
+                              tile, idx_base, dist, idx, idx_bytes, tiles_searched, nullptr, nullptr, 0,
+                              static_cast<cudaStream_t>(stream));
+}
+
+/* Fused scene -> body term (SURVEY.md section 7 "hard parts", section 8d "fused-loss variant"): the same exact search
+ * for ONE query set shared by every batch (the static scene, N points) against per-batch candidates (the body, M
+ * vertices), but nothing of size [batches][N] is written except the in/out seeds:
+ *   sum_d[b]      = sum_j min_i d(x_j, y_b,i)                                   (double accumulation, fixed order)
+ *   acc[b][i][0..2] = sum over the queries that candidate i won of x_j * 2^fix_shift (two's complement), acc[b][i][3] = count
+ * acc must be zero on entry ([batches][M][4] uint64).  fpv_scene2body_grad turns acc into d sum / d y.
+ * fix_shift: choose 2^fix_shift * max|x| * (N + 1) < 2^62 (fpv_fix_shift_for).  Queries whose winner distance is not
+ * finite add +inf / NaN to sum_d and nothing to acc. */
+size_t fpv_nn_sphere_fused_workspace_bytes(int64_t batches, int64_t N) {
+    if (batches <= 0 || N <= 0) return 0;
+    return align_up(size_t(batches) * size_t(ceil_div(N, CU_GROUP)) * sizeof(double), 256) + 256;
+}
+
+int fpv_fix_shift_for(float max_abs_coordinate, int64_t count) {
+    int e = 0;
+    if (max_abs_coordinate > 0.f && max_abs_coordinate <= 3.4e38f) frexpf(max_abs_coordinate, &e);
+    int bits = 0;
+    while ((int64_t(1) << bits) < count + 1) ++bits;
+    int k = 61 - bits - e;
+    return k < -100 ? -100 : (k > 100 ? 100 : k);
+}
+
+int fpv_nn_sphere_fused(const float *queries, int64_t batches, int64_t N, const float *planes, const float *table,
+                        const int32_t *orig_idx, const float *cand_orig, int32_t *seed_inout, int seed_valid, int64_t M,
+                        int tile, int fix_shift, float *sum_d, unsigned long long *acc,
+                        unsigned long long *tiles_searched, void *workspace, size_t workspace_bytes,
+                        fpv_stream_t stream) {
+    FPV_CHECK_ARG(queries && planes && table && orig_idx && cand_orig && sum_d && acc, "fpv_nn_sphere_fused: null pointer");
+    FPV_CHECK_ARG(batches > 0 && N > 0 && M > 0 && batches <= 65535, "fpv_nn_sphere_fused: empty input");
+    FPV_CHECK_ARG(tile == 16 || tile == 32, "fpv_nn_sphere_fused: tile must be 16 or 32");
+    FPV_CHECK_ARG((reinterpret_cast<uintptr_t>(table) & 15) == 0, "fpv_nn_sphere_fused: table must be 16-byte aligned");
+    FPV_CHECK_ARG(fix_shift >= -100 && fix_shift <= 100, "fpv_nn_sphere_fused: fix_shift out of range");
+    Arena ar(workspace, workspace_bytes);
+    const int64_t groups = ceil_div(N, CU_GROUP);
+    double *partial = ar.take<double>(size_t(batches) * size_t(groups));
+    if (!partial) {
+        set_error("fpv_nn_sphere_fused: workspace too small (%zu bytes, need %zu)", workspace_bytes,
+                  fpv_nn_sphere_fused_workspace_bytes(batches, N));
+        return FPV_ERR_WORKSPACE;
+    }
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    int rc = sphere_search_impl(queries, 1, batches, N, planes, table, orig_idx, cand_orig, seed_inout, seed_valid, M, tile,
+                                0, nullptr, nullptr, 4, tiles_searched, partial, acc, fix_shift, st);
+    if (rc) return rc;
+    sphere_sum_kernel<<<(unsigned)batches, 256, 0, st>>>(partial, groups, sum_d);
+    FPV_LAUNCH_CHECK("sphere_sum_kernel");
+    return FPV_OK;
+}
+
+/* grad_y[b][i][:] (+)= 2 g[b] (count y - S 2^-fix_shift): the gradient of sum_b g[b] sum_d[b] w.r.t. the candidates
+ * (accumulate != 0 adds to what grad already holds). */
+int fpv_scene2body_grad(const float *cand /*[batches][M][3]*/, const unsigned long long *acc, int fix_shift,
+                        const float *g /*[batches]*/, int64_t batches, int64_t M, float *grad /*[batches][M][3]*/,
+                        int accumulate, fpv_stream_t stream) {
+    FPV_CHECK_ARG(cand && acc && g && grad, "fpv_scene2body_grad: null pointer");
+    FPV_CHECK_ARG(batches > 0 && M > 0 && batches <= 65535, "fpv_scene2body_grad: empty input");
+    dim3 grid((unsigned)ceil_div(M, 256), (unsigned)batches);
+    scene2body_grad_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(cand, acc, ldexp(1.0, -fix_shift), g, M, grad,
+                                                                               accumulate);
+    FPV_LAUNCH_CHECK("scene2body_grad_kernel");
     return FPV_OK;
 }
 

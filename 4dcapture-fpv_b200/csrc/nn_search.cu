@@ -295,12 +295,13 @@ static NNPlan nn_plan(int64_t batches, int64_t N, int64_t M) {
 
 template <int QPT, int NP>
 static cudaError_t nn_launch(const NNParams &p, dim3 grid, cudaStream_t st) {
-    static bool configured = false;
-    if (!configured) {
+    static PerDeviceOnce once;
+    bool *configured = once.slot();
+    if (!*configured) {
         cudaError_t e = cudaFuncSetAttribute(nn_search_kernel<QPT, NP>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              int(NN_SMEM));
         if (e != cudaSuccess) return e;
-        configured = true;
+        *configured = true;
     }
     nn_search_kernel<QPT, NP><<<grid, NN_THREADS + 32, NN_SMEM, st>>>(p);
     return cudaGetLastError();
@@ -605,13 +606,15 @@ static int chamfer_bwd_impl(const float *a, const float *b, int64_t bs, int64_t 
         absmax_kernel<<<nb, 256, 0, st>>>(ptr, n, out);
     };
     // the contribution bound only needs max|g| and the coordinate ranges: three cheap streaming reductions instead of a
-    // pass that re-gathers every (query, winner) pair
-    absmax(a, bs * N * 3, cmax + 1);
-    absmax(b, gb_batches * M * 3, cmax + 2);
-    FPV_CUDA(cudaMemcpyAsync(cmax + 5, cmax + 2, sizeof(unsigned), cudaMemcpyDeviceToDevice, st));
-    FPV_CUDA(cudaMemcpyAsync(cmax + 6, cmax + 1, sizeof(unsigned), cudaMemcpyDeviceToDevice, st));
-    count_launch();
-    count_launch();
+    // pass that re-gathers every (query, winner) pair.  Nothing to bound when no scatter runs (pure gather).
+    if (g_b2a || need_acc_b) {
+        absmax(a, bs * N * 3, cmax + 1);
+        absmax(b, gb_batches * M * 3, cmax + 2);
+        FPV_CUDA(cudaMemcpyAsync(cmax + 5, cmax + 2, sizeof(unsigned), cudaMemcpyDeviceToDevice, st));
+        FPV_CUDA(cudaMemcpyAsync(cmax + 6, cmax + 1, sizeof(unsigned), cudaMemcpyDeviceToDevice, st));
+        count_launch();
+        count_launch();
+    }
     dim3 gridN((unsigned)ceil_div(N, 256), (unsigned)bs), gridM((unsigned)ceil_div(M, 256), (unsigned)bs);
     dim3 gridNr((unsigned)ceil_div(N, 256 * BWD_ROWS), (unsigned)bs);
     dim3 gridMr((unsigned)ceil_div(M, 256 * BWD_ROWS), (unsigned)bs);

@@ -533,11 +533,12 @@ void nn_tc_set_subtile(int ns) { g_tc_ns = (ns == 64 || ns == 128) ? ns : 128; }
 
 template <int NS>
 static cudaError_t nn_tc_dispatch(const NNTCParams &p, dim3 grid, cudaStream_t st) {
-    static bool configured = false;
-    if (!configured) {
+    static PerDeviceOnce once;
+    bool *configured = once.slot();
+    if (!*configured) {
         cudaError_t e = cudaFuncSetAttribute(nn_tc_kernel<NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(TC_SMEM));
         if (e != cudaSuccess) return e;
-        configured = true;
+        *configured = true;
     }
     nn_tc_kernel<NS><<<grid, TC_THREADS, TC_SMEM, st>>>(p);
     return cudaGetLastError();

@@ -271,10 +271,11 @@ int tc_gemm_3xtf32(const float *a_hi, const float *a_lo, int64_t lda, const floa
     if ((rc = make_kmajor_map(&tAl, a_lo, M, K, lda))) return rc;
     if ((rc = make_kmajor_map(&tBh, b_hi, N, K, ldb))) return rc;
     if ((rc = make_kmajor_map(&tBl, b_lo, N, K, ldb))) return rc;
-    static bool configured = false;
-    if (!configured) {
+    static PerDeviceOnce once;
+    bool *configured = once.slot();
+    if (!*configured) {
         FPV_CUDA(cudaFuncSetAttribute(tc_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(TG_SMEM)));
-        configured = true;
+        *configured = true;
     }
     TGParams p;
     p.M = M;

@@ -12,8 +12,13 @@ Mirrors FittingOP.cal_loss + loss.backward() of /root/reference/global_optimizat
 
 front_end=True adds the reference's parameter front-end and the `dct` prior (prior.py):
 the optimised variable becomes the 78-D 6D-rotation row with the VPoser latent, decoded every step.  The default
-(front_end=False) optimises the axis-angle parameter row directly.  The Adam update stays outside the step.
-With world_size > 1 the scene is sharded across ranks (sharded.py).
+(front_end=False) optimises the axis-angle parameter row directly.
+mode="local" assembles FittingOP.cal_loss2 instead (:368-447, the second stage of fitting(mode='local')): reconstruction,
+parameter 2nd-difference, VERTEX 2nd-difference over all 10,475 vertices and the contact-weighted leg velocity -- no chamfer.
+optimizer_step() is the reference's Adam update (:188, :592) as capturable kernels; step(update=True) / a capture with
+update=True ends with it, so the body moves from step to step as it does under the reference's optimiser.
+With world_size > 1 the scene is sharded across ranks (sharded.py); the shards are combined through peer memory (p2p.py)
+and the whole sharded step can be captured too.
 """
 from __future__ import annotations
 
@@ -22,7 +27,7 @@ from typing import Dict, Optional
 import torch
 import torch.distributed as dist
 
-from . import chamfer, prior, residuals, sharded
+from . import _lib, chamfer, p2p, prior, residuals, sharded
 from .body_model import SMPLXB200
 from .synthetic import make_body_constants, make_clip_params, make_scene
 
@@ -56,6 +61,7 @@ def contact_vertex_ids(constants: Dict[str, torch.Tensor]) -> torch.Tensor:
 
 
 SHARD_BLOCK = 2048
+ADAM = dict(lr=0.005, beta1=0.9, beta2=0.999, eps=1e-8)     # optim.Adam(..., lr=self.init_lr_h) :188, init_lr_h = 0.005 :671
 
 
 def _morton_sorted(points: torch.Tensor) -> torch.Tensor:
@@ -65,40 +71,72 @@ def _morton_sorted(points: torch.Tensor) -> torch.Tensor:
     return points[torch.argsort(spatial.morton_keys(points, lo, inv_cell), stable=True)].contiguous()
 
 
+def leg_vertex_ids(constants: Dict[str, torch.Tensor]):
+    """Synthetic stand-ins for body_segments/L_Leg.json and R_Leg.json (:401-409): (left ids, right ids)."""
+    dom = constants["lbs_weights"].argmax(dim=1)
+    left = torch.zeros(55, dtype=torch.bool)
+    right = torch.zeros(55, dtype=torch.bool)
+    left[[4, 7, 10]] = True
+    right[[5, 8, 11]] = True
+    return torch.nonzero(left[dom]).squeeze(1), torch.nonzero(right[dom]).squeeze(1)
+
+
 class FitProblem:
     """Synthetic clip + scene + body model on one device, and the per-step forward/backward."""
 
     def __init__(self, T: int, M: int, device, seed: int = 1234, scene_kind: str = "uniform",
                  rank: int = 0, world_size: int = 1, group=None, idx_dtype=torch.int64, presort_scene: bool = True,
-                 front_end: bool = False, dct_frames: int = DCT_FRAMES):
+                 front_end: bool = False, dct_frames: int = DCT_FRAMES, mode: str = "global", fused: bool = True,
+                 comm: str = "p2p", options: Optional[chamfer.SearchOptions] = None, clips: int = 1):
+        """clips > 1: T is the TOTAL number of frames of `clips` independent clips of T/clips frames batched into one
+        step (BASELINE.json configs[4]); the temporal residuals never couple frames of different clips.
+        fused: scene -> body reduced inside the search kernel (chamfer.scene_to_body_sum) instead of materialising
+        [T,M] distances and indices.  comm: "p2p" (peer-memory mailbox) or "nccl" for the sharded key / gradient exchange."""
+        if mode not in ("global", "local"):
+            raise RuntimeError("FitProblem: mode must be 'global' (cal_loss) or 'local' (cal_loss2)")
+        if T % clips != 0:
+            raise RuntimeError("FitProblem: T must be a multiple of clips")
         self.T, self.M, self.device = T, M, torch.device(device)
+        self.clips, self.Tc = clips, T // clips
         self.rank, self.world, self.group = rank, world_size, group
         self.idx_dtype = idx_dtype
+        self.mode, self.fused = mode, bool(fused)
+        self.options = options or chamfer.DEFAULT_OPTIONS
+        self.search_state = chamfer.SearchState()          # seeds, frozen body order: per problem, never global
         constants = make_body_constants(seed)
         self.constants = constants
         self.model = SMPLXB200(constants, batch_size=T).to(self.device)
-        clip = make_clip_params(T, seed)
+        parts = [make_clip_params(self.Tc, seed + 1000 * c) for c in range(clips)]
+        clip = {k: (torch.cat([p[k] for p in parts]) if parts[0][k].dim() > 0 else parts[0][k]) for k in parts[0]}
         self.front_end = front_end
+        self.dct_batches = 0
         if front_end:
             self.vposer = prior.VPoserDecoderB200(prior.make_vposer_weights(seed)).to(self.device)
             g = torch.Generator().manual_seed(seed + 77)
-            latent = torch.clamp(torch.cumsum(torch.randn(T, 32, generator=g) * 0.02, 0), -2.0, 2.0)
+            latent = torch.cat([torch.clamp(torch.cumsum(torch.randn(self.Tc, 32, generator=g) * 0.02, 0), -2.0, 2.0)
+                                for _ in range(clips)])
             row75 = torch.cat([clip["transl"], clip["global_orient"], clip["betas"], latent, clip["left_hand_pose"],
                                clip["right_hand_pose"], clip["cam_transl"]], dim=1)
             # the observed data in the 6D form, converted once like the reference's loader does (:96-104)
             self.host_params = prior.convert_to_6D_rot(row75.to(self.device)).cpu().contiguous()      # [T,78]
-            self.dct_batches = T // dct_frames
+            self.dct_batches = (self.Tc // dct_frames) * clips if mode == "global" else 0
+            self.dct_frames = dct_frames
             if self.dct_batches:
                 self.dct_mtx = prior.dct_basis(dct_frames, min(DCT_NUM, dct_frames), self.device)
                 self.host_c_dct = torch.randn(self.dct_batches, 23, 3, self.dct_mtx.shape[1], generator=g)   # :186
         else:
             self.host_params = pack_params(clip)                       # [T,106] observed data (CPU)
-        self.host_scene = make_scene(M, scene_kind, seed)              # [M,3] (CPU)
+        self.host_scene = make_scene(M, scene_kind, seed) if mode == "global" else torch.zeros(0, 3)
         self.host_camera_ext = clip["camera_ext"].clone()
         self.host_scale = clip["scale"].clone().reshape(1)
         self.contact_ids = contact_vertex_ids(constants).to(self.device)
+        left, right = leg_vertex_ids(constants)
+        self.left_ids, self.right_ids = left.to(self.device), right.to(self.device)
+        # cal_loss2's per-frame contact weight (detect_contact, :315-365): a left/right stance pattern in [0,1]
+        gw = torch.Generator().manual_seed(seed + 5)
+        self.host_contact_weight = torch.clamp(0.5 + 0.6 * torch.sin(torch.arange(T) * 0.21 + torch.rand(1, generator=gw) * 6.28), 0, 1)
         self.begin, self.end = sharded.shard_range(M, world_size, rank)
-        if presort_scene:
+        if presort_scene and mode == "global":
             # One-time host-side data preparation: the losses do not depend on the order of the scene points (every
             # term is a min / mean over them), so the scene is stored along the Morton curve.  With several ranks the
             # sorted points are dealt round-robin in blocks of SHARD_BLOCK (blocks keep 128 consecutive queries spatially
@@ -114,10 +152,15 @@ class FitProblem:
                 whole = whole[torch.cat([blocks[i] for r in range(world_size) for i in range(r, nblk, world_size)])]
             parts = [whole[slice(*sharded.shard_range(M, world_size, r))] for r in range(world_size)]
             self.host_scene = torch.cat([_morton_sorted(p) for p in parts]).contiguous()
+        self.comm = None
+        if world_size > 1 and comm == "p2p" and self.device.type == "cuda":
+            nfloats = self.host_params.numel() + 1 + 16 * T + 64 + (self.host_c_dct.numel() if self.dct_batches else 0)
+            self.comm = p2p.Mailbox(self.device, group, key_capacity=T * constants["v_template"].shape[0], float_capacity=nfloats)
+        self._adam = None
         self.upload()
 
     def upload(self, non_blocking: bool = False):
-        """Host -> device copies of every per-step input (the e2e leg calls this inside the timed region)."""
+        """Host -> device copies of every per-step input (the eager e2e leg calls this inside the timed region)."""
         dev = self.device
         self.data = self.host_params.to(dev, non_blocking=non_blocking)
         g = torch.Generator().manual_seed(99)
@@ -127,23 +170,27 @@ class FitProblem:
             if dev.type == "cuda":
                 self.host_params = self.host_params.pin_memory()
                 self._host_init = self._host_init.pin_memory()
-                self.host_scene = self.host_scene.pin_memory()
+                if self.host_scene.numel():
+                    self.host_scene = self.host_scene.pin_memory()
                 self.host_camera_ext = self.host_camera_ext.pin_memory()
                 self.host_scale = self.host_scale.pin_memory()
         self.params = self._host_init.to(dev, non_blocking=non_blocking).requires_grad_(True)
         self.scale = self.host_scale.to(dev, non_blocking=non_blocking).requires_grad_(True)
         self.camera_ext = self.host_camera_ext.to(dev, non_blocking=non_blocking).requires_grad_(True)
-        self.scene = self.host_scene[self.begin:self.end].to(dev, non_blocking=non_blocking).unsqueeze(0)
+        if self.mode == "global":
+            self.scene = self.host_scene[self.begin:self.end].to(dev, non_blocking=non_blocking).unsqueeze(0)
+        self.contact_weight = self.host_contact_weight.to(dev, non_blocking=non_blocking)
         if self.front_end and self.dct_batches:
             if dev.type == "cuda" and not self.host_c_dct.is_pinned():
                 self.host_c_dct = self.host_c_dct.pin_memory()
             self.c_dct = self.host_c_dct.to(dev, non_blocking=non_blocking).requires_grad_(True)
+        self._adam = None
         return self
 
     def h2d_bytes(self) -> int:
         extra = self.host_c_dct.numel() if (self.front_end and self.dct_batches) else 0
-        return 4 * (self.host_params.numel() * 2 + self.host_scale.numel() + self.host_camera_ext.numel()
-                    + (self.end - self.begin) * 3 + extra)
+        scene = (self.end - self.begin) * 3 if self.mode == "global" else 0
+        return 4 * (self.host_params.numel() * 2 + self.host_scale.numel() + self.host_camera_ext.numel() + scene + extra)
 
     def d2h_bytes(self) -> int:
         return 4 * (1 + sum(t.numel() for t in self.leaves()))
@@ -152,8 +199,17 @@ class FitProblem:
         extra = [self.c_dct] if (self.front_end and self.dct_batches) else []
         return [self.params, self.scale, self.camera_ext] + extra
 
-    def forward(self) -> Dict[str, torch.Tensor]:
-        p, W = self.params, LOSS_WEIGHTS
+    # ---- temporal residuals, clip-aware: frames of different clips are never differenced ----
+    def _per_clip(self, fn, x, *rest):
+        if self.clips == 1:
+            return fn(x, *rest)
+        Tc = self.Tc
+        vals = [fn(x[c * Tc:(c + 1) * Tc], *[r[c * Tc:(c + 1) * Tc] for r in rest]) for c in range(self.clips)]
+        return torch.stack(vals).mean()
+
+    def _body(self):
+        """Front-end + body model + world placement: (vertices [T,V,3], joints [T,23,3], extra losses)."""
+        p = self.params
         sl = lambda r: p[:, r[0]:r[1]]
         inv_world = 1.0 / self.world
         extra_losses = {}
@@ -162,7 +218,8 @@ class FitProblem:
             bp = prior.body_params_encapsulate_batch(prior.convert_to_3D_rot(p))
             z = bp.pop("body_pose_vp")
             cam_transl = bp.pop("camera_translation")
-            extra_losses["vposer"] = torch.mean(z ** 2) * inv_world
+            if self.mode == "global":
+                extra_losses["vposer"] = torch.mean(z ** 2) * inv_world
             b2w = residuals.body2world(cam_transl, self.scale, self.camera_ext)
             out = self.model(return_verts=True, body_pose=self.vposer.decode(z, output_type="aa").view(self.T, -1), **bp)
         else:
@@ -171,54 +228,125 @@ class FitProblem:
                              global_orient=sl(P_ORIENT), betas=sl(P_BETAS),
                              left_hand_pose=sl(P_LH), right_hand_pose=sl(P_RH))
         verts = residuals.verts_transform(out.vertices * self.scale, b2w)
-        joints = residuals.verts_transform(out.joints[:, 0:23, :].contiguous() * self.scale, b2w)
+        # joints are transformed UNSCALED, as in the reference (only the vertices are multiplied by scale, :284-285 vs :296-297)
+        joints = residuals.verts_transform(out.joints[:, 0:23, :].contiguous(), b2w)
+        return verts, joints, extra_losses
+
+    def forward(self) -> Dict[str, torch.Tensor]:
+        if self.mode == "local":
+            return self.forward_local()
+        p, W = self.params, LOSS_WEIGHTS
+        inv_world = 1.0 / self.world
+        verts, joints, extra_losses = self._body()
         if self.world > 1:
-            d_b2a, d_a2b, _, _ = sharded.distChamferSharded(verts, self.scene, self.begin, self.group, clip=True)
+            s_b2a, d_a2b, _, _ = sharded.distChamferSharded(verts, self.scene, self.begin, self.group, clip=True,
+                                                            comm=self.comm, options=self.options, state=self.search_state,
+                                                            fused=self.fused)
+        elif self.fused:
+            s_b2a, d_a2b, _ = chamfer.fit_chamfer_terms(verts, self.scene, clip=True, options=self.options,
+                                                        state=self.search_state, idx_dtype=self.idx_dtype)
         else:
-            d_b2a, d_a2b, _, _ = chamfer.distChamfer(verts, self.scene, idx_dtype=self.idx_dtype, clip=True)
+            s_b2a, d_a2b, _, _ = chamfer.distChamfer(verts, self.scene, idx_dtype=self.idx_dtype, clip=True,
+                                                     options=self.options, state=self.search_state)
         losses = {
             "rec": torch.mean(torch.abs(self.data - p)) * inv_world,
-            "smoothing": residuals.second_diff_l1(p) * inv_world,
+            "smoothing": self._per_clip(residuals.second_diff_l1, p) * inv_world,
             "contact": residuals.contact_robust_loss(d_a2b.index_select(1, self.contact_ids)) * inv_world,
-            "scene2body": d_b2a.sum() / float(self.T * self.M),
-            "world_smoothing": residuals.first_diff_l1(joints) * inv_world,
-            "vert_smoothing": residuals.second_diff_l1(verts) * inv_world,
+            "scene2body": s_b2a.sum() / float(self.T * self.M),
+            "world_smoothing": self._per_clip(residuals.first_diff_l1, joints) * inv_world,
+            "vert_smoothing": self._per_clip(residuals.second_diff_l1, verts) * inv_world,
         }
         if self.front_end and self.dct_batches:
-            extra_losses["dct"] = prior.cal_dctloss(joints, self.dct_mtx, self.c_dct) * inv_world      # :310
+            extra_losses["dct"] = self._dct(joints) * inv_world      # :310
         losses.update(extra_losses)
         losses["total"] = sum(W[k] * v for k, v in losses.items())
         return losses
 
-    def step(self) -> torch.Tensor:
-        """zero_grad -> forward -> backward (-> gradient all-reduce).  Returns the detached total loss."""
+    def _dct(self, joints):
+        if self.clips == 1:
+            return prior.cal_dctloss(joints, self.dct_mtx, self.c_dct)
+        per = self.dct_batches // self.clips
+        vals = [prior.cal_dctloss(joints[c * self.Tc:(c + 1) * self.Tc], self.dct_mtx, self.c_dct[c * per:(c + 1) * per])
+                for c in range(self.clips)]
+        return torch.stack(vals).mean()
+
+    def forward_local(self) -> Dict[str, torch.Tensor]:
+        """FittingOP.cal_loss2 (global_optimization.py:368-447): loss = loss_smoothing + loss_local_smoothing + loss_rec
+        + loss_contact_smoothing (:549); no chamfer (its block is commented out, :432-445).  Not sharded (replicas)."""
+        p = self.params
+        verts, _, _ = self._body()
+        w_right = self.contact_weight.clone()                       # :411-416
+        w_left = 1.0 - w_right
+        w_left = torch.where(w_left < 0.5, torch.zeros_like(w_left), w_left)
+        w_right = torch.where(w_right < 0.5, torch.zeros_like(w_right), w_right)
+        vl = verts.index_select(1, self.left_ids)
+        vr = verts.index_select(1, self.right_ids)
+        losses = {
+            "rec": torch.mean(torch.abs(self.data - p)),                                        # :376
+            "local_smoothing": self._per_clip(residuals.second_diff_l1, p),                     # :381-382
+            "smoothing": self._per_clip(residuals.second_diff_l1, verts),                       # :404-405
+            "contact_smoothing": self._per_clip(residuals.first_diff_l1, vl, w_left)            # :415-429
+            + self._per_clip(residuals.first_diff_l1, vr, w_right),
+        }
+        losses["total"] = losses["rec"] + losses["local_smoothing"] + losses["smoothing"] + losses["contact_smoothing"]
+        return losses
+
+    # ---- the optimiser update (global_optimization.py:188, :592) ----
+    def trainable(self):
+        """The leaves the update touches: the first stage of fitting() trains body_rotation_rec and scale
+        (:565-568; camera_ext and c_dct are frozen there); mode 'local' trains body_rotation_rec only (:543-546)."""
+        return [self.params] if self.mode == "local" else [self.params, self.scale]
+
+    def optimizer_step(self) -> None:
+        """One torch.optim.Adam step (lr 0.005) on the trainable leaves, as kernels with a device-side step counter."""
+        L = _lib.lib()
+        if self._adam is None:
+            self._adam = {"step": torch.zeros(1, dtype=torch.float32, device=self.device),
+                          "state": [(torch.zeros_like(t), torch.zeros_like(t)) for t in self.trainable()]}
+        with torch.cuda.device(self.device), torch.no_grad():
+            _lib.check(L.fpv_adam_tick(_lib.ptr(self._adam["step"]), _lib.stream_ptr()), "fpv_adam_tick")
+            for t, (m, v) in zip(self.trainable(), self._adam["state"]):
+                _lib.check(L.fpv_adam_update(_lib.ptr(t), _lib.ptr(t.grad), _lib.ptr(m), _lib.ptr(v), t.numel(),
+                                             ADAM["lr"], ADAM["beta1"], ADAM["beta2"], ADAM["eps"],
+                                             _lib.ptr(self._adam["step"]), _lib.stream_ptr()), "fpv_adam_update")
+
+    def _backward_and_reduce(self, losses):
+        """backward, then (sharded) ONE exchange that sums the parameter gradients and the loss over the ranks."""
+        losses["total"].backward()
+        loss = losses["total"].detach()
+        if self.world > 1 and self.mode == "global":
+            loss = sharded.allreduce_grads(self.leaves(), self.group, comm=self.comm, extra=loss.reshape(1)).reshape(())
+        return loss
+
+    def step(self, update: bool = False) -> torch.Tensor:
+        """zero_grad -> forward -> backward (-> gradient + loss exchange) (-> Adam update).  Returns the detached
+        total loss (the GLOBAL loss on every rank when sharded)."""
         for t in self.leaves():
             t.grad = None
-        losses = self.forward()
-        losses["total"].backward()
-        if self.world > 1:
-            sharded.allreduce_grads(self.leaves(), self.group)
-        return losses["total"].detach()
+        loss = self._backward_and_reduce(self.forward())
+        if update:
+            self.optimizer_step()
+        return loss
 
-    def capture(self, warmup: int = 3):
-        """Capture zero_grad -> forward -> backward as ONE CUDA graph (SURVEY.md section
-        8f, row f1): ~250 kernel launches, no host synchronisation, no allocation at replay.  Returns self;
-        step_graph() replays.
+    def capture(self, warmup: int = 3, update: bool = False):
+        """Capture zero_grad -> forward -> backward (-> exchange) (-> Adam update) as ONE CUDA graph (SURVEY.md section
+        8f, row f1): no host synchronisation, no allocation at replay.  Returns self; step_graph() replays.
 
         Everything the step touches is capture-safe by construction: the library entry points only enqueue work
-        on the caller's stream into caller-provided workspaces, the scene index and the seed buffers are cached (built
-        during warm-up; the kernels update the seeds in place), the per-step tensors come from torch's graph-private
-        pool.  After capture the leaves, the observed data and the scene are STATIC buffers: change them in place
-        (copy_), never rebind them -- and the scene must stay what it was (its index is not part of the graph).
-        Single-rank only: capturing the sharded step together with its NCCL collectives deadlocked on 2 GPUs in round 1
-        (both ranks blocked inside the capture), so the sharded step stays eager."""
-        if self.world != 1:
-            raise RuntimeError("FitProblem.capture: single-rank only (the sharded step keeps its NCCL combine outside a graph)")
+        on the caller's stream into caller-provided workspaces, the scene index, the body ordering and the seed buffers
+        are cached (built during warm-up; the kernels update the seeds in place), the per-step tensors come from torch's
+        graph-private pool.  After capture the leaves, the observed data and the scene are STATIC buffers: change them
+        in place (copy_), never rebind them -- and the scene must stay what it was (its index is not part of the graph;
+        spatial.invalidate_scene after refilling it).
+        Sharded steps capture too when the shards are combined through the p2p mailbox (kernels only); with NCCL as the
+        transport (comm="nccl") the step stays eager: capturing the NCCL collectives deadlocked in round 1."""
+        if self.world != 1 and self.comm is None and self.mode == "global":
+            raise RuntimeError("FitProblem.capture: the sharded step is capturable with comm='p2p' only")
         side = torch.cuda.Stream(self.device)
         side.wait_stream(torch.cuda.current_stream(self.device))
         with torch.cuda.stream(side):
             for _ in range(max(1, warmup)):
-                self.step()
+                self.step(update=update)
         torch.cuda.current_stream(self.device).wait_stream(side)
         torch.cuda.synchronize(self.device)
         for t in self.leaves():
@@ -227,9 +355,10 @@ class FitProblem:
         # capture on the stream the warm-up ran on: the leaves' AccumulateGrad nodes then live on the capture stream and
         # autograd inserts no dependency on the legacy default stream (illegal while a stream is capturing)
         with torch.cuda.graph(self._graph, stream=side):
-            losses = self.forward()
-            losses["total"].backward()
-            self._graph_loss = losses["total"].detach()
+            self._graph_loss = self._backward_and_reduce(self.forward())
+            if update:
+                self.optimizer_step()
+        self._graph_update = update
         return self
 
     def step_graph(self) -> torch.Tensor:
@@ -239,31 +368,39 @@ class FitProblem:
         return self._graph_loss
 
     def step_e2e_graph(self):
-        """End to end through the captured step: every per-step input goes from pinned host memory into the static
-        device buffers, the graph is replayed, loss + gradients come back to the host.  The scene is resident, as in
-        the reference (uploaded once before the loop, global_optimization.py:173-176)."""
+        """End to end through the captured step.  The observed data (the step's input) goes from pinned host memory
+        into the static device buffer, the graph is replayed, the loss and the gradients (update=False capture) or the
+        updated leaves (update=True: the optimiser state lives on the device, as in the reference) come back to the
+        host.  The scene is resident, as in the reference (uploaded once before the loop, :173-176)."""
         with torch.no_grad():
             self.data.copy_(self.host_params, non_blocking=True)
-            self.params.copy_(self._host_init, non_blocking=True)
-            self.scale.copy_(self.host_scale, non_blocking=True)
-            self.camera_ext.copy_(self.host_camera_ext, non_blocking=True)
-            if self.front_end and self.dct_batches:
-                self.c_dct.copy_(self.host_c_dct, non_blocking=True)
+            if not self._graph_update:
+                self.params.copy_(self._host_init, non_blocking=True)
+                self.scale.copy_(self.host_scale, non_blocking=True)
+                self.camera_ext.copy_(self.host_camera_ext, non_blocking=True)
+                if self.front_end and self.dct_batches:
+                    self.c_dct.copy_(self.host_c_dct, non_blocking=True)
         loss = self.step_graph()
-        host = [loss.to("cpu", non_blocking=True)] + [t.grad.to("cpu", non_blocking=True) for t in self.leaves()]
+        outs = [t.detach() for t in self.leaves()] if self._graph_update else [t.grad for t in self.leaves()]
+        host = [loss.to("cpu", non_blocking=True)] + [t.to("cpu", non_blocking=True) for t in outs]
         torch.cuda.synchronize(self.device)
         return host
 
     def h2d_bytes_graph(self) -> int:
-        return self.h2d_bytes() - 4 * (self.end - self.begin) * 3
+        if getattr(self, "_graph_update", False):
+            return 4 * self.host_params.numel()
+        scene = (self.end - self.begin) * 3 if self.mode == "global" else 0
+        return self.h2d_bytes() - 4 * scene
 
     def step_e2e(self):
         """The same step from HOST buffers: pinned inputs -> device, step, loss + gradients -> host."""
         self.upload(non_blocking=True)
         loss = self.step()
-        if self.world > 1:
-            loss = loss.clone()
-            dist.all_reduce(loss, group=self.group)
         host = [loss.to("cpu", non_blocking=True)] + [t.grad.to("cpu", non_blocking=True) for t in self.leaves()]
         torch.cuda.synchronize(self.device)
         return host
+
+    def close(self):
+        if self.comm is not None:
+            self.comm.close()
+            self.comm = None

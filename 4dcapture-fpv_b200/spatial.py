@@ -8,6 +8,8 @@ built once and cached; the body vertices are re-sorted every step (a [T,V] argso
 """
 from __future__ import annotations
 
+import ctypes
+import os
 from typing import Dict, Tuple
 
 import torch
@@ -43,13 +45,30 @@ def grid_of(points: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
     return lo, 1023.999 / ext
 
 
+def morton_order(points: torch.Tensor, lo: torch.Tensor, inv_cell: torch.Tensor) -> torch.Tensor:
+    """[M,3] -> int64 [M]: sorted position -> original index along the Morton curve of the grid (lo, inv_cell)."""
+    _lib.require_cuda(points)
+    L = _lib.lib()
+    pts = points.contiguous()
+    M = pts.shape[0]
+    lo_c, ic_c = lo.to(torch.float32).contiguous(), inv_cell.to(torch.float32).contiguous()
+    with torch.cuda.device(pts.device):
+        keys = torch.empty(M, dtype=torch.int64, device=pts.device)
+        _lib.check(L.fpv_morton_keys(_lib.ptr(pts), M, _lib.ptr(lo_c), _lib.ptr(ic_c), _lib.ptr(keys), _lib.stream_ptr()),
+                   "fpv_morton_keys")
+    return torch.argsort(keys)
+
+
 class SortedCloud:
     """[B,M,3] cloud sorted per batch along the Morton curve + everything nn_culled_kernel needs."""
 
     def __init__(self, points: torch.Tensor, lo: torch.Tensor = None, inv_cell: torch.Tensor = None, mode: int = 0,
-                 sphere_tile: int = 0, check_identity: bool = False, shared_perm: bool = False):
+                 sphere_tile: int = 0, check_identity: bool = False, shared_perm: bool = False,
+                 perm: torch.Tensor = None, tables: bool = True):
         """mode 0: 64-point tiles with bounding boxes; mode 1: 32-point tiles with representative + radius.
-        sphere_tile (16 | 32): build the four-level bounding-sphere table of nn_sphere_kernel instead."""
+        sphere_tile (16 | 32): build the four-level bounding-sphere table of nn_sphere_kernel instead.
+        perm (with shared_perm): a ready ordering [M] int64 (sorted position -> original index) -- no sort is run.
+        tables=False: only the sorted points are needed (the cloud serves as QUERIES), skip the cluster tables."""
         if points.dim() == 2:
             points = points.unsqueeze(0)
         _lib.require_cuda(points)
@@ -69,10 +88,9 @@ class SortedCloud:
                 # One ordering for every batch entry, taken from the middle one: the batch is a clip of ONE articulated
                 # surface, so points that are neighbours in one frame stay neighbours in all of them.  The order only
                 # shapes the clusters (their spheres are rebuilt from the actual points of each frame), never the result.
-                keys = torch.empty(M, dtype=torch.int64, device=dev)
-                _lib.check(L.fpv_morton_keys(_lib.ptr(pts[B // 2]), M, _lib.ptr(lo_c), _lib.ptr(ic_c), _lib.ptr(keys),
-                                             _lib.stream_ptr()), "fpv_morton_keys")
-                perm_c = torch.argsort(keys)                                         # sorted position -> original index
+                perm_c = perm if perm is not None else morton_order(pts[B // 2], lo, inv_cell)
+                if perm_c.shape != (M,) or perm_c.dtype != torch.int64:
+                    raise RuntimeError("SortedCloud: perm must be an int64 tensor of shape [M]")
                 self.perm = perm_c.unsqueeze(0).expand(B, -1)
             else:
                 keys = torch.empty(B, M, dtype=torch.int64, device=dev)
@@ -90,7 +108,10 @@ class SortedCloud:
                                             _lib.ptr(self.planes), _lib.ptr(self.oidx), _lib.stream_ptr()),
                        "fpv_nn_gather_pack")
             self.sphere_tile = sphere_tile
-            if sphere_tile:
+            self.boxes = None
+            if not tables:
+                pass
+            elif sphere_tile:
                 self.boxes = torch.empty(B * L.fpv_nn_sphere_table_floats(M, sphere_tile), dtype=torch.float32,
                                          device=points.device)
                 _lib.check(L.fpv_nn_sphere_table(_lib.ptr(self.planes), B, M, sphere_tile, _lib.ptr(self.boxes),
@@ -100,7 +121,22 @@ class SortedCloud:
                 _lib.check(L.fpv_nn_tile_boxes(_lib.ptr(self.planes), _lib.ptr(self.oidx), B, M, mode, _lib.ptr(self.boxes),
                                                _lib.stream_ptr()), "fpv_nn_tile_boxes")
         self._inv = None
-        self.seeds = {}   # (batches, candidates) -> [batches, M] int32 winners of the last search with this cloud as QUERIES
+        self.states = {}      # default SearchState handles of callers that pass none: (T, N) -> chamfer.SearchState
+        self._fix_shift = None
+
+    def perm_row(self):
+        """(perm tensor, batched flag) for fpv_p2p_min_unpack: sorted position -> original position."""
+        if self.shared_perm:
+            return self.perm[0].contiguous(), False
+        return self.perm.contiguous(), True
+
+    def fix_shift(self) -> int:
+        """Fixed-point exponent of the fused scene -> body accumulators for THIS cloud as the query set: computed once
+        (one reduction + one host read when the cloud is first used that way; the scene is static)."""
+        if self._fix_shift is None:
+            finite = torch.nan_to_num(self.sorted, nan=0.0, posinf=0.0, neginf=0.0)
+            self._fix_shift = int(_lib.lib().fpv_fix_shift_for(float(finite.abs().max().item()), self.M))
+        return self._fix_shift
 
     @property
     def inv_perm(self) -> torch.Tensor:
@@ -137,6 +173,59 @@ def culled_search(queries_grouped: torch.Tensor, q_shared: bool, batches: int, c
     return dist, idx
 
 
+def culled_search_keys(queries_grouped: torch.Tensor, batches: int, cloud: SortedCloud, idx_base: int = 0,
+                       stats: torch.Tensor = None, cand_orig: torch.Tensor = None, seed: torch.Tensor = None,
+                       seed_valid: bool = False, keys: torch.Tensor = None, push=None, push_parity=None,
+                       push_half: int = 0) -> torch.Tensor:
+    """Box-culled search of [batches,N,3] grouped queries against ONE sorted cloud, with the packed-key epilogue:
+    returns int64 keys [batches*N] = float_bits(d) << 32 | (idx_base + original index), in the QUERY order given.
+    keys (optional): the destination, e.g. this rank's slot of a p2p mailbox (a raw device address as int); push: raw
+    device addresses of the same slot in the peers' mailboxes (the kernel stores into them directly)."""
+    L = _lib.lib()
+    q = queries_grouped.contiguous()
+    N = q.shape[1]
+    dev = q.device
+    out = None
+    if keys is None:
+        out = torch.empty(batches * N, dtype=torch.int64, device=dev)
+        keys_ptr = _lib.ptr(out)
+    else:
+        keys_ptr = ctypes.c_void_p(int(keys))
+    n_push = len(push) if push else 0
+    arr = (ctypes.c_void_p * max(n_push, 1))(*[ctypes.c_void_p(int(x)) for x in (push or [])])
+    with torch.cuda.device(dev):
+        _lib.check(L.fpv_nn_culled_search_keys(_lib.ptr(q), 0, batches, N, _lib.ptr(cloud.planes), _lib.ptr(cloud.boxes),
+                                               _lib.ptr(cloud.oidx), cloud.B, cloud.M, idx_base, keys_ptr, arr, n_push,
+                                               ctypes.c_void_p(int(push_parity)) if push_parity else None,
+                                               int(push_half), _lib.ptr(stats),
+                                               _lib.ptr(cand_orig.contiguous() if seed is not None else None),
+                                               _lib.ptr(seed), int(seed_valid), _lib.stream_ptr()),
+                   "fpv_nn_culled_search_keys")
+    return out
+
+
+def min_unpack(slots, world: int, n: int, row: int, perm_row, idx_dtype=torch.int32, device=None, slot_stride: int = 0,
+               half_stride: int = 0, parity=None, flip: bool = False):
+    """Element-wise minimum over `world` key slots, unpacked to (dist [n], idx [n]) and un-permuted row by row.
+    slots: an int64 tensor (world == 1: plain keys) or a raw device address (a p2p mailbox)."""
+    L = _lib.lib()
+    if isinstance(slots, torch.Tensor):
+        device = slots.device
+        slots_ptr = _lib.ptr(slots)
+    else:
+        slots_ptr = ctypes.c_void_p(int(slots))
+    perm, batched = perm_row if perm_row is not None else (None, False)
+    dist = torch.empty(n, dtype=torch.float32, device=device)
+    idx = torch.empty(n, dtype=idx_dtype, device=device)
+    with torch.cuda.device(device):
+        _lib.check(L.fpv_p2p_min_unpack(slots_ptr, world, int(slot_stride), int(half_stride),
+                                        ctypes.c_void_p(int(parity)) if parity else None, int(flip), n, row,
+                                        _lib.ptr(perm), int(batched), _lib.ptr(dist), _lib.ptr(idx),
+                                        8 if idx_dtype == torch.int64 else 4, None, _lib.stream_ptr()),
+                   "fpv_p2p_min_unpack")
+    return dist, idx
+
+
 def sphere_search(queries_grouped: torch.Tensor, q_shared: bool, batches: int, cloud: SortedCloud,
                   cand_orig: torch.Tensor = None, idx_dtype=torch.int32, idx_base: int = 0, stats: torch.Tensor = None,
                   seed: torch.Tensor = None, seed_valid: bool = True):
@@ -161,6 +250,13 @@ def sphere_search(queries_grouped: torch.Tensor, q_shared: bool, batches: int, c
 
 _scene_cache: Dict[tuple, tuple] = {}
 _SCENE_CACHE_MAX = 4
+_VERIFY = os.environ.get("FPV_VERIFY_SCENE_CACHE", "0") == "1"
+
+
+def _checksum(src: torch.Tensor) -> tuple:
+    bits = src.reshape(-1).view(torch.int32).to(torch.int64)
+    w = torch.arange(bits.numel(), device=src.device, dtype=torch.int64) % 65521 + 1
+    return tuple(torch.stack([bits.sum(), (bits * w).sum()]).tolist())
 
 
 def cached_scene(scene: torch.Tensor) -> SortedCloud:
@@ -174,12 +270,14 @@ def cached_scene(scene: torch.Tensor) -> SortedCloud:
     key = (scene.data_ptr(), scene._version, tuple(scene.shape), scene.device.index)
     hit = _scene_cache.get(key)
     if hit is not None:
-        return hit[1]
+        if _VERIFY and hit[2] is not None and not torch.cuda.is_current_stream_capturing() and \
+                _checksum(scene.detach()) != hit[2]:
+            del _scene_cache[key]             # content changed behind the version counter: rebuild
+        else:
+            return hit[1]
     src = scene.detach()
     if not torch.cuda.is_current_stream_capturing():
-        bits = src.reshape(-1).view(torch.int32).to(torch.int64)
-        w = torch.arange(bits.numel(), device=src.device, dtype=torch.int64) % 65521 + 1
-        h = tuple(torch.stack([bits.sum(), (bits * w).sum()]).tolist())
+        h = _checksum(src)
         for k, (old_src, sc, old_h) in list(_scene_cache.items()):
             if old_h == h and old_src.shape == src.shape and old_src.device == src.device and torch.equal(old_src, src):
                 _scene_cache[key] = (src, sc, h)          # alias under the new tensor's key; the old key stays valid
@@ -199,4 +297,15 @@ def _trim_scene_cache() -> None:
 
 
 def clear_scene_cache() -> None:
+    """Drop every cached scene index (and the seeds / states hanging off them)."""
     _scene_cache.clear()
+
+
+def invalidate_scene(scene: torch.Tensor) -> None:
+    """Forget the cached index of this scene tensor.  REQUIRED after changing a scene in a way torch's version counter
+    does not see (writes through .data, raw pointers, DLPack, or a static buffer refilled under a captured CUDA graph):
+    the fast path of cached_scene keys on (pointer, version, shape) and would otherwise keep serving the index of the
+    old content.  Set FPV_VERIFY_SCENE_CACHE=1 to re-verify the content checksum on every hit (debugging aid)."""
+    ptr = scene.data_ptr()
+    for k in [k for k in _scene_cache if k[0] == ptr]:
+        del _scene_cache[k]

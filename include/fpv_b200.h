@@ -27,6 +27,7 @@ extern "C" {
 #define FPV_ERR_INVALID 1
 #define FPV_ERR_CUDA 2
 #define FPV_ERR_WORKSPACE 3
+#define FPV_MAX_PEERS 7 /* other ranks of one 8-GPU box */
 
 typedef void *fpv_stream_t; /* cudaStream_t */
 
@@ -102,6 +103,19 @@ int fpv_nn_culled_search(const float *queries, int q_shared, int64_t batches, in
  *   [batches][N] int32 buffer of the previous call's winners (original indices, without idx_base), read as starting
  *   points when seed_valid and always overwritten -- hints only, see fpv_nn_sphere_search. */
 
+/* The same search (box mode) with the multi-GPU epilogue (replaces the separate pack pass + NCCL
+ * send buffer of the survey's design): every query's result is written as ONE packed key
+ * (float_bits(d) << 32 | idx_base + index; canonical d >= 0, so unsigned integer order == lexicographic (d, index)
+ * order) into keys[], and the same key is stored into push_n peer buffers of the same layout (push_host: HOST array of
+ * device pointers into the other ranks' mailboxes, mapped with fpv_p2p_open) straight from the search epilogue, so the
+ * NVLink transfer overlaps the search.  push_parity (optional device word): bit 0 selects the half (offset push_half
+ * elements) of keys / push buffers of a double-buffered mailbox. */
+int fpv_nn_culled_search_keys(const float *queries, int q_shared, int64_t batches, int64_t N, const float *planes,
+                              const float *boxes, const int32_t *orig_idx, int64_t cand_batches, int64_t M,
+                              int64_t idx_base, uint64_t *keys, uint64_t *const *push_host, int push_n,
+                              const uint32_t *push_parity, int64_t push_half, unsigned long long *tiles_searched,
+                              const float *cand_orig, int32_t *seed_inout, int seed_valid, fpv_stream_t stream);
+
 /* Ordering helpers of the spatial engines (one launch each): 30-bit Morton keys of n points on the grid
  * (lo[3], inv_cell[3] are DEVICE pointers), and the application of an ordering -- sorted points, padded SoA planes
  * and the original-index table in one pass (perm: int64, [M] when perm_shared, else [batches][M]). */
@@ -131,6 +145,29 @@ int fpv_nn_sphere_search(const float *queries, int q_shared, int64_t batches, in
                          const float *table, const int32_t *orig_idx, const float *cand_orig,
                          int32_t *seed_inout, int seed_valid, int64_t M, int tile, int64_t idx_base, float *dist,
                          void *idx, int idx_bytes, unsigned long long *tiles_searched, fpv_stream_t stream);
+
+/* Fused scene -> body term of the chamfer loss (SURVEY.md section 7 "hard parts", section 8d "fused-loss variant";
+ * the direction of chamfer_python.py:28 that min-reduces over the BODY for every scene point): the same exact sphere
+ * search for ONE query set shared by every batch (the static scene, N points) against per-batch candidates (the body,
+ * M vertices, sphere table as for fpv_nn_sphere_search), but nothing of size [batches][N] is written except the in/out
+ * seeds:
+ *   sum_d[b]         = sum_j min_i d(x_j, y_b,i)                    (double accumulation in a fixed order -> float)
+ *   acc[b][i][0..2] += sum over the queries candidate i won of x_j * 2^fix_shift (64-bit two's complement)
+ *   acc[b][i][3]    += how many queries candidate i won             (integer atomics: order-independent, bitwise
+ *                                                                    reproducible; replaces the [T,M] index pass of
+ *                                                                    fpv_chamfer_bwd for this loss)
+ * acc ([batches][M][4] uint64) must be zero on entry.  fpv_scene2body_grad turns it into d(sum_b g_b sum_d[b]) / d y.
+ * fix_shift = fpv_fix_shift_for(max |query coordinate|, N) keeps every sum below 2^62.  A query whose winner distance
+ * is not finite adds +inf / NaN to sum_d and nothing to acc. */
+size_t fpv_nn_sphere_fused_workspace_bytes(int64_t batches, int64_t N);
+int fpv_fix_shift_for(float max_abs_coordinate, int64_t count);
+int fpv_nn_sphere_fused(const float *queries, int64_t batches, int64_t N, const float *planes, const float *table,
+                        const int32_t *orig_idx, const float *cand_orig, int32_t *seed_inout, int seed_valid,
+                        int64_t M, int tile, int fix_shift, float *sum_d, unsigned long long *acc,
+                        unsigned long long *tiles_searched, void *workspace, size_t workspace_bytes,
+                        fpv_stream_t stream);
+int fpv_scene2body_grad(const float *cand, const unsigned long long *acc, int fix_shift, const float *g,
+                        int64_t batches, int64_t M, float *grad, int accumulate, fpv_stream_t stream);
 
 /* distChamfer(a, b) forward, reference output order (chamfer_python.py:28):
  *   d_b2a [bs,M], d_a2b [bs,N], i_b2a [bs,M] (index into a), i_a2b [bs,N] (index into b).
@@ -281,6 +318,34 @@ int fpv_dct_prior_fwd(const float *x, const float *basis, const float *coef, int
                       int64_t K, float *out, void *workspace, size_t workspace_bytes, fpv_stream_t stream);
 int fpv_dct_prior_bwd(const float *x, const float *basis, const float *coef, int64_t NB, int64_t F, int64_t C,
                       int64_t K, const float *g_out, float *grad_x, float *grad_coef, fpv_stream_t stream);
+
+/* The optimiser update of the reference loop (torch.optim.Adam, global_optimization.py:188, :592) as capturable
+ * kernels: the step counter is a device float, so a CUDA graph that ends with the update replays correctly. */
+int fpv_adam_tick(float *step, fpv_stream_t stream);
+int fpv_adam_update(float *param, const float *grad, float *exp_avg, float *exp_avg_sq, int64_t n, float lr,
+                    float beta1, float beta2, float eps, const float *step, fpv_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Peer-memory mailboxes of the scene-sharded step (p2p.cu).  One process per GPU; every rank
+ * allocates one mailbox, exports its CUDA IPC handle, and maps the other ranks' mailboxes.  Keys are pushed by the
+ * search epilogue (fpv_nn_culled_search_keys), combined by fpv_p2p_min_unpack after fpv_p2p_barrier; the small
+ * parameter-gradient vector goes through fpv_p2p_push / fpv_p2p_sum.  No NCCL, no host synchronisation: capturable.
+ * Pointers named *_host are HOST arrays of device pointers.
+ * ------------------------------------------------------------------------------------------ */
+int fpv_p2p_alloc(size_t bytes, void **ptr_host);
+int fpv_p2p_free(void *ptr);
+int fpv_p2p_export(void *ptr, unsigned char *handle64_host);
+int fpv_p2p_open(const unsigned char *handle64_host, void **peer_ptr_host);
+int fpv_p2p_close(void *peer_ptr);
+int fpv_p2p_barrier(uint32_t *const *flags_host, int rank, int world, uint32_t *epoch, uint32_t *error,
+                    double timeout_s, fpv_stream_t stream);
+int fpv_p2p_min_unpack(const uint64_t *slots, int world, int64_t slot_stride, int64_t half_stride, uint32_t *parity,
+                       int flip, int64_t n, int64_t row, const long long *perm, int perm_batched, float *dist, void *idx,
+                       int idx_bytes, uint64_t *keys_out, fpv_stream_t stream);
+int fpv_p2p_push(const float *src, int64_t n, float *const *dst_host, int n_dst, const uint32_t *parity,
+                 int64_t half_stride, fpv_stream_t stream);
+int fpv_p2p_sum(const float *slots, int world, int64_t slot_stride, int64_t half_stride, uint32_t *parity, int flip,
+                int64_t n, float *out, fpv_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -11,14 +11,15 @@ from oracle import smplx_oracle as so
 pytestmark = pytest.mark.gpu
 
 
-def _oracle_step(fpv, prob):
+def _oracle_step(fpv, prob, dtype=torch.float64):
+    """dtype=float32 runs the SAME assembly in plain torch float32 -- the arithmetic the reference itself runs."""
     from importlib import import_module
     fit = import_module("4dcapture-fpv_b200.fit")
     W = fit.LOSS_WEIGHTS
-    p = prob.params.detach().cpu().double().requires_grad_(True)
-    scale = prob.scale.detach().cpu().double().requires_grad_(True)
-    cam = prob.camera_ext.detach().cpu().double().requires_grad_(True)
-    data = prob.data.cpu().double()
+    p = prob.params.detach().cpu().to(dtype).requires_grad_(True)
+    scale = prob.scale.detach().cpu().to(dtype).requires_grad_(True)
+    cam = prob.camera_ext.detach().cpu().to(dtype).requires_grad_(True)
+    data = prob.data.cpu().to(dtype)
     sl = lambda r: p[:, r[0]:r[1]]
     extra = {}
     c_dct = None
@@ -26,19 +27,19 @@ def _oracle_step(fpv, prob):
         r75 = po.convert_to_3D_rot(p)
         z = r75[:, 16:48]
         extra["vposer"] = torch.mean(z ** 2)
-        wd = {k: getattr(prob.vposer, k).detach().cpu().double() for k in ("w1", "b1", "w2", "b2", "w3", "b3")}
+        wd = {k: getattr(prob.vposer, k).detach().cpu().to(dtype) for k in ("w1", "b1", "w2", "b2", "w3", "b3")}
         b2w = ro.body2world(r75[:, 72:75], scale, cam)
         v, j = so.smplx_forward(prob.constants, betas=r75[:, 6:16], global_orient=r75[:, 3:6],
                                 body_pose=po.vposer_decode_aa(wd, z).view(p.shape[0], -1), transl=r75[:, 0:3],
-                                left_hand_pose=r75[:, 48:60], right_hand_pose=r75[:, 60:72], dtype=torch.float64)
+                                left_hand_pose=r75[:, 48:60], right_hand_pose=r75[:, 60:72], dtype=dtype)
     else:
         b2w = ro.body2world(sl(fit.P_CAM), scale, cam)
         v, j = so.smplx_forward(prob.constants, betas=sl(fit.P_BETAS), global_orient=sl(fit.P_ORIENT),
                                 body_pose=sl(fit.P_POSE), transl=sl(fit.P_TRANSL), left_hand_pose=sl(fit.P_LH),
-                                right_hand_pose=sl(fit.P_RH), dtype=torch.float64)
+                                right_hand_pose=sl(fit.P_RH), dtype=dtype)
     verts = ro.verts_transform(v * scale, b2w)
-    joints = ro.verts_transform(j[:, 0:23] * scale, b2w)
-    scene = prob.host_scene.double()
+    joints = ro.verts_transform(j[:, 0:23], b2w)          # global_optimization.py:296-297: joints are NOT scaled
+    scene = prob.host_scene.to(dtype)
     # indices from the canonical fp32 oracle on the fp32 vertices the GPU path sees; distances re-derived in
     # float64 through those indices so autograd flows exactly as torch.min would route it
     v32 = verts.detach().float().numpy()
@@ -51,8 +52,8 @@ def _oracle_step(fpv, prob):
                   contact=ro.contact_robust_loss(d_a2b[:, cid]), scene2body=d_b2a.mean(),
                   world_smoothing=ro.first_diff_l1(joints), vert_smoothing=ro.second_diff_l1(verts))
     if prob.front_end and prob.dct_batches:
-        c_dct = prob.c_dct.detach().cpu().double().requires_grad_(True)
-        extra["dct"] = po.dct_loss(joints, prob.dct_mtx.cpu().double(), c_dct)
+        c_dct = prob.c_dct.detach().cpu().to(dtype).requires_grad_(True)
+        extra["dct"] = po.dct_loss(joints, prob.dct_mtx.cpu().to(dtype), c_dct)
     losses.update(extra)
     total = sum(W[k] * x for k, x in losses.items())
     total.backward()
@@ -61,19 +62,28 @@ def _oracle_step(fpv, prob):
     return total.item(), p.grad, scale.grad, cam.grad
 
 
+def _check_grads(pairs, floors=None):
+    """1e-5 of the largest entry, or 1.5x the distance of plain torch float32 from the float64 truth where that is
+    larger (gradients that are ill-conditioned signed sums of ~30k vertex terms: the floor any fp32 path shares)."""
+    for k, (got, ref, name) in enumerate(pairs):
+        err = (got.cpu().double() - ref).abs().max().item()
+        tol = 1e-5 * ref.abs().max().item() + 1e-8
+        if floors is not None:
+            tol = max(tol, 1.5 * (floors[k].double() - ref).abs().max().item())
+        assert err <= tol, (name, err, tol)
+
+
 def test_fit_step_matches_oracle(fpv, cuda_dev):
     prob = fpv.FitProblem(T=6, M=20000, device=cuda_dev, seed=1235)
     loss = prob.step()
     ref_loss, gp, gs, gc = _oracle_step(fpv, prob)
-    assert loss.item() == pytest.approx(ref_loss, rel=2e-5)
-    for got, ref, name in [(prob.params.grad, gp, "params"), (prob.scale.grad, gs, "scale"), (prob.camera_ext.grad, gc, "camera_ext")]:
-        err = (got.cpu().double() - ref).abs().max().item()
-        tol = 5e-5 * ref.abs().max().item() + 1e-8
-        assert err <= tol, (name, err, tol)
+    _, *floors = _oracle_step(fpv, prob, torch.float32)
+    assert loss.item() == pytest.approx(ref_loss, rel=1e-5)
+    _check_grads([(prob.params.grad, gp, "params"), (prob.scale.grad, gs, "scale"), (prob.camera_ext.grad, gc, "camera_ext")], floors)
     l2 = prob.step()
     assert l2.item() == loss.item()                                   # same inputs -> bitwise same loss
     host = prob.step_e2e()
-    assert host[0].item() == pytest.approx(ref_loss, rel=2e-5) and host[1].shape == (6, 106)
+    assert host[0].item() == pytest.approx(ref_loss, rel=1e-5) and host[1].shape == (6, 106)
 
 
 def test_fit_step_cuda_graph_replay_matches_eager(fpv, cuda_dev):
@@ -104,12 +114,10 @@ def test_fit_step_with_reference_front_end_matches_oracle(fpv, cuda_dev):
     assert prob.params.shape == (8, 78) and prob.dct_batches == 2 and len(prob.leaves()) == 4
     loss = prob.step()
     ref_loss, gp, gs, gc, gd = _oracle_step(fpv, prob)
-    assert loss.item() == pytest.approx(ref_loss, rel=2e-5)
-    for got, ref, name in [(prob.params.grad, gp, "params"), (prob.scale.grad, gs, "scale"),
-                           (prob.camera_ext.grad, gc, "camera_ext"), (prob.c_dct.grad, gd, "c_dct")]:
-        err = (got.cpu().double() - ref).abs().max().item()
-        tol = 5e-5 * ref.abs().max().item() + 1e-8
-        assert err <= tol, (name, err, tol)
+    _, *floors = _oracle_step(fpv, prob, torch.float32)
+    assert loss.item() == pytest.approx(ref_loss, rel=1e-5)
+    _check_grads([(prob.params.grad, gp, "params"), (prob.scale.grad, gs, "scale"),
+                  (prob.camera_ext.grad, gc, "camera_ext"), (prob.c_dct.grad, gd, "c_dct")], floors)
     assert prob.step().item() == loss.item()
     prob.capture()
     assert torch.equal(prob.step_graph(), loss)
@@ -125,3 +133,53 @@ def test_fit_e2e_graph_matches_eager(fpv, cuda_dev):
     assert len(graph) == len(eager)
     for g, e in zip(graph, eager):
         assert torch.equal(g, e)
+
+
+def _oracle_local_step(fpv, prob):
+    """FittingOP.cal_loss2 (global_optimization.py:368-447) assembled from the float64 oracles."""
+    p = prob.params.detach().cpu().double().requires_grad_(True)
+    scale = prob.scale.detach().cpu().double()
+    cam = prob.camera_ext.detach().cpu().double()
+    data = prob.data.cpu().double()
+    r75 = po.convert_to_3D_rot(p)
+    wd = {k: getattr(prob.vposer, k).detach().cpu().double() for k in ("w1", "b1", "w2", "b2", "w3", "b3")}
+    b2w = ro.body2world(r75[:, 72:75], scale, cam)
+    v, _ = so.smplx_forward(prob.constants, betas=r75[:, 6:16], global_orient=r75[:, 3:6],
+                            body_pose=po.vposer_decode_aa(wd, r75[:, 16:48]).view(p.shape[0], -1), transl=r75[:, 0:3],
+                            left_hand_pose=r75[:, 48:60], right_hand_pose=r75[:, 60:72], dtype=torch.float64)
+    verts = ro.verts_transform(v * scale, b2w)
+    loss_rec = torch.mean(torch.abs(data - p))                                   # :376 (weights all one)
+    diff_local = p[0:-1] - p[1:]
+    loss_local = torch.mean(torch.abs(diff_local[0:-1] - diff_local[1:]))        # :381-382
+    diff = verts[0:-1] - verts[1:]
+    loss_smooth = torch.mean(torch.abs(diff[0:-1] - diff[1:]))                   # :404-405
+    vl, vr = verts[:, prob.left_ids.cpu()], verts[:, prob.right_ids.cpu()]
+    dl, dr = vl[0:-1] - vl[1:], vr[0:-1] - vr[1:]                                # :412-413
+    w_right = prob.contact_weight.cpu().double().clone()                         # :415-420
+    w_left = 1 - w_right
+    w_left[w_left < 0.5] = 0.0
+    w_right[w_right < 0.5] = 0.0
+    wl = w_left[1:].unsqueeze(1).unsqueeze(1).repeat(1, dl.shape[1], dl.shape[2])
+    wr = w_right[1:].unsqueeze(1).unsqueeze(1).repeat(1, dr.shape[1], dr.shape[2])
+    loss_cs = torch.mean(torch.abs(dl * wl)) + torch.mean(torch.abs(dr * wr))    # :429
+    total = loss_smooth + loss_local + loss_rec + loss_cs                        # :549
+    total.backward()
+    return total.item(), p.grad
+
+
+def test_local_mode_step_matches_cal_loss2(fpv, cuda_dev):
+    """mode='local' (second stage of fitting(mode='local'), :536-556): the vertex-space second difference over all
+    10,475 vertices and the contact-weighted leg velocity, forward and backward to the 78-D row."""
+    prob = fpv.FitProblem(T=7, M=0, device=cuda_dev, seed=1241, front_end=True, mode="local")
+    loss = prob.step()
+    ref_loss, gp = _oracle_local_step(fpv, prob)
+    assert loss.item() == pytest.approx(ref_loss, rel=1e-5)
+    _check_grads([(prob.params.grad, gp, "params")])
+    assert prob.scale.grad is None or float(prob.scale.grad.abs().max()) >= 0.0
+    before = prob.params.detach().clone()
+    l2 = prob.step(update=True)
+    assert l2.item() == loss.item() and not torch.equal(prob.params.detach(), before)
+    prob.capture(update=True)
+    a = prob.step_graph().item()
+    b = prob.step_graph().item()
+    assert np.isfinite(a) and np.isfinite(b) and b != a                          # the captured update moves the body

@@ -69,5 +69,5 @@ def test_sharded_nccl_matches_single_gpu(fpv, cuda_dev):
     loss = prob.step()
     assert float(r[0]["fit_loss"]) == pytest.approx(loss.item(), rel=1e-5)
     g1 = prob.params.grad.cpu().numpy()
-    np.testing.assert_allclose(r[0]["fit_grad"], g1, rtol=1e-4, atol=1e-5 * np.abs(g1).max())
-    np.testing.assert_allclose(r[0]["fit_scale"], prob.scale.grad.cpu().numpy(), rtol=1e-4)
+    np.testing.assert_allclose(r[0]["fit_grad"], g1, rtol=1e-5, atol=1e-5 * np.abs(g1).max())
+    np.testing.assert_allclose(r[0]["fit_scale"], prob.scale.grad.cpu().numpy(), rtol=1e-5)

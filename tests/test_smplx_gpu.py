@@ -68,6 +68,12 @@ def test_backward_matches_float64_autograd(fpv, cuda_dev, use_joints):
     v64, j64 = so.smplx_forward(c, **po, dtype=torch.float64)
     lo = (v64 * gv.double()).sum() + ((j64 * gj.double()).sum() if use_joints else 0.0)
     lo.backward()
+    # the same loss through plain torch float32 autograd (the arithmetic the reference itself runs): where a
+    # gradient is an ill-conditioned signed sum of thousands of terms, ITS distance from the float64 truth is the
+    # floor any fp32 implementation shares, and the bar is 1e-5 or that floor, whichever is larger
+    p32 = {k: v.clone().requires_grad_(True) for k, v in p.items()}
+    v32, j32 = so.smplx_forward(c, **p32, dtype=torch.float32)
+    ((v32 * gv).sum() + ((j32 * gj).sum() if use_joints else 0.0)).backward()
     grads = []
     for _ in range(2):
         pg = {k: v.clone().to(cuda_dev).requires_grad_(True) for k, v in p.items()}
@@ -78,7 +84,9 @@ def test_backward_matches_float64_autograd(fpv, cuda_dev, use_joints):
     for k in KEYS:
         ref = po[k].grad
         tol = 1e-5 * float(ref.abs().max()) + 1e-7
-        assert (grads[0][k].double() - ref).abs().max() <= 3 * tol, (k, float((grads[0][k].double() - ref).abs().max()), tol)
+        floor32 = float((p32[k].grad.double() - ref).abs().max())
+        err = float((grads[0][k].double() - ref).abs().max())
+        assert err <= max(tol, 1.5 * floor32), (k, err, tol, floor32)
         assert torch.equal(grads[0][k], grads[1][k]), f"{k}: backward is not run-to-run deterministic"
 
 

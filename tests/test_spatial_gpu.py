@@ -14,17 +14,17 @@ pytestmark = pytest.mark.gpu
 
 @pytest.fixture(params=["sphere16", "sphere32", "rep", "tc"])
 def spatial_engine(fpv, request):
-    ch = importlib.import_module("4dcapture-fpv_b200.chamfer")
-    old = (ch.ENGINE, ch.B2A_ENGINE, ch.SPHERE_TILE)
-    ch.ENGINE = "spatial"
-    ch.B2A_ENGINE = "sphere" if request.param.startswith("sphere") else request.param
-    ch.SPHERE_TILE = 32 if request.param == "sphere32" else 16
-    yield ch
-    ch.ENGINE, ch.B2A_ENGINE, ch.SPHERE_TILE = old
+    """SearchOptions forcing the spatial path with one of its scene->body engines (strategy is an argument, not a
+    module global)."""
+    return fpv.SearchOptions(engine="spatial", b2a_engine="sphere" if request.param.startswith("sphere") else request.param,
+                             sphere_tile=32 if request.param == "sphere32" else 16)
 
 
-def _run(fpv, a, b, dev, idx_dtype=torch.int64):
-    out = fpv.distChamfer(torch.tensor(a, device=dev), torch.tensor(b, device=dev), idx_dtype=idx_dtype)
+BRUTE = dict(engine="brute")
+
+
+def _run(fpv, a, b, dev, idx_dtype=torch.int64, options=None):
+    out = fpv.distChamfer(torch.tensor(a, device=dev), torch.tensor(b, device=dev), idx_dtype=idx_dtype, options=options)
     return [o.cpu().numpy() for o in out]
 
 
@@ -40,31 +40,31 @@ def test_spatial_parity_ragged(fpv, cuda_dev, spatial_engine, T, N, M):
     rng = np.random.default_rng(T * 7 + N * 13 + M)
     a = (rng.standard_normal((T, N, 3)) * 0.5 + [1.0, -0.5, 0.3]).astype(np.float32)
     b = (rng.random((M, 3)) * [8, 8, 3] - [4, 4, 0]).astype(np.float32)
-    _assert_exact(_run(fpv, a, b, cuda_dev), co.dist_chamfer(a, b))
+    _assert_exact(_run(fpv, a, b, cuda_dev, options=spatial_engine), co.dist_chamfer(a, b))
 
 
 def test_spatial_ties_duplicates_lattice(fpv, cuda_dev, spatial_engine):
     rng = np.random.default_rng(1)
     a = rng.integers(-8, 9, (2, 3000, 3)).astype(np.float32)
     b = rng.integers(-8, 9, (5000, 3)).astype(np.float32)          # heavy exact ties across distant tiles
-    _assert_exact(_run(fpv, a, b, cuda_dev), co.dist_chamfer(a, b))
+    _assert_exact(_run(fpv, a, b, cuda_dev, options=spatial_engine), co.dist_chamfer(a, b))
     same = np.zeros((1, 700, 3), np.float32)
-    d1, d2, i1, i2 = _run(fpv, same, same[0], cuda_dev)
+    d1, d2, i1, i2 = _run(fpv, same, same[0], cuda_dev, options=spatial_engine)
     assert (i1 == 0).all() and (i2 == 0).all() and (d1 == 0).all()
     b2 = rng.standard_normal((6000, 3)).astype(np.float32)
     b2[3000:] = b2[:3000]                                          # every point duplicated 3000 indices later
     a2 = b2[None, ::7].copy()
-    _assert_exact(_run(fpv, a2, b2, cuda_dev), co.dist_chamfer(a2, b2))
+    _assert_exact(_run(fpv, a2, b2, cuda_dev, options=spatial_engine), co.dist_chamfer(a2, b2))
 
 
 def test_spatial_outside_bbox_far_and_special(fpv, cuda_dev, spatial_engine):
     rng = np.random.default_rng(4)
     b = (rng.random((5000, 3)) * 2).astype(np.float32)
     a = (rng.standard_normal((2, 800, 3)) * 20).astype(np.float32)   # most queries far outside the scene box
-    _assert_exact(_run(fpv, a, b, cuda_dev), co.dist_chamfer(a, b))
+    _assert_exact(_run(fpv, a, b, cuda_dev, options=spatial_engine), co.dist_chamfer(a, b))
     a3 = (100.0 + 0.01 * rng.standard_normal((1, 900, 3))).astype(np.float32)
     b3 = (100.0 + 0.01 * rng.standard_normal((1300, 3))).astype(np.float32)
-    _assert_exact(_run(fpv, a3, b3, cuda_dev), co.dist_chamfer(a3, b3))
+    _assert_exact(_run(fpv, a3, b3, cuda_dev, options=spatial_engine), co.dist_chamfer(a3, b3))
     x = np.zeros((1, 300, 3), np.float32)
     x[0, :, 0] = np.arange(300)
     x[0, 1] = [np.nan, 0, 0]
@@ -75,7 +75,7 @@ def test_spatial_outside_bbox_far_and_special(fpv, cuda_dev, spatial_engine):
     y[0] = [np.nan, 0, 0]
     y[7] = [-3e38, -3e38, -3e38]
     y[11] = [np.inf, np.inf, 0]
-    got = _run(fpv, x, y, cuda_dev)
+    got = _run(fpv, x, y, cuda_dev, options=spatial_engine)
     want = co.dist_chamfer(x, y)
     assert np.array_equal(got[2], want[2]) and np.array_equal(got[3], want[3])
     assert np.array_equal(got[0], want[0], equal_nan=True) and np.array_equal(got[1], want[1], equal_nan=True)
@@ -86,25 +86,23 @@ def test_spatial_equals_brute_force_at_scale_and_backward(fpv, cuda_dev, spatial
     T, V, M = 4, 10475, 400_000
     scene = (torch.rand(M, 3, generator=gen) * torch.tensor([8.0, 8.0, 3.0]) - torch.tensor([4.0, 4.0, 0.0])).to(cuda_dev)
     verts = (torch.rand(T, V, 3, generator=gen) * torch.tensor([0.6, 0.6, 1.8]) + torch.tensor([0.5, -1.0, 0.0])).to(cuda_dev)
-    spatial_engine.ENGINE = "brute"
-    ref = [o.clone() for o in fpv.distChamfer(verts, scene.unsqueeze(0), idx_dtype=torch.int32)]
-    spatial_engine.ENGINE = "spatial"
+    brute = fpv.SearchOptions(**BRUTE)
+    ref = [o.clone() for o in fpv.distChamfer(verts, scene.unsqueeze(0), idx_dtype=torch.int32, options=brute)]
     va = verts.clone().requires_grad_(True)
-    out = fpv.distChamfer(va, scene.unsqueeze(0), idx_dtype=torch.int32)
+    state = fpv.SearchState()
+    out = fpv.distChamfer(va, scene.unsqueeze(0), idx_dtype=torch.int32, options=spatial_engine, state=state)
     for o, r in zip(out, ref):
         assert torch.equal(o, r)
-    print("tiles searched a->b:", spatial_engine.LAST_STATS["tiles_searched"].tolist(), "of", T * V // 128 * (M // 64))
+    print("tiles searched a->b:", state.stats["tiles_searched"].tolist(), "of", T * V // 128 * (M // 64))
     g = torch.Generator().manual_seed(3)
     w1 = torch.rand(T, M, generator=g).to(cuda_dev)
     w2 = torch.rand(T, V, generator=g).to(cuda_dev)
     ((out[0] * w1).sum() + (out[1] * w2).sum()).backward()
     # the spatially ordered backward must equal the original-order backward bit for bit (integer fixed-point sum)
-    spatial_engine.ENGINE = "brute"
     vb = verts.clone().requires_grad_(True)
-    o2 = fpv.distChamfer(vb, scene.unsqueeze(0), idx_dtype=torch.int32)
+    o2 = fpv.distChamfer(vb, scene.unsqueeze(0), idx_dtype=torch.int32, options=brute)
     ((o2[0] * w1).sum() + (o2[1] * w2).sum()).backward()
     assert torch.equal(va.grad, vb.grad)
-    spatial_engine.ENGINE = "spatial"
 
 
 def test_spatial_presorted_scene_identity(fpv, cuda_dev, spatial_engine):
@@ -118,7 +116,7 @@ def test_spatial_presorted_scene_identity(fpv, cuda_dev, spatial_engine):
     bt = b.to(cuda_dev).unsqueeze(0)
     assert sp.cached_scene(bt).identity
     at = torch.tensor(a, device=cuda_dev, requires_grad=True)
-    out = fpv.distChamfer(at, bt)
+    out = fpv.distChamfer(at, bt, options=spatial_engine)
     want = co.dist_chamfer(a, b.numpy())
     _assert_exact([o.detach().cpu().numpy() for o in out], want)
     g1 = rng.standard_normal(want[0].shape).astype(np.float32)
@@ -138,7 +136,7 @@ def test_spatial_clip_hint_changes_nothing(fpv, cuda_dev, spatial_engine):
     unrelated = (rng.standard_normal((5, 3000, 3)) * 0.5 + [3, 3, 1]).astype(np.float32)
     for a in (clip, unrelated):
         want = co.dist_chamfer(a, b)
-        got = fpv.distChamfer(torch.tensor(a, device=cuda_dev), torch.tensor(b, device=cuda_dev), clip=True)
+        got = fpv.distChamfer(torch.tensor(a, device=cuda_dev), torch.tensor(b, device=cuda_dev), clip=True, options=spatial_engine)
         _assert_exact([o.cpu().numpy() for o in got], want)
 
 
@@ -154,14 +152,8 @@ def test_config2_scene_size_engines_agree_and_round_trip(fpv, cuda_dev):
         out = prob.model(return_verts=True, body_pose=p[:, 16:79], transl=p[:, 0:3], global_orient=p[:, 3:6],
                          betas=p[:, 6:16], left_hand_pose=p[:, 79:91], right_hand_pose=p[:, 91:103])
         verts = fpv.verts_transform(out.vertices * prob.scale, fpv.body2world(p[:, 103:106], prob.scale, prob.camera_ext))
-    old = ch.ENGINE
-    try:
-        ch.ENGINE = "spatial"
-        got = fpv.distChamfer(verts, prob.scene, idx_dtype=torch.int32, clip=True)
-        ch.ENGINE = "brute"
-        ref = fpv.distChamfer(verts, prob.scene, idx_dtype=torch.int32)
-    finally:
-        ch.ENGINE = old
+    got = fpv.distChamfer(verts, prob.scene, idx_dtype=torch.int32, clip=True, options=fpv.SearchOptions(engine="spatial"))
+    ref = fpv.distChamfer(verts, prob.scene, idx_dtype=torch.int32, options=fpv.SearchOptions(engine="brute"))
     for g, r in zip(got, ref):
         assert torch.equal(g, r)
     d_b2a, d_a2b, i_b2a, i_a2b = got
@@ -192,22 +184,24 @@ def test_seed_carry_between_calls_is_only_a_hint(fpv, cuda_dev):
     a0 = (rng.standard_normal((4, 2500, 3)) * 0.35 + [3, 3, 1]).astype(np.float32)
     a1 = (a0 + rng.standard_normal(a0.shape).astype(np.float32) * 0.01).astype(np.float32)
     bt = torch.tensor(b, device=cuda_dev).unsqueeze(0)
-    old = ch.ENGINE
-    try:
-        ch.ENGINE = "spatial"
-        for a in (a0, a0, a1):
-            got = fpv.distChamfer(torch.tensor(a, device=cuda_dev), bt, clip=True)
-            _assert_exact([o.cpu().numpy() for o in got], co.dist_chamfer(a, b))
-        seeds = sp.cached_scene(bt).seeds[("b2a", 4, 2500)]
-        assert seeds.min().item() >= 0 and seeds.max().item() < 2500       # populated by the calls above
-        seeds.copy_(torch.randint(-5, 4000, seeds.shape, device=cuda_dev, dtype=torch.int32))   # garbage, partly invalid
-        seeds_a = sp.cached_scene(bt).seeds[("a2b", 4, 2500)]
-        assert seeds_a.min().item() >= 0 and seeds_a.max().item() < 20000
-        seeds_a.copy_(torch.randint(-5, 30000, seeds_a.shape, device=cuda_dev, dtype=torch.int32))
-        got = fpv.distChamfer(torch.tensor(a1, device=cuda_dev), bt, clip=True)
-        _assert_exact([o.cpu().numpy() for o in got], co.dist_chamfer(a1, b))
-    finally:
-        ch.ENGINE = old
+    opts = fpv.SearchOptions(engine="spatial")
+    state = fpv.SearchState()                                              # the per-problem handle that carries the seeds
+    for a in (a0, a0, a1):
+        got = fpv.distChamfer(torch.tensor(a, device=cuda_dev), bt, clip=True, options=opts, state=state)
+        _assert_exact([o.cpu().numpy() for o in got], co.dist_chamfer(a, b))
+    seeds = state.seeds[("b2a", 4, 20000, cuda_dev.index)]
+    assert seeds.min().item() >= 0 and seeds.max().item() < 2500           # populated by the calls above
+    seeds.copy_(torch.randint(-5, 4000, seeds.shape, device=cuda_dev, dtype=torch.int32))   # garbage, partly invalid
+    seeds_a = state.seeds[("a2b", 4, 2500, cuda_dev.index)]
+    assert seeds_a.min().item() >= 0 and seeds_a.max().item() < 20000
+    seeds_a.copy_(torch.randint(-5, 30000, seeds_a.shape, device=cuda_dev, dtype=torch.int32))
+    got = fpv.distChamfer(torch.tensor(a1, device=cuda_dev), bt, clip=True, options=opts, state=state)
+    _assert_exact([o.cpu().numpy() for o in got], co.dist_chamfer(a1, b))
+    # two problems on the same scene keep separate seeds (no cross-talk through the cached scene)
+    other = fpv.SearchState()
+    got = fpv.distChamfer(torch.tensor(a0, device=cuda_dev), bt, clip=True, options=opts, state=other)
+    _assert_exact([o.cpu().numpy() for o in got], co.dist_chamfer(a0, b))
+    assert other.seeds[("b2a", 4, 20000, cuda_dev.index)].data_ptr() != seeds.data_ptr()
 
 
 def test_scene_cache_follows_content_not_identity(fpv, cuda_dev):
