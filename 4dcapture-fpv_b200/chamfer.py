@@ -106,17 +106,23 @@ def _default_state(scene: spatial.SortedCloud, T: int, N: int) -> SearchState:
 
 def _body_cloud(a_c: torch.Tensor, scene: spatial.SortedCloud, opts: SearchOptions, state: SearchState, clip: bool,
                 spheres: bool) -> spatial.SortedCloud:
-    """The body in Morton order with its cluster table.  clip=True: ONE ordering for every frame, computed on the first
-    call (middle frame) and frozen in the state -- no sort on the per-step path."""
+    """The body in Morton order with its cluster table.  The curve runs on the BODY's own bounding grid (finer cells
+    than the room's, and -- unlike a grid taken from the scene -- identical on every rank of a scene-sharded run, so
+    packed keys can be exchanged in sorted order).  clip=True: ONE ordering for every frame, computed on the first call
+    (middle frame) and frozen in the state -- no sort on the per-step path."""
     T, N, _ = a_c.shape
     shared = clip and opts.body_shared_order and T > 1
     perm = None
+    lo = inv_cell = None
     if shared:
         key = (N, a_c.device.index)
         perm = state.body_perm.get(key)
         if perm is None:
-            perm = state.body_perm[key] = spatial.morton_order(a_c[T // 2], scene.lo, scene.inv_cell)
-    return spatial.SortedCloud(a_c, scene.lo, scene.inv_cell, mode=1,
+            lo, inv_cell = spatial.grid_of(a_c[T // 2])
+            perm = state.body_perm[key] = spatial.morton_order(a_c[T // 2], lo, inv_cell)
+    else:
+        lo, inv_cell = spatial.grid_of(a_c)
+    return spatial.SortedCloud(a_c, lo, inv_cell, mode=1,
                                sphere_tile=opts.sphere_tile if (spheres and opts.b2a_engine == "sphere") else 0,
                                shared_perm=shared, perm=perm, tables=spheres)
 

@@ -231,7 +231,9 @@ __global__ void __launch_bounds__(CU_WARPS * 32) nn_culled_kernel(const CulledPa
             const int sidx = s0 + lane;
             float slb = CUDART_INF_F;
             if (sidx < p.nsuper) slb = box_lb(sboxes + int64_t(sidx) * CU_SLOT, gmin, gmax);
-            unsigned smask = __ballot_sync(0xffffffffu, slb <= worst);
+            // (a lane past the table must never vote: with a query that has no finite best -- NaN / infinite / huge
+            // coordinates -- `worst` is +inf and INF <= INF would send the warp into tiles that do not exist)
+            unsigned smask = __ballot_sync(0xffffffffu, sidx < p.nsuper && slb <= worst);
             while (smask) {
                 const int sl = __ffs(smask) - 1;
                 smask &= smask - 1;
@@ -324,16 +326,18 @@ __global__ void __launch_bounds__(CU_WARPS * 32) nn_culled_kernel(const CulledPa
         const int sidx = s0 + lane;
         float slb = CUDART_INF_F;
         if (sidx < p.nsuper) slb = box_lb(sboxes + int64_t(sidx) * CU_SLOT, gmin, gmax);
-        unsigned smask = __ballot_sync(0xffffffffu, slb <= worst);
+        // a lane past the table must never vote (worst can be +inf: INF <= INF), see the rep-mode sweep above
+        unsigned smask = __ballot_sync(0xffffffffu, sidx < p.nsuper && slb <= worst);
         while (smask) {
             const int sl = __ffs(smask) - 1;
             smask &= smask - 1;
             if (!(__shfl_sync(0xffffffffu, slb, sl) <= worst)) continue;
             const int t0 = (s0 + sl) * 32;
             const int t = t0 + lane;
+            const bool tv = t < p.ntile && t != seed;
             float lb = CUDART_INF_F;
-            if (t < p.ntile && t != seed) lb = box_lb(boxes + int64_t(t) * CU_SLOT, gmin, gmax);
-            unsigned mask = __ballot_sync(0xffffffffu, lb <= worst);
+            if (tv) lb = box_lb(boxes + int64_t(t) * CU_SLOT, gmin, gmax);
+            unsigned mask = __ballot_sync(0xffffffffu, tv && lb <= worst);
             while (mask) {
                 const int l = __ffs(mask) - 1;
                 mask &= mask - 1;

@@ -75,13 +75,12 @@ class SortedCloud:
         L = _lib.lib()
         B, M, _ = points.shape
         self.B, self.M, self.mode = B, M, mode
-        if lo is None:
-            lo, inv_cell = grid_of(points)
+        if lo is None and not (shared_perm and perm is not None):
+            lo, inv_cell = grid_of(points)      # (a ready ordering needs no grid)
         self.lo, self.inv_cell = lo, inv_cell
         self.shared_perm = bool(shared_perm and B > 1)
         dev = points.device
         pts = points.contiguous()
-        lo_c, ic_c = lo.to(torch.float32).contiguous(), inv_cell.to(torch.float32).contiguous()
         Mp = (M + 63) // 64 * 64
         with torch.cuda.device(dev):
             if self.shared_perm:
@@ -93,6 +92,7 @@ class SortedCloud:
                     raise RuntimeError("SortedCloud: perm must be an int64 tensor of shape [M]")
                 self.perm = perm_c.unsqueeze(0).expand(B, -1)
             else:
+                lo_c, ic_c = lo.to(torch.float32).contiguous(), inv_cell.to(torch.float32).contiguous()
                 keys = torch.empty(B, M, dtype=torch.int64, device=dev)
                 _lib.check(L.fpv_morton_keys(_lib.ptr(pts), B * M, _lib.ptr(lo_c), _lib.ptr(ic_c), _lib.ptr(keys),
                                              _lib.stream_ptr()), "fpv_morton_keys")

@@ -222,3 +222,28 @@ def test_scene_cache_follows_content_not_identity(fpv, cuda_dev):
     s1.add_(1.0)                                                      # in-place change bumps the version: rebuilt
     assert sp.cached_scene(s1) is not c1
     sp.clear_scene_cache()
+
+
+@pytest.mark.parametrize("special", [[np.nan, 0, 0], [np.inf, 0, 0], [-np.inf, 0, 0], [3e38, 3e38, 3e38], [1e20, 0, 0]])
+def test_special_query_does_not_poison_its_group(fpv, cuda_dev, special):
+    """A query without a finite nearest neighbour (NaN / infinite / overflowing coordinates) keeps its group's worst
+    distance at +inf; the tile sweep must still stay inside the table (round-2 fix: lanes past the last super-tile voted
+    INF <= INF and the warp searched tiles that do not exist, handing garbage winners to its finite neighbours)."""
+    sp = importlib.import_module("4dcapture-fpv_b200.spatial")
+    rng = np.random.default_rng(0)
+    for ys in (np.stack([np.zeros(400), np.arange(400) * 0.5, np.zeros(400)], 1).astype(np.float32),
+               (rng.random((400, 3)) * 10).astype(np.float32), (rng.random((5000, 3)) * 10).astype(np.float32)):
+        x = np.zeros((1, 200, 3), np.float32)
+        x[0, :, 0] = np.arange(200) * 0.05
+        x[0, 1] = special
+        scene = sp.cached_scene(torch.tensor(ys, device=cuda_dev).unsqueeze(0))
+        stats = torch.zeros(1, dtype=torch.int64, device=cuda_dev)
+        d, i = sp.culled_search(torch.tensor(x, device=cuda_dev), False, 1, scene, torch.int64, stats=stats)
+        wd, wi = co.nn(x[0], ys)
+        assert int(stats.item()) <= 2 * ((ys.shape[0] + 63) // 64)               # never more tiles than exist (2 groups)
+        assert np.array_equal(d[0].cpu().numpy(), wd, equal_nan=True) and np.array_equal(i[0].cpu().numpy(), wi)
+        got = fpv.distChamfer(torch.tensor(x, device=cuda_dev), torch.tensor(ys, device=cuda_dev),
+                              options=fpv.SearchOptions(engine="spatial"))
+        want = co.dist_chamfer(x, ys)
+        assert np.array_equal(got[3].cpu().numpy(), want[3]) and np.array_equal(got[1].cpu().numpy(), want[1], equal_nan=True)
+        assert np.array_equal(got[2].cpu().numpy(), want[2]) and np.array_equal(got[0].cpu().numpy(), want[0], equal_nan=True)
