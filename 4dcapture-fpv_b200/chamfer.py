@@ -44,12 +44,15 @@ class SearchOptions:
                   "rep"     single-level representative/radius culling over 32-vertex clusters
                   "tc"      tensor-core filter over all vertices (nn_tc.cu)
       carry_seeds start both searches from the previous call's winners (hints; never change a result)
-      body_shared_order  clip=True batches: one Morton order for all frames, computed once and kept in the SearchState"""
+      body_shared_order  clip=True batches: one ordering for all frames, computed once and kept in the SearchState
+      body_order  that ordering: "kd" (balanced k-d partition aligned with the sphere hierarchy, built once on the host:
+                  clusters less than half as wide as along a Morton curve) or "morton" """
     engine: str = "auto"
     b2a_engine: str = "sphere"
     sphere_tile: int = 16
     carry_seeds: bool = True
     body_shared_order: bool = True
+    body_order: str = "kd"
     spatial_min_points: int = 4096
 
     def __post_init__(self):
@@ -57,6 +60,8 @@ class SearchOptions:
             raise RuntimeError(f"SearchOptions: unknown engine {self.engine!r}")
         if self.b2a_engine not in ("sphere", "rep", "tc"):
             raise RuntimeError(f"SearchOptions: unknown b2a_engine {self.b2a_engine!r}")
+        if self.body_order not in ("kd", "morton"):
+            raise RuntimeError(f"SearchOptions: unknown body_order {self.body_order!r}")
         if self.sphere_tile not in (16, 32):
             raise RuntimeError("SearchOptions: sphere_tile must be 16 or 32")
 
@@ -109,7 +114,7 @@ def _body_cloud(a_c: torch.Tensor, scene: spatial.SortedCloud, opts: SearchOptio
     """The body in Morton order with its cluster table.  The curve runs on the BODY's own bounding grid (finer cells
     than the room's, and -- unlike a grid taken from the scene -- identical on every rank of a scene-sharded run, so
     packed keys can be exchanged in sorted order).  clip=True: ONE ordering for every frame, computed on the first call
-    (middle frame) and frozen in the state -- no sort on the per-step path."""
+    (middle frame; a k-d partition by default) and frozen in the state -- no sort on the per-step path."""
     T, N, _ = a_c.shape
     shared = clip and opts.body_shared_order and T > 1
     perm = None
@@ -118,8 +123,12 @@ def _body_cloud(a_c: torch.Tensor, scene: spatial.SortedCloud, opts: SearchOptio
         key = (N, a_c.device.index)
         perm = state.body_perm.get(key)
         if perm is None:
-            lo, inv_cell = spatial.grid_of(a_c[T // 2])
-            perm = state.body_perm[key] = spatial.morton_order(a_c[T // 2], lo, inv_cell)
+            if opts.body_order == "kd":
+                perm = spatial.kd_order(a_c[T // 2], leaf=opts.sphere_tile)        # host-side, once per problem
+            else:
+                lo, inv_cell = spatial.grid_of(a_c[T // 2])
+                perm = spatial.morton_order(a_c[T // 2], lo, inv_cell)
+            state.body_perm[key] = perm
     else:
         lo, inv_cell = spatial.grid_of(a_c)
     return spatial.SortedCloud(a_c, lo, inv_cell, mode=1,

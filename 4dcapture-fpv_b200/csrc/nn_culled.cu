@@ -658,8 +658,12 @@ __device__ __noinline__ void fused_row_accumulate(unsigned long long *accb, bool
     }
 }
 
-template <int TILE, int MINB, bool FUSED>
+// MODE 0: distances + indices out.  MODE 1: fused accumulate in the kernel (FUSED).  MODE 2: only the winners (into the
+// in/out seed buffer, -1 for a query without a finite winner) and the per-warp distance sums; a separate streaming
+// kernel (s2b_accum_kernel) then builds the accumulators from the winners.
+template <int TILE, int MINB, int MODE>
 __global__ void __launch_bounds__(CU_WARPS * 32, MINB) nn_sphere_kernel(const SphereParams p) {
+    constexpr bool FUSED = MODE == 1;
     constexpr int ST = TILE < 32 ? 32 : TILE;
     __shared__ __align__(16) float stile[CU_WARPS][3][ST];  // canonical fallback path only
     __shared__ long long rowsum[FUSED ? CU_WARPS : 1][CU_QPT][3];  // FUSED: fixed-point coordinate sums of the warp's 4 rows
@@ -874,7 +878,19 @@ __global__ void __launch_bounds__(CU_WARPS * 32, MINB) nn_sphere_kernel(const Sp
             traverse(std::true_type{});
         else
             traverse(std::false_type{});
-        if (FUSED) {
+        if (MODE == 2) {
+            double dsum = 0.0;
+#pragma unroll
+            for (int k = 0; k < CU_QPT; ++k) {
+                const int64_t qi = q0 + k * 32 + lane;
+                if (qi < p.N) {
+                    dsum += double(best[k]);
+                    p.seed[int64_t(b) * p.N + qi] = best[k] < CUDART_INF_F ? bidx[k] : -1;
+                }
+            }
+            dsum = warp_sum(dsum);  // fixed shuffle tree: deterministic
+            if (lane == 0) p.sum_partial[int64_t(b) * p.groups + group] = dsum;
+        } else if (FUSED) {
             unsigned long long *accb = p.acc + int64_t(b) * p.M * 4;
             double dsum = 0.0;
 #pragma unroll
@@ -1022,6 +1038,87 @@ __global__ void sphere_expand_kernel(const float *__restrict__ planes, int64_t M
 }
 
 // ---- fused-loss helpers -----------------------------------------------------------------------------------------
+// Accumulators of the fused scene -> body term from the winners (MODE 2): for every batch b and query j with winner
+// w = win[b][j] >= 0:  acc[b][w] += (x_j * 2^k, 1).  A warp walks rows of 32 consecutive queries (coalesced index and
+// point loads; the static query cloud is served by L2 after the first batch), groups the lanes that picked the same
+// winner (match.any), sums every group through the integer warp-reduce unit, and one lane per group touches memory; a
+// row with ONE winner (the far field) costs four atomics and no point loads.  Integer adds: the result does not depend
+// on the order of arrival.
+constexpr int S2B_ROWS = 8;
+
+// rowsum[r][0..2] = sum over the 32 queries of row r of x * 2^k (fixed point): the static part of the fast path
+__global__ void __launch_bounds__(256) s2b_rowsum_kernel(const float *__restrict__ x, int64_t N, float fix_scale,
+                                                         long long *__restrict__ rowsum) {
+    const int lane = threadIdx.x & 31;
+    const int64_t row = int64_t(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row * 32 >= N) return;
+    const int64_t i = row * 32 + lane;
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        const long long v = i < N ? __float2ll_rn(__fmul_rn(__ldg(x + 3 * i + a), fix_scale)) : 0;
+        const int lo = int(v & 0x1FFFFF), mid = int((v >> 21) & 0x1FFFFF), hi = int(v >> 42);
+        const long long slo = __reduce_add_sync(0xffffffffu, lo), smid = __reduce_add_sync(0xffffffffu, mid);
+        const long long shi = __reduce_add_sync(0xffffffffu, hi);
+        if (lane == 0) rowsum[row * 4 + a] = slo + (smid << 21) + (shi << 42);
+    }
+    if (lane == 0) rowsum[row * 4 + 3] = 0;
+}
+
+__global__ void __launch_bounds__(256) s2b_accum_kernel(const float *__restrict__ x, int64_t N, const int *__restrict__ win,
+                                                        int64_t M, float fix_scale, const long long *__restrict__ rowsum,
+                                                        unsigned long long *__restrict__ acc) {
+    const int64_t b = blockIdx.y;
+    const int lane = threadIdx.x & 31;
+    const int64_t row0 = (int64_t(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5)) * (32 * S2B_ROWS);
+    if (row0 >= N) return;
+    unsigned long long *accb = acc + b * M * 4;
+    const int *wb = win + b * N;
+    int w[S2B_ROWS];
+#pragma unroll
+    for (int r = 0; r < S2B_ROWS; ++r) {   // all index loads of the warp's rows in flight before the first is used
+        const int64_t i = row0 + r * 32 + lane;
+        w[r] = i < N ? __ldg(wb + i) : -1;
+    }
+#pragma unroll
+    for (int r = 0; r < S2B_ROWS; ++r) {
+        if (row0 + r * 32 >= N) break;
+        const int64_t i = row0 + r * 32 + lane;
+        const bool valid = w[r] >= 0;
+        const int t = valid ? w[r] : (-1 - lane);  // a lane past the end / without a winner is a group of its own
+        // lanes that picked the same winner, consecutive or not, form one group: one set of atomics per group
+        const unsigned grp = __match_any_sync(0xffffffffu, t);
+        if (grp == 0xffffffffu && valid) {
+            // ONE winner for the whole row (the far field): the row's coordinate sum is static -- four atomics, no point loads
+            if (lane < 4) {
+                const unsigned long long add =
+                    lane < 3 ? static_cast<unsigned long long>(__ldg(rowsum + ((row0 >> 5) + r) * 4 + lane)) : 32ull;
+                atomicAdd(accb + 4 * int64_t(t) + lane, add);
+            }
+            continue;
+        }
+        long long v[3] = {0, 0, 0};
+        if (valid) {
+            v[0] = __float2ll_rn(__fmul_rn(__ldg(x + 3 * i), fix_scale));
+            v[1] = __float2ll_rn(__fmul_rn(__ldg(x + 3 * i + 1), fix_scale));
+            v[2] = __float2ll_rn(__fmul_rn(__ldg(x + 3 * i + 2), fix_scale));
+        }
+        // group sums through the integer warp-reduce unit, three 21-bit limbs per coordinate (exact: <= 32 addends)
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            const int lo = int(v[k] & 0x1FFFFF), mid = int((v[k] >> 21) & 0x1FFFFF), hi = int(v[k] >> 42);
+            const long long slo = __reduce_add_sync(grp, lo), smid = __reduce_add_sync(grp, mid);
+            const long long shi = __reduce_add_sync(grp, hi);
+            v[k] = slo + (smid << 21) + (shi << 42);
+        }
+        if (valid && lane == __ffs(grp) - 1) {
+            atomicAdd(accb + 4 * int64_t(t) + 0, static_cast<unsigned long long>(v[0]));
+            atomicAdd(accb + 4 * int64_t(t) + 1, static_cast<unsigned long long>(v[1]));
+            atomicAdd(accb + 4 * int64_t(t) + 2, static_cast<unsigned long long>(v[2]));
+            atomicAdd(accb + 4 * int64_t(t) + 3, static_cast<unsigned long long>(__popc(grp)));
+        }
+    }
+}
+
 // sum_d[b] = sum over the query groups of the per-warp partial sums, in a fixed order (deterministic)
 __global__ void __launch_bounds__(256) sphere_sum_kernel(const double *__restrict__ partial, int64_t groups,
                                                          float *__restrict__ sum_d) {
@@ -1274,6 +1371,7 @@ int fpv_nn_sphere_table(const float *planes, int64_t batches, int64_t M, int til
 }
 
 static int g_sphere_ctas_per_sm = 512;
+static int g_fused_variant = 2;  // 1: accumulate inside the search kernel; 2: winners only + a separate streaming accumulate
 
 /* Frame chunking of the temporally seeded sphere search: the grid is sized to about ctas_per_sm CTAs per SM
  * (more CTAs = better load balance over the heavy-tailed per-group cost, but every chunk pays one unseeded frame). */
@@ -1341,15 +1439,20 @@ static int sphere_search_impl(const float *queries, int q_shared, int64_t batche
         profile_begin(nm, st, 12.0 * double(q_shared ? N : batches * N) + 12.0 * double(M) * double(batches) + out_bytes,
                       double(batches * N) * double(M));
     }
-    if (fused) {
+    if (fused && g_fused_variant == 1) {
         if (tile == 16)
-            nn_sphere_kernel<16, 8, true><<<grid, CU_WARPS * 32, 0, st>>>(p);
+            nn_sphere_kernel<16, 8, 1><<<grid, CU_WARPS * 32, 0, st>>>(p);
         else
-            nn_sphere_kernel<32, 8, true><<<grid, CU_WARPS * 32, 0, st>>>(p);
+            nn_sphere_kernel<32, 8, 1><<<grid, CU_WARPS * 32, 0, st>>>(p);
+    } else if (fused) {
+        if (tile == 16)
+            nn_sphere_kernel<16, 8, 2><<<grid, CU_WARPS * 32, 0, st>>>(p);
+        else
+            nn_sphere_kernel<32, 8, 2><<<grid, CU_WARPS * 32, 0, st>>>(p);
     } else if (tile == 16) {
-        nn_sphere_kernel<16, 8, false><<<grid, CU_WARPS * 32, 0, st>>>(p);  // 64 registers, 32 resident warps: latency-bound
+        nn_sphere_kernel<16, 8, 0><<<grid, CU_WARPS * 32, 0, st>>>(p);  // 64 registers, 32 resident warps: latency-bound
     } else {
-        nn_sphere_kernel<32, 8, false><<<grid, CU_WARPS * 32, 0, st>>>(p);
+        nn_sphere_kernel<32, 8, 0><<<grid, CU_WARPS * 32, 0, st>>>(p);
     }
     profile_end(st);
     FPV_LAUNCH_CHECK("nn_sphere_kernel");
@@ -1383,7 +1486,8 @@ int fpv_nn_sphere_search(const float *queries, int q_shared, int64_t batches, in
  * finite add +inf / NaN to sum_d and nothing to acc. */
 size_t fpv_nn_sphere_fused_workspace_bytes(int64_t batches, int64_t N) {
     if (batches <= 0 || N <= 0) return 0;
-    return align_up(size_t(batches) * size_t(ceil_div(N, CU_GROUP)) * sizeof(double), 256) + 256;
+    return align_up(size_t(batches) * size_t(ceil_div(N, CU_GROUP)) * sizeof(double), 256) +
+           align_up(size_t(ceil_div(N, 32)) * 4 * sizeof(long long), 256) + 256;
 }
 
 int fpv_fix_shift_for(float max_abs_coordinate, int64_t count) {
@@ -1400,7 +1504,8 @@ int fpv_nn_sphere_fused(const float *queries, int64_t batches, int64_t N, const 
                         int tile, int fix_shift, float *sum_d, unsigned long long *acc,
                         unsigned long long *tiles_searched, void *workspace, size_t workspace_bytes,
                         fpv_stream_t stream) {
-    FPV_CHECK_ARG(queries && planes && table && orig_idx && cand_orig && sum_d && acc, "fpv_nn_sphere_fused: null pointer");
+    FPV_CHECK_ARG(queries && planes && table && orig_idx && cand_orig && sum_d && acc && seed_inout,
+                  "fpv_nn_sphere_fused: null pointer (the in/out seed buffer is required: it carries the winners)");
     FPV_CHECK_ARG(batches > 0 && N > 0 && M > 0 && batches <= 65535, "fpv_nn_sphere_fused: empty input");
     FPV_CHECK_ARG(tile == 16 || tile == 32, "fpv_nn_sphere_fused: tile must be 16 or 32");
     FPV_CHECK_ARG((reinterpret_cast<uintptr_t>(table) & 15) == 0, "fpv_nn_sphere_fused: table must be 16-byte aligned");
@@ -1408,7 +1513,8 @@ int fpv_nn_sphere_fused(const float *queries, int64_t batches, int64_t N, const 
     Arena ar(workspace, workspace_bytes);
     const int64_t groups = ceil_div(N, CU_GROUP);
     double *partial = ar.take<double>(size_t(batches) * size_t(groups));
-    if (!partial) {
+    long long *rowsum = ar.take<long long>(size_t(ceil_div(N, 32)) * 4);
+    if (!partial || !rowsum) {
         set_error("fpv_nn_sphere_fused: workspace too small (%zu bytes, need %zu)", workspace_bytes,
                   fpv_nn_sphere_fused_workspace_bytes(batches, N));
         return FPV_ERR_WORKSPACE;
@@ -1417,8 +1523,29 @@ int fpv_nn_sphere_fused(const float *queries, int64_t batches, int64_t N, const 
     int rc = sphere_search_impl(queries, 1, batches, N, planes, table, orig_idx, cand_orig, seed_inout, seed_valid, M, tile,
                                 0, nullptr, nullptr, 4, tiles_searched, partial, acc, fix_shift, st);
     if (rc) return rc;
+    if (g_fused_variant != 1) {
+        dim3 grid((unsigned)ceil_div(N, 256 * S2B_ROWS), (unsigned)batches);
+        if (profile_on()) {
+            char nm[48];
+            snprintf(nm, sizeof(nm), "s2b_accum Q=%lld M=%lld", (long long)(batches * N), (long long)M);
+            profile_begin(nm, st, 12.0 * double(N) + 4.0 * double(batches * N) + 32.0 * double(batches * M), double(batches * N));
+        }
+        // (the row sums are static per query cloud; recomputing them costs one pass over 12 N bytes, ~2 us per million points)
+        s2b_rowsum_kernel<<<(unsigned)ceil_div(ceil_div(N, 32), 8), 256, 0, st>>>(queries, N, ldexpf(1.0f, fix_shift), rowsum);
+        count_launch();
+        s2b_accum_kernel<<<grid, 256, 0, st>>>(queries, N, seed_inout, M, ldexpf(1.0f, fix_shift), rowsum, acc);
+        profile_end(st);
+        FPV_LAUNCH_CHECK("s2b_accum_kernel");
+    }
     sphere_sum_kernel<<<(unsigned)batches, 256, 0, st>>>(partial, groups, sum_d);
     FPV_LAUNCH_CHECK("sphere_sum_kernel");
+    return FPV_OK;
+}
+
+/* Tuning hook: 1 = accumulate inside the search kernel, 2 (default) = winners only + a separate streaming accumulate. */
+int fpv_nn_sphere_fused_variant(int variant) {
+    FPV_CHECK_ARG(variant == 1 || variant == 2, "fpv_nn_sphere_fused_variant: 1 or 2");
+    g_fused_variant = variant;
     return FPV_OK;
 }
 

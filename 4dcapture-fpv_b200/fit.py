@@ -71,6 +71,18 @@ def _morton_sorted(points: torch.Tensor) -> torch.Tensor:
     return points[torch.argsort(spatial.morton_keys(points, lo, inv_cell), stable=True)].contiguous()
 
 
+def _kd_sorted(points: torch.Tensor) -> torch.Tensor:
+    """[M,3] CPU cloud re-ordered as a left-balanced k-d partition: every aligned block of 64 * 2^k points is a cell."""
+    from . import spatial
+    out = points[spatial.kd_order(points, leaf=64, align="pow2")]
+    # inside a 64-point cell: along the Morton curve, so that the 32 consecutive points a warp row holds are neighbours
+    # (neighbours share their nearest body vertex: fewer groups per row in the accumulate pass)
+    lo, inv_cell = spatial.grid_of(out)
+    fine = spatial.morton_keys(out, lo, inv_cell)
+    cell = torch.arange(out.shape[0]) // 64
+    return out[torch.argsort(cell * (1 << 30) + fine, stable=True)].contiguous()
+
+
 def leg_vertex_ids(constants: Dict[str, torch.Tensor]):
     """Synthetic stand-ins for body_segments/L_Leg.json and R_Leg.json (:401-409): (left ids, right ids)."""
     dom = constants["lbs_weights"].argmax(dim=1)
@@ -87,7 +99,8 @@ class FitProblem:
     def __init__(self, T: int, M: int, device, seed: int = 1234, scene_kind: str = "uniform",
                  rank: int = 0, world_size: int = 1, group=None, idx_dtype=torch.int64, presort_scene: bool = True,
                  front_end: bool = False, dct_frames: int = DCT_FRAMES, mode: str = "global", fused: bool = True,
-                 comm: str = "p2p", options: Optional[chamfer.SearchOptions] = None, clips: int = 1):
+                 comm: str = "p2p", options: Optional[chamfer.SearchOptions] = None, clips: int = 1,
+                 scene_order: str = "morton"):
         """clips > 1: T is the TOTAL number of frames of `clips` independent clips of T/clips frames batched into one
         step (BASELINE.json configs[4]); the temporal residuals never couple frames of different clips.
         fused: scene -> body reduced inside the search kernel (chamfer.scene_to_body_sum) instead of materialising
@@ -145,13 +158,15 @@ class FitProblem:
             # body->scene search and unbalances the scene->body search: 58 vs 30 ms/step at 2 GPUs).  Each shard is
             # then ordered on its own grid, which is the order spatial.cached_scene would sort it into (its
             # permutation becomes the identity and the per-step gathers that undo it disappear).
-            whole = _morton_sorted(self.host_scene)
+            order = _kd_sorted if scene_order == "kd" else _morton_sorted
+            whole = order(self.host_scene)
             if world_size > 1:
                 nblk = (M + SHARD_BLOCK - 1) // SHARD_BLOCK
                 blocks = torch.arange(M).split(SHARD_BLOCK)
                 whole = whole[torch.cat([blocks[i] for r in range(world_size) for i in range(r, nblk, world_size)])]
             parts = [whole[slice(*sharded.shard_range(M, world_size, r))] for r in range(world_size)]
-            self.host_scene = torch.cat([_morton_sorted(p) for p in parts]).contiguous()
+            self.host_scene = torch.cat([order(p) for p in parts]).contiguous()
+        self.scene_presorted = bool(presort_scene and mode == "global" and scene_order == "kd")
         self.comm = None
         if world_size > 1 and comm == "p2p" and self.device.type == "cuda":
             nfloats = self.host_params.numel() + 1 + 16 * T + 64 + (self.host_c_dct.numel() if self.dct_batches else 0)
@@ -179,6 +194,9 @@ class FitProblem:
         self.camera_ext = self.host_camera_ext.to(dev, non_blocking=non_blocking).requires_grad_(True)
         if self.mode == "global":
             self.scene = self.host_scene[self.begin:self.end].to(dev, non_blocking=non_blocking).unsqueeze(0)
+            if self.scene_presorted and dev.type == "cuda":
+                from . import spatial
+                spatial.cached_scene(self.scene, presorted=True)     # index it in the order it arrives in
         self.contact_weight = self.host_contact_weight.to(dev, non_blocking=non_blocking)
         if self.front_end and self.dct_batches:
             if dev.type == "cuda" and not self.host_c_dct.is_pinned():

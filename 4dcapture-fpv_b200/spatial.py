@@ -59,23 +59,72 @@ def morton_order(points: torch.Tensor, lo: torch.Tensor, inv_cell: torch.Tensor)
     return torch.argsort(keys)
 
 
+def kd_order(points: torch.Tensor, leaf: int = 16, align: str = "pow4") -> torch.Tensor:
+    """[M,3] -> int64 [M] ordering (sorted position -> original index) of a k-d partition: the cloud is split
+    recursively along its longest axis, with every split placed on a block boundary so that aligned blocks of
+    consecutive positions are k-d cells -- compact in all three axes, where a Morton curve jumps.
+      align="pow4": splits near the median on multiples of the largest leaf * 4^k that fits: the blocks of leaf, 4 leaf,
+                    16 leaf, 64 leaf positions (the clusters and upper levels of nn_sphere_kernel's hierarchy) are cells;
+      align="pow2": left-balanced tree (left part = the largest leaf * 2^k below the size): EVERY aligned block of
+                    leaf * 2^k positions is a cell (tiles of 64, query groups of 128, super-tiles of 2048 of the scene).
+    Host-side (numpy), deterministic, run once per cloud; non-finite points go last."""
+    import numpy as np
+    pts = points.detach().to("cpu", torch.float64).numpy()
+    M = pts.shape[0]
+    finite = np.isfinite(pts).all(axis=1)
+    order = np.concatenate([np.nonzero(finite)[0], np.nonzero(~finite)[0]])
+    nf = int(finite.sum())
+    out = order.copy()
+
+    def split(lo: int, hi: int):
+        n = hi - lo
+        if n <= leaf:
+            return
+        blk = leaf
+        if align == "pow2":
+            while blk * 2 < n:
+                blk *= 2
+            left = blk
+        else:
+            while blk * 4 * 2 <= n:
+                blk *= 4
+            left = max(blk, int(round(n / 2.0 / blk)) * blk)
+        if left >= n:
+            left = n - 1 if n - 1 > 0 else 1
+        idx = out[lo:hi]
+        p = pts[idx]
+        axis = int(np.argmax(p.max(axis=0) - p.min(axis=0)))
+        part = np.argpartition(p[:, axis], left - 1) if left < n else np.arange(n)
+        # argpartition leaves both halves unordered; a stable secondary order keeps the result deterministic
+        lpart = np.sort(part[:left])
+        rpart = np.sort(part[left:])
+        out[lo:hi] = np.concatenate([idx[lpart], idx[rpart]])
+        split(lo, lo + left)
+        split(lo + left, hi)
+
+    if nf > 1:
+        split(0, nf)
+    return torch.from_numpy(out.astype(np.int64)).to(points.device)
+
+
 class SortedCloud:
     """[B,M,3] cloud sorted per batch along the Morton curve + everything nn_culled_kernel needs."""
 
     def __init__(self, points: torch.Tensor, lo: torch.Tensor = None, inv_cell: torch.Tensor = None, mode: int = 0,
                  sphere_tile: int = 0, check_identity: bool = False, shared_perm: bool = False,
-                 perm: torch.Tensor = None, tables: bool = True):
+                 perm: torch.Tensor = None, tables: bool = True, presorted: bool = False):
         """mode 0: 64-point tiles with bounding boxes; mode 1: 32-point tiles with representative + radius.
         sphere_tile (16 | 32): build the four-level bounding-sphere table of nn_sphere_kernel instead.
         perm (with shared_perm): a ready ordering [M] int64 (sorted position -> original index) -- no sort is run.
-        tables=False: only the sorted points are needed (the cloud serves as QUERIES), skip the cluster tables."""
+        tables=False: only the sorted points are needed (the cloud serves as QUERIES), skip the cluster tables.
+        presorted: the cloud already arrives in a spatial order of the caller's choice (e.g. kd_order): keep it."""
         if points.dim() == 2:
             points = points.unsqueeze(0)
         _lib.require_cuda(points)
         L = _lib.lib()
         B, M, _ = points.shape
         self.B, self.M, self.mode = B, M, mode
-        if lo is None and not (shared_perm and perm is not None):
+        if lo is None and not (shared_perm and perm is not None) and not presorted:
             lo, inv_cell = grid_of(points)      # (a ready ordering needs no grid)
         self.lo, self.inv_cell = lo, inv_cell
         self.shared_perm = bool(shared_perm and B > 1)
@@ -83,7 +132,9 @@ class SortedCloud:
         pts = points.contiguous()
         Mp = (M + 63) // 64 * 64
         with torch.cuda.device(dev):
-            if self.shared_perm:
+            if presorted:
+                self.perm = perm_c = torch.arange(M, device=dev).unsqueeze(0).expand(B, -1).contiguous()
+            elif self.shared_perm:
                 # One ordering for every batch entry, taken from the middle one: the batch is a clip of ONE articulated
                 # surface, so points that are neighbours in one frame stay neighbours in all of them.  The order only
                 # shapes the clusters (their spheres are rebuilt from the actual points of each frame), never the result.
@@ -99,7 +150,8 @@ class SortedCloud:
                 self.perm = perm_c = torch.argsort(keys, dim=1, stable=(B == 1))
             # a cloud that already arrives in Morton order (FitProblem pre-sorts its scene once) needs no gather on the
             # way in and no un-permute of the results on the way out; checked once per cached cloud, never per step
-            self.identity = bool(check_identity and B == 1 and torch.equal(self.perm[0], torch.arange(M, device=dev)))
+            self.identity = bool(presorted or (check_identity and B == 1 and
+                                               torch.equal(self.perm[0], torch.arange(M, device=dev))))
             # sorted points, padded SoA planes and the original-index table in one pass
             self.sorted = torch.empty_like(pts)
             self.planes = torch.empty(L.fpv_nn_planes_bytes(B, M) // 4, dtype=torch.float32, device=dev)
@@ -259,8 +311,10 @@ def _checksum(src: torch.Tensor) -> tuple:
     return tuple(torch.stack([bits.sum(), (bits * w).sum()]).tolist())
 
 
-def cached_scene(scene: torch.Tensor) -> SortedCloud:
-    """Sorted form of a static cloud [1,M,3], rebuilt only when its CONTENT changes.
+def cached_scene(scene: torch.Tensor, presorted: bool = False) -> SortedCloud:
+    """Sorted form of a static cloud [1,M,3], rebuilt only when its CONTENT changes.  presorted=True (first call for
+    this scene): the caller has already put the cloud in a spatial order (fit.FitProblem sorts it once on the host);
+    it is indexed as it is, with no permutation to undo afterwards.
 
     Fast path: (data_ptr, version, shape) of a tensor we hold a strong reference to (its memory cannot be recycled
     while cached) -- no device work, capture-safe; this is the reference's situation, one scene tensor alive for the
@@ -285,7 +339,7 @@ def cached_scene(scene: torch.Tensor) -> SortedCloud:
                 return sc
     else:
         h = None
-    sc = SortedCloud(src, check_identity=True)
+    sc = SortedCloud(src, check_identity=True, presorted=presorted)
     _scene_cache[key] = (src, sc, h)
     _trim_scene_cache()
     return sc

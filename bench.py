@@ -221,7 +221,7 @@ def run_b200(args):
     idx_dtype = torch.int64 if args.idx64 else torch.int32
     prob = pkg.FitProblem(T=args.T, M=args.M, device=dev, seed=1235, rank=rank, world_size=world, idx_dtype=idx_dtype,
                           front_end=not args.no_front_end, scene_kind=args.scene, fused=not args.no_fused,
-                          comm=args.comm, clips=args.clips)
+                          comm=args.comm, clips=args.clips, scene_order=args.scene_order)
 
     def barrier():
         if world > 1:
@@ -363,7 +363,8 @@ def run_b200(args):
                                     else "materialised [T,M] distances + indices",
                    "exchange": ("peer-memory mailbox (keys pushed from the search epilogue, flag barrier)" if prob.comm is not None
                                 else "NCCL all_reduce") if world > 1 else "none",
-                   "scene_order": "Morton-sorted once on the host" + (", dealt to ranks in blocks of 2048" if world > 1 else ""),
+                   "scene_order": ("k-d partitioned" if args.scene_order == "kd" else "Morton-sorted") + " once on the host" +
+                                  (", dealt to ranks in blocks of 2048" if world > 1 else ""),
                    "search": "body->scene: Morton-tiled box-culled exact search; scene->body: per-query bounding-sphere hierarchy over "
                              "the body in a frozen Morton order; both seeded with the previous step's winners (hints; results exact)",
                    "l2": "per-step working set (seed buffer + tables > 1.2 GB) exceeds the 126 MB L2; no explicit flush"},
@@ -418,6 +419,8 @@ def main():
     ap.add_argument("--no-fused", action="store_true", help="materialise the [T,M] scene->body outputs instead of the fused sum")
     ap.add_argument("--comm", default="p2p", choices=["p2p", "nccl"], help="transport of the sharded key / gradient exchange")
     ap.add_argument("--no-local", action="store_true", help="skip the cal_loss2 (mode 'local') leg")
+    ap.add_argument("--scene-order", default="kd", choices=["kd", "morton"],
+                    help="one-time host-side ordering of the scene: left-balanced k-d partition (default) or Morton curve")
     ap.add_argument("--no-front-end", action="store_true",
                     help="optimise the axis-angle row directly (skip the 6D codec, VPoser decode and DCT prior)")
     args = ap.parse_args()
