@@ -213,6 +213,8 @@ def run_b200(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"       # keep stdout to the ONE JSON line (NCCL prints its banner there)
         dist.init_process_group("nccl", device_id=dev)
     pkg = load_pkg()
     L = pkg._lib.lib()

@@ -1,5 +1,6 @@
-"""GPU, >= 2 devices, NCCL: the scene-sharded chamfer and the sharded fit step vs the single-GPU path.
-Skipped on a 1-GPU box (the world_size-2 host logic is covered on CPU by tests/test_sharded_gloo.py)."""
+"""GPU, >= 2 devices, one rank per GPU: the scene-sharded chamfer over NCCL and the sharded fit step (peer-memory
+mailbox over NVLink) vs the single-GPU path.  Skipped on a 1-GPU box, where tests/test_p2p_gpu.py runs the same
+multi-rank path with two ranks on one device and tests/test_sharded_gloo.py covers the host logic on CPU."""
 import os
 import sys
 import tempfile
@@ -36,8 +37,7 @@ def _worker(rank, world, init_file, out_dir):
     loss.backward()
     fpv.allreduce_grads([a])
     prob = fpv.FitProblem(T=4, M=30_000, device=dev, seed=1236, rank=rank, world_size=world)
-    fl = prob.step().clone()
-    dist.all_reduce(fl)
+    fl = prob.step().clone()                                      # already the GLOBAL loss (summed in the gradient exchange)
     fit_grad, fit_scale = prob.params.grad.clone(), prob.scale.grad.clone()
     np.savez(os.path.join(out_dir, f"r{rank}.npz"), d_a2b=d_a2b.detach().cpu().numpy(), i_a2b=i_a2b.cpu().numpy(),
              d_b2a=d_b2a.detach().cpu().numpy(), i_b2a=i_b2a.cpu().numpy(), grad=a.grad.cpu().numpy(),
