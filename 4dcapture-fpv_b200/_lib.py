@@ -68,8 +68,9 @@ SIGNATURES = {
                                           c_void_p, c_void_p, c_int, c_void_p]),
     "fpv_nn_sphere_fused_workspace_bytes": (c_size_t, [c_int64, c_int64]),
     "fpv_fix_shift_for": (c_int, [c_float, c_int64]),
-    "fpv_nn_sphere_fused": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int,
-                                    c_int64, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "fpv_nn_sphere_fused": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p,
+                                    c_int, c_int64, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t,
+                                    c_void_p]),
     "fpv_nn_sphere_fused_variant": (c_int, [c_int]),
     "fpv_scene2body_grad": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int64, c_int64, c_void_p, c_int, c_void_p]),
     "fpv_adam_tick": (c_int, [c_void_p, c_void_p]),
@@ -89,8 +90,9 @@ SIGNATURES = {
     "fpv_nn_gather_pack": (c_int, [c_void_p, c_void_p, c_int, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_void_p]),
     "fpv_nn_sphere_table_floats": (c_size_t, [c_int64, c_int]),
     "fpv_nn_sphere_table": (c_int, [c_void_p, c_int64, c_int64, c_int, c_void_p, c_void_p]),
-    "fpv_nn_sphere_search": (c_int, [c_void_p, c_int, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
-                                     c_int, c_int64, c_int, c_int64, c_void_p, c_void_p, c_int, c_void_p, c_void_p]),
+    "fpv_nn_sphere_search": (c_int, [c_void_p, c_int, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_int,
+                                     c_void_p, c_int, c_int64, c_int, c_int64, c_void_p, c_void_p, c_int, c_void_p,
+                                     c_void_p]),
     "fpv_chamfer_fwd_workspace_bytes": (c_size_t, [c_int64, c_int64, c_int64, c_int]),
     "fpv_chamfer_fwd": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int, c_void_p, c_void_p,
                                 c_void_p, c_void_p, c_int, c_void_p, c_size_t, c_void_p]),

@@ -131,9 +131,16 @@ def _body_cloud(a_c: torch.Tensor, scene: spatial.SortedCloud, opts: SearchOptio
             state.body_perm[key] = perm
     else:
         lo, inv_cell = spatial.grid_of(a_c)
-    return spatial.SortedCloud(a_c, lo, inv_cell, mode=1,
-                               sphere_tile=opts.sphere_tile if (spheres and opts.b2a_engine == "sphere") else 0,
-                               shared_perm=shared, perm=perm, tables=spheres)
+    cloud = spatial.SortedCloud(a_c, lo, inv_cell, mode=1,
+                                sphere_tile=opts.sphere_tile if (spheres and opts.b2a_engine == "sphere") else 0,
+                                shared_perm=shared, perm=perm, tables=spheres)
+    if shared:      # the inverse table of a frozen ordering is frozen too
+        pkey = ("pos", N, a_c.device.index)
+        if pkey in state.body_perm:
+            cloud._pos = state.body_perm[pkey]
+        else:
+            state.body_perm[pkey] = cloud.pos_table()[0]
+    return cloud
 
 
 def _search_a2b(a_c, b_c, scene, body, idx_dtype, idx_base, opts, state):
@@ -163,7 +170,7 @@ def _search_b2a(a_c, scene, body, idx_dtype, opts, state):
         # winners of the previous call on this scene (an optimiser loop calls with a slowly moving body): every
         # (frame, scene point) starts from the exact distance to that vertex.  A hint only.
         seed, seed_valid = state.seed_buffer("b2a", T, M, dev, opts.carry_seeds)
-        d_s2, i_s2 = spatial.sphere_search(scene.sorted, True, T, body, cand_orig=a_c, idx_dtype=idx_dtype, stats=stats2,
+        d_s2, i_s2 = spatial.sphere_search(scene.sorted, True, T, body, idx_dtype=idx_dtype, stats=stats2,
                                            seed=seed, seed_valid=seed_valid)
         state.stats["tiles_searched_b2a"] = stats2
     elif opts.b2a_engine == "rep":
@@ -485,8 +492,9 @@ class _FusedTermsFn(torch.autograd.Function):
         fix_shift = scene.fix_shift()
         with torch.cuda.device(dev):
             ws = _lib.workspace(L.fpv_nn_sphere_fused_workspace_bytes(T, M), dev)
+            pos, pos_shared = body.pos_table()
             _lib.check(L.fpv_nn_sphere_fused(_lib.ptr(scene.sorted), T, M, _lib.ptr(body.planes), _lib.ptr(body.boxes),
-                                             _lib.ptr(body.oidx), _lib.ptr(a_c), _lib.ptr(seed), int(seed_valid), N,
+                                             _lib.ptr(body.oidx), _lib.ptr(pos), int(pos_shared), _lib.ptr(seed), int(seed_valid), N,
                                              body.sphere_tile, fix_shift, _lib.ptr(sum_d), _lib.ptr(acc), _lib.ptr(stats),
                                              _lib.ptr(ws), ws.numel(), _lib.stream_ptr()), "fpv_nn_sphere_fused")
         state.stats["tiles_searched_b2a"] = stats

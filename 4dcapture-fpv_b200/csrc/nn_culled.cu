@@ -508,7 +508,8 @@ struct SphereParams {
                             // stride in float4
     const int *oidx;
     int64_t oidx_bstride;
-    const float *cand_orig;  // [cand batches][M][3] candidates in ORIGINAL order (temporal seeding), may be null
+    const int *pos_of;       // [cand batches or 1][M] sorted position of every ORIGINAL candidate index (seeding), may be null
+    int64_t pos_bstride;     //   0 when one ordering serves every batch
     int *seed;               // [batches][N] in/out: last call's winners (original indices; < 0 = none), may be null
     int seed_read;           // 0: the buffer holds nothing yet, only write it
     int n0, n1, n2, n3;
@@ -534,16 +535,16 @@ __device__ __forceinline__ bool sphere_needed(const float4 e, const float lim, c
                                               const float2 (&a2)[2]) {
     const float2 mx = make_float2(e.x, e.x), my = make_float2(e.y, e.y), mz = make_float2(e.z, e.z);
     const float2 mr = make_float2(e.w, e.w);
-    bool need = false;
+    float2 t[2];
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
-        float2 t = __ffma2_rn(qx2[h], mx, a2[h]);
-        t = __ffma2_rn(qy2[h], my, t);
-        t = __ffma2_rn(qz2[h], mz, t);
-        t = __ffma2_rn(sq2[h], mr, t);
-        need |= (t.x <= lim) | (t.y <= lim);  // NaN (NaN / infinite query) never asks
+        t[h] = __ffma2_rn(qx2[h], mx, a2[h]);
+        t[h] = __ffma2_rn(qy2[h], my, t[h]);
+        t[h] = __ffma2_rn(qz2[h], mz, t[h]);
+        t[h] = __ffma2_rn(sq2[h], mr, t[h]);
     }
-    return need;
+    // one comparison for the four queries: min drops NaNs (a NaN / infinite query never asks; a query next to it still does)
+    return fminf(fmin3(t[0].x, t[0].y, t[1].x), t[1].y) <= lim;
 }
 
 // Search one cluster, read as expanded groups (-2y, |y|^2) straight from L1, for the warp's 128 queries; returns true when a query of this lane
@@ -552,9 +553,14 @@ template <int TILE>
 __device__ __forceinline__ bool sphere_search_tile(const float4 *__restrict__ xp_tile, const SphereParams &p, int b, int j0,
                                                    const float (&qx)[CU_QPT],
                                                    const float (&qy)[CU_QPT], const float (&qz)[CU_QPT],
-                                                   const float (&thr)[CU_QPT], float (&best)[CU_QPT],
-                                                   int (&bidx)[CU_QPT]) {
+                                                   const float (&thr)[CU_QPT], const int (&sgrp)[CU_QPT],
+                                                   float (&best)[CU_QPT], int (&bidx)[CU_QPT]) {
     bool improved = false;
+    // a query's SEED group (the four sorted candidates around its seed winner) was evaluated canonically when the seed
+    // was taken, so its filter hits there -- the seed winner always passes its own threshold -- carry no news: masked
+    int rel[CU_QPT];
+#pragma unroll
+    for (int q = 0; q < CU_QPT; ++q) rel[q] = sgrp[q] - (j0 >> 2);
 #pragma unroll
     for (int j4 = 0; j4 < TILE / 4; ++j4) {
         // warp-uniform addresses: every load is one broadcast request served by L1
@@ -574,7 +580,7 @@ __device__ __forceinline__ bool sphere_search_tile(const float4 *__restrict__ xp
             s1 = __ffma2_rn(by, my1, s1);
             s0 = __ffma2_rn(bz, mz0, s0);
             s1 = __ffma2_rn(bz, mz1, s1);
-            hit[q] = fminf(fmin3(s0.x, s0.y, s1.x), s1.y) <= thr[q];
+            hit[q] = (fminf(fmin3(s0.x, s0.y, s1.x), s1.y) <= thr[q]) && rel[q] != j4;
             any |= hit[q];
         }
         if (any) {  // rare: canonical re-evaluation of the four candidates, lexicographic update
@@ -716,7 +722,36 @@ __global__ void __launch_bounds__(CU_WARPS * 32, MINB) nn_sphere_kernel(const Sp
         const float4 *tab = p.table + int64_t(b) * p.table_bstride;
         const int *oidx = p.oidx + int64_t(b) * p.oidx_bstride;
         // seed, in order of preference: the winner of the previous CALL for this (frame, query) (an optimiser moves the
-        // body by millimetres per step), the winner of the previous FRAME of this call, a coarse pass over the frame
+        // body by millimetres per step), the winner of the previous FRAME of this call, a coarse pass over the frame.
+        // A seed is taken together with the three sorted candidates that share its group of four: all four are evaluated
+        // canonically here, and the traversal then ignores the query's filter hits in that group (sgrp).
+        int sgrp[CU_QPT] = {-1, -1, -1, -1};
+        auto seed_from = [&](const int (&sd)[CU_QPT]) {
+            const int *pos = p.pos_of + int64_t(b) * p.pos_bstride;
+            const float4 *px4 = reinterpret_cast<const float4 *>(planes);
+            const float4 *py4 = reinterpret_cast<const float4 *>(planes + p.Mp);
+            const float4 *pz4 = reinterpret_cast<const float4 *>(planes + 2 * p.Mp);
+            const int4 *o4 = reinterpret_cast<const int4 *>(oidx);
+#pragma unroll
+            for (int k = 0; k < CU_QPT; ++k) {
+                const int g = __ldg(pos + sd[k]) >> 2;
+                const float4 cx = __ldg(px4 + g), cy = __ldg(py4 + g), cz = __ldg(pz4 + g);
+                const int4 co = __ldg(o4 + g);
+                const float ex[4] = {cx.x, cx.y, cx.z, cx.w}, ey[4] = {cy.x, cy.y, cy.z, cy.w}, ez[4] = {cz.x, cz.y, cz.z, cz.w};
+                const int eo[4] = {co.x, co.y, co.z, co.w};
+                best[k] = CUDART_INF_F;
+                bidx[k] = 0;
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    const float e = cu_d2(qx[k], qy[k], qz[k], ex[c], ey[c], ez[c]);
+                    if (e <= best[k] && (e < best[k] || eo[c] < bidx[k])) {  // (+inf padding / NaN never win)
+                        best[k] = e;
+                        bidx[k] = eo[c];
+                    }
+                }
+                sgrp[k] = g;
+            }
+        };
         bool seeded = false;
         if (p.seed_read) {
             int sd[CU_QPT];
@@ -729,38 +764,16 @@ __global__ void __launch_bounds__(CU_WARPS * 32, MINB) nn_sphere_kernel(const Sp
                 ok &= unsigned(sd[k]) < unsigned(p.M);
             }
             seeded = __all_sync(0xffffffffu, ok);
-            if (seeded) {
-                const float *co = p.cand_orig + int64_t(b) * p.M * 3;
-#pragma unroll
-                for (int k = 0; k < CU_QPT; ++k) {
-                    const float *y = co + 3 * int64_t(sd[k]);
-                    best[k] = cu_d2(qx[k], qy[k], qz[k], __ldg(y), __ldg(y + 1), __ldg(y + 2));
-                    bidx[k] = sd[k];
-                    if (!(best[k] < CUDART_INF_F)) {
-                        best[k] = CUDART_INF_F;
-                        bidx[k] = 0;
-                    }
-                }
-            }
+            if (seeded) seed_from(sd);
         }
-        const bool temporal = (b > b0) && p.q_bstride == 0 && p.cand_orig != nullptr;
+        const bool temporal = (b > b0) && p.q_bstride == 0 && p.pos_of != nullptr;
         if (seeded) {
         } else if (temporal) {
-            // seed: exact distance to the previous frame's winner, re-evaluated on this frame's vertices
-            const float *co = p.cand_orig + int64_t(b) * p.M * 3;
+            // seed: the previous frame's winner (and its group), re-evaluated on this frame's vertices
+            int sd[CU_QPT];
 #pragma unroll
-            for (int k = 0; k < CU_QPT; ++k) {
-                if (best[k] < CUDART_INF_F) {
-                    const float *y = co + 3 * int64_t(bidx[k]);
-                    best[k] = cu_d2(qx[k], qy[k], qz[k], __ldg(y), __ldg(y + 1), __ldg(y + 2));
-                    if (!(best[k] < CUDART_INF_F)) {
-                        best[k] = CUDART_INF_F;
-                        bidx[k] = 0;
-                    }
-                } else {
-                    bidx[k] = 0;
-                }
-            }
+            for (int k = 0; k < CU_QPT; ++k) sd[k] = (best[k] < CUDART_INF_F) ? bidx[k] : 0;
+            seed_from(sd);
         } else {
             // seed: the first point of every level-2 group (real candidates)
 #pragma unroll
@@ -825,7 +838,7 @@ __global__ void __launch_bounds__(CU_WARPS * 32, MINB) nn_sphere_kernel(const Sp
                 for (int i = 0; i < 4; ++i) {
                     // canonical mode asks for everything that is not padding (lim != NaN)
                     const bool need = CANON ? (lim[i] == lim[i]) : sphere_needed(e[i], lim[i], qx2, qy2, qz2, sq2, a2);
-                    mine |= unsigned(need) << i;
+                    if (need) mine |= 1u << i;
                 }
                 return __reduce_or_sync(0xffffffffu, mine);   // one warp-wide OR instead of four votes
             };
@@ -853,7 +866,7 @@ __global__ void __launch_bounds__(CU_WARPS * 32, MINB) nn_sphere_kernel(const Sp
                                 float thr[CU_QPT];
 #pragma unroll
                                 for (int k = 0; k < CU_QPT; ++k) thr[k] = thrb[k] + cr2s;
-                                if (sphere_search_tile<TILE>(xp + j0, p, b, j0, qx, qy, qz, thr, best, bidx))
+                                if (sphere_search_tile<TILE>(xp + j0, p, b, j0, qx, qy, qz, thr, sgrp, best, bidx))
                                     refresh();
                             } else {
                                 __syncwarp();
@@ -1382,7 +1395,8 @@ int fpv_nn_sphere_set_chunking(int ctas_per_sm) {
 }
 
 static int sphere_search_impl(const float *queries, int q_shared, int64_t batches, int64_t N, const float *planes,
-                              const float *table, const int32_t *orig_idx, const float *cand_orig, int32_t *seed_inout,
+                              const float *table, const int32_t *orig_idx, const int32_t *pos_of, int pos_shared,
+                              int32_t *seed_inout,
                               int seed_valid, int64_t M, int tile, int64_t idx_base, float *dist, void *idx, int idx_bytes,
                               unsigned long long *tiles_searched, double *sum_partial, unsigned long long *acc,
                               int fix_shift, cudaStream_t st) {
@@ -1404,7 +1418,8 @@ static int sphere_search_impl(const float *queries, int q_shared, int64_t batche
     p.table_bstride = L.float4s(tile);
     p.oidx = orig_idx;
     p.oidx_bstride = p.Mp;
-    p.cand_orig = cand_orig;
+    p.pos_of = pos_of;
+    p.pos_bstride = pos_shared ? 0 : M;
     p.seed = seed_inout;
     p.seed_read = (seed_inout && seed_valid) ? 1 : 0;
     p.batches = int(batches);
@@ -1419,7 +1434,7 @@ static int sphere_search_impl(const float *queries, int q_shared, int64_t batche
     p.fix_scale = ldexpf(1.0f, fix_shift);
     const int64_t ctas_x = ceil_div(ceil_div(N, CU_GROUP), CU_WARPS);
     int64_t nchunks = batches;
-    if (q_shared && cand_orig) {  // walk frames inside the warp, but keep >= ~2 resident waves of CTAs
+    if (q_shared && pos_of) {  // walk frames inside the warp, but keep >= ~2 resident waves of CTAs
         // with per-call seeds every frame starts seeded: frames need not share a CTA, so the grid can be much finer
         nchunks = ceil_div(int64_t(sm_count()) * g_sphere_ctas_per_sm * (p.seed_read ? 4 : 1), ctas_x);
         if (nchunks < 1) nchunks = 1;
@@ -1459,19 +1474,20 @@ static int sphere_search_impl(const float *queries, int q_shared, int64_t batche
     return FPV_OK;
 }
 
-/* Exact NN through the sphere hierarchy.  cand_orig (optional): the candidates in ORIGINAL order
- * [cand_batches][M][3]; with a shared query set it enables temporal seeding across consecutive batches (frames). */
+/* Exact NN through the sphere hierarchy.  pos_of (optional): the sorted position of every ORIGINAL candidate index
+ * ([M] when pos_shared, else [batches][M]); it turns winners (original indices) back into table positions, which
+ * enables seeding -- across consecutive batches (frames) of a shared query set, and from call to call (seed_inout). */
 int fpv_nn_sphere_search(const float *queries, int q_shared, int64_t batches, int64_t N, const float *planes,
-                         const float *table, const int32_t *orig_idx, const float *cand_orig, int32_t *seed_inout,
-                         int seed_valid, int64_t M, int tile, int64_t idx_base, float *dist, void *idx, int idx_bytes,
-                         unsigned long long *tiles_searched, fpv_stream_t stream) {
+                         const float *table, const int32_t *orig_idx, const int32_t *pos_of, int pos_shared,
+                         int32_t *seed_inout, int seed_valid, int64_t M, int tile, int64_t idx_base, float *dist,
+                         void *idx, int idx_bytes, unsigned long long *tiles_searched, fpv_stream_t stream) {
     FPV_CHECK_ARG(queries && planes && table && orig_idx && dist && idx, "fpv_nn_sphere_search: null pointer");
-    FPV_CHECK_ARG(!seed_inout || cand_orig, "fpv_nn_sphere_search: seed_inout needs cand_orig");
+    FPV_CHECK_ARG(!seed_inout || pos_of, "fpv_nn_sphere_search: seed_inout needs pos_of");
     FPV_CHECK_ARG(batches > 0 && N > 0 && M > 0 && batches <= 65535, "fpv_nn_sphere_search: empty input");
     FPV_CHECK_ARG(idx_bytes == 4 || idx_bytes == 8, "fpv_nn_sphere_search: idx_bytes must be 4 or 8");
     FPV_CHECK_ARG(tile == 16 || tile == 32, "fpv_nn_sphere_search: tile must be 16 or 32");
     FPV_CHECK_ARG((reinterpret_cast<uintptr_t>(table) & 15) == 0, "fpv_nn_sphere_search: table must be 16-byte aligned");
-    return sphere_search_impl(queries, q_shared, batches, N, planes, table, orig_idx, cand_orig, seed_inout, seed_valid, M,
+    return sphere_search_impl(queries, q_shared, batches, N, planes, table, orig_idx, pos_of, pos_shared, seed_inout, seed_valid, M,
                               tile, idx_base, dist, idx, idx_bytes, tiles_searched, nullptr, nullptr, 0,
                               static_cast<cudaStream_t>(stream));
 }
@@ -1500,11 +1516,11 @@ int fpv_fix_shift_for(float max_abs_coordinate, int64_t count) {
 }
 
 int fpv_nn_sphere_fused(const float *queries, int64_t batches, int64_t N, const float *planes, const float *table,
-                        const int32_t *orig_idx, const float *cand_orig, int32_t *seed_inout, int seed_valid, int64_t M,
+                        const int32_t *orig_idx, const int32_t *pos_of, int pos_shared, int32_t *seed_inout, int seed_valid, int64_t M,
                         int tile, int fix_shift, float *sum_d, unsigned long long *acc,
                         unsigned long long *tiles_searched, void *workspace, size_t workspace_bytes,
                         fpv_stream_t stream) {
-    FPV_CHECK_ARG(queries && planes && table && orig_idx && cand_orig && sum_d && acc && seed_inout,
+    FPV_CHECK_ARG(queries && planes && table && orig_idx && pos_of && sum_d && acc && seed_inout,
                   "fpv_nn_sphere_fused: null pointer (the in/out seed buffer is required: it carries the winners)");
     FPV_CHECK_ARG(batches > 0 && N > 0 && M > 0 && batches <= 65535, "fpv_nn_sphere_fused: empty input");
     FPV_CHECK_ARG(tile == 16 || tile == 32, "fpv_nn_sphere_fused: tile must be 16 or 32");
@@ -1520,7 +1536,7 @@ int fpv_nn_sphere_fused(const float *queries, int64_t batches, int64_t N, const 
         return FPV_ERR_WORKSPACE;
     }
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    int rc = sphere_search_impl(queries, 1, batches, N, planes, table, orig_idx, cand_orig, seed_inout, seed_valid, M, tile,
+    int rc = sphere_search_impl(queries, 1, batches, N, planes, table, orig_idx, pos_of, pos_shared, seed_inout, seed_valid, M, tile,
                                 0, nullptr, nullptr, 4, tiles_searched, partial, acc, fix_shift, st);
     if (rc) return rc;
     if (g_fused_variant != 1) {

@@ -118,8 +118,9 @@ class _ShardedChamferFn(torch.autograd.Function):
                     ctx.fix_shift = scene.fix_shift()
                     with torch.cuda.device(dev):
                         wsb = _lib.workspace(L.fpv_nn_sphere_fused_workspace_bytes(T, Ms), dev)
+                        pos, pos_shared = body.pos_table()
                         _lib.check(L.fpv_nn_sphere_fused(_lib.ptr(scene.sorted), T, Ms, _lib.ptr(body.planes),
-                                                         _lib.ptr(body.boxes), _lib.ptr(body.oidx), _lib.ptr(a_c),
+                                                         _lib.ptr(body.boxes), _lib.ptr(body.oidx), _lib.ptr(pos), int(pos_shared),
                                                          _lib.ptr(seed2), int(seed2_valid), N, body.sphere_tile,
                                                          ctx.fix_shift, _lib.ptr(d_b2a), _lib.ptr(acc), _lib.ptr(stats2),
                                                          _lib.ptr(wsb), wsb.numel(), _lib.stream_ptr()),

@@ -173,8 +173,17 @@ class SortedCloud:
                 _lib.check(L.fpv_nn_tile_boxes(_lib.ptr(self.planes), _lib.ptr(self.oidx), B, M, mode, _lib.ptr(self.boxes),
                                                _lib.stream_ptr()), "fpv_nn_tile_boxes")
         self._inv = None
+        self._pos = None
         self.states = {}      # default SearchState handles of callers that pass none: (T, N) -> chamfer.SearchState
         self._fix_shift = None
+
+    def pos_table(self):
+        """(int32 table, shared flag): sorted position of every ORIGINAL index -- what the sphere search needs to turn
+        seeds (original indices) back into table positions.  Cached; [M] when one ordering serves every batch."""
+        if self._pos is None:
+            inv = self.inv_perm
+            self._pos = (inv[0] if self.shared_perm or self.B == 1 else inv).to(torch.int32).contiguous()
+        return self._pos, bool(self.shared_perm or self.B == 1)
 
     def perm_row(self):
         """(perm tensor, batched flag) for fpv_p2p_min_unpack: sorted position -> original position."""
@@ -279,21 +288,22 @@ def min_unpack(slots, world: int, n: int, row: int, perm_row, idx_dtype=torch.in
 
 
 def sphere_search(queries_grouped: torch.Tensor, q_shared: bool, batches: int, cloud: SortedCloud,
-                  cand_orig: torch.Tensor = None, idx_dtype=torch.int32, idx_base: int = 0, stats: torch.Tensor = None,
-                  seed: torch.Tensor = None, seed_valid: bool = True):
-    """Exact NN through the bounding-sphere hierarchy of `cloud` (built with sphere_tile).  cand_orig [batches,M,3]
-    (the candidates in original order) enables temporal seeding across consecutive batches when q_shared; seed
-    [batches,N] int32 (in/out) carries the winners from one call to the next (hints only)."""
+                  idx_dtype=torch.int32, idx_base: int = 0, stats: torch.Tensor = None,
+                  seed: torch.Tensor = None, seed_valid: bool = True, seeding: bool = True):
+    """Exact NN through the bounding-sphere hierarchy of `cloud` (built with sphere_tile).  seeding: consecutive
+    batches of a shared query set seed each other (temporal coherence of a clip); seed [batches,N] int32 (in/out)
+    carries the winners from one call to the next (hints only)."""
     L = _lib.lib()
     q = queries_grouped.contiguous()
     N = q.shape[1]
     dev = q.device
     dist = torch.empty(batches, N, dtype=torch.float32, device=dev)
     idx = torch.empty(batches, N, dtype=idx_dtype, device=dev)
-    co = cand_orig.contiguous() if cand_orig is not None else None
+    pos, pos_shared = cloud.pos_table() if (seeding or seed is not None) else (None, True)
     with torch.cuda.device(dev):
         _lib.check(L.fpv_nn_sphere_search(_lib.ptr(q), int(q_shared), batches, N, _lib.ptr(cloud.planes),
-                                          _lib.ptr(cloud.boxes), _lib.ptr(cloud.oidx), _lib.ptr(co), _lib.ptr(seed), int(seed_valid), cloud.M,
+                                          _lib.ptr(cloud.boxes), _lib.ptr(cloud.oidx), _lib.ptr(pos), int(pos_shared),
+                                          _lib.ptr(seed), int(seed_valid), cloud.M,
                                           cloud.sphere_tile, idx_base, _lib.ptr(dist), _lib.ptr(idx),
                                           8 if idx_dtype == torch.int64 else 4, _lib.ptr(stats), _lib.stream_ptr()),
                    "fpv_nn_sphere_search")

@@ -130,9 +130,10 @@ int fpv_nn_sphere_set_chunking(int ctas_per_sm);
 
 /* Sphere-hierarchy variant for moving candidate sets (scene -> body): clusters of `tile` (16 | 32) sorted points
  * with bounding spheres on four levels (tile, x4, x16, x64 points); a query needs a cluster only if |x - c| <= sqrt(best_x) + r.  With a
- * shared query set and cand_orig (the candidates in ORIGINAL order, [batches][M][3]) consecutive batches (frames)
- * seed each other: every query starts from the exact distance to its previous frame's winner.
- * seed_inout (optional, device, [batches][N] int32, needs cand_orig): the winners of the previous CALL on the same
+ * shared query set and pos_of (the sorted position of every ORIGINAL candidate index: [M] when pos_shared, else
+ * [batches][M]) consecutive batches (frames) seed each other: every query starts from the exact distance to its
+ * previous frame's winner and the three sorted candidates next to it.
+ * seed_inout (optional, device, [batches][N] int32, needs pos_of): the winners of the previous CALL on the same
  * problem (original candidate indices; any value outside [0,M) = no seed, e.g. -1 on the first call); read as the
  * starting point of every (batch, query) when seed_valid != 0, and always overwritten with this call's winners.
  * Seeds are hints: any content yields the same exact result.
@@ -142,7 +143,7 @@ size_t fpv_nn_sphere_table_floats(int64_t M, int tile);
 int fpv_nn_sphere_table(const float *planes, int64_t batches, int64_t M, int tile, float *table,
                         fpv_stream_t stream);
 int fpv_nn_sphere_search(const float *queries, int q_shared, int64_t batches, int64_t N, const float *planes,
-                         const float *table, const int32_t *orig_idx, const float *cand_orig,
+                         const float *table, const int32_t *orig_idx, const int32_t *pos_of, int pos_shared,
                          int32_t *seed_inout, int seed_valid, int64_t M, int tile, int64_t idx_base, float *dist,
                          void *idx, int idx_bytes, unsigned long long *tiles_searched, fpv_stream_t stream);
 
@@ -162,8 +163,8 @@ int fpv_nn_sphere_search(const float *queries, int q_shared, int64_t batches, in
 size_t fpv_nn_sphere_fused_workspace_bytes(int64_t batches, int64_t N);
 int fpv_fix_shift_for(float max_abs_coordinate, int64_t count);
 int fpv_nn_sphere_fused(const float *queries, int64_t batches, int64_t N, const float *planes, const float *table,
-                        const int32_t *orig_idx, const float *cand_orig, int32_t *seed_inout, int seed_valid,
-                        int64_t M, int tile, int fix_shift, float *sum_d, unsigned long long *acc,
+                        const int32_t *orig_idx, const int32_t *pos_of, int pos_shared, int32_t *seed_inout,
+                        int seed_valid, int64_t M, int tile, int fix_shift, float *sum_d, unsigned long long *acc,
                         unsigned long long *tiles_searched, void *workspace, size_t workspace_bytes,
                         fpv_stream_t stream);
 int fpv_nn_sphere_fused_variant(int variant); /* tuning: 1 = accumulate inside the search kernel, 2 = separate pass */

@@ -38,13 +38,13 @@ for order in ("morton_body", "kd"):
             perm = sp.morton_order(verts[T // 2], scene.lo, scene.inv_cell)
         body = sp.SortedCloud(verts, None, None, mode=1, sphere_tile=tile, shared_perm=True, perm=perm)
         seed = torch.empty(T, M, dtype=torch.int32, device=dev)
-        d, i = sp.sphere_search(scene.sorted, True, T, body, cand_orig=verts, seed=seed, seed_valid=False)
+        d, i = sp.sphere_search(scene.sorted, True, T, body, seed=seed, seed_valid=False)
         st = torch.zeros(2, dtype=torch.int64, device=dev)
-        d, i = sp.sphere_search(scene.sorted, True, T, body, cand_orig=verts, stats=st, seed=seed)
+        d, i = sp.sphere_search(scene.sorted, True, T, body, stats=st, seed=seed)
         if ref is None:
             ref = (d.clone(), i.clone())
         same = torch.equal(d, ref[0]) and torch.equal(i, ref[1])
-        ms_plain = timeit(lambda: sp.sphere_search(scene.sorted, True, T, body, cand_orig=verts, seed=seed))
+        ms_plain = timeit(lambda: sp.sphere_search(scene.sorted, True, T, body, seed=seed))
         del d, i
         sum_d = torch.empty(T, dtype=torch.float32, device=dev)
         acc = torch.zeros(T, 10475, 4, dtype=torch.int64, device=dev)
@@ -52,7 +52,7 @@ for order in ("morton_body", "kd"):
         fs = scene.fix_shift()
         P = fpv._lib.ptr
         def fused():
-            fpv._lib.check(L.fpv_nn_sphere_fused(P(scene.sorted), T, M, P(body.planes), P(body.boxes), P(body.oidx), P(verts), P(seed), 1,
+            fpv._lib.check(L.fpv_nn_sphere_fused(P(scene.sorted), T, M, P(body.planes), P(body.boxes), P(body.oidx), P(body.pos_table()[0]), 1, P(seed), 1,
                                                  10475, tile, fs, P(sum_d), P(acc), None, P(ws), ws.numel(), fpv._lib.stream_ptr()))
         L.fpv_nn_sphere_fused_variant(1)
         ms_fused1 = timeit(fused)

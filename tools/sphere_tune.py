@@ -37,12 +37,12 @@ ref = None
 use_seeds = os.environ.get("SEEDS", "1") != "0"
 seed = torch.empty(T, M, dtype=torch.int32, device=dev) if use_seeds else None
 if use_seeds:
-    sp.sphere_search(scene.sorted, True, T, body, cand_orig=verts, seed=seed, seed_valid=False)   # fills the seed buffer
+    sp.sphere_search(scene.sorted, True, T, body, seed=seed, seed_valid=False)   # fills the seed buffer
 for c in sweep:
     L.fpv_nn_sphere_set_chunking(c)
     st = torch.zeros(2, dtype=torch.int64, device=dev)
-    d, i = sp.sphere_search(scene.sorted, True, T, body, cand_orig=verts, stats=st, seed=seed)
-    ms = timeit(lambda: sp.sphere_search(scene.sorted, True, T, body, cand_orig=verts, seed=seed))
+    d, i = sp.sphere_search(scene.sorted, True, T, body, stats=st, seed=seed)
+    ms = timeit(lambda: sp.sphere_search(scene.sorted, True, T, body, seed=seed))
     if ref is None:
         ref = (d, i)
     same = torch.equal(d, ref[0]) and torch.equal(i, ref[1])
