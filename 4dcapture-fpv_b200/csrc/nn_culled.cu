@@ -940,6 +940,8 @@ __global__ void __launch_bounds__(CU_WARPS * 32, MINB) nn_sphere_kernel(const Sp
     if (p.tiles_searched && lane == 0) atomicAdd(p.tiles_searched, searched);
 }
 
+__host__ __device__ inline int64_t ceil_div_dev(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
 // Padded level sizes of the sphere table (whole sibling groups of 4 on every level).
 struct SphereLayout {
     int n0, n1, n2, n3, n0p, n1p, n2p, n3p;
@@ -957,40 +959,52 @@ struct SphereLayout {
     __host__ __device__ int64_t float4s(int tile) const { return 2 * int64_t(entries()) + int64_t(n0p) * tile; }
 };
 
-// one thread per (padded) sphere entry of any level: box centre of the finite member points, covering radius
-// (inflated), stored in the expanded-test form (see above); padding entries are never asked for
-__global__ void sphere_table_kernel(const float *__restrict__ planes, int64_t M, int64_t Mp, int tile,
-                                    float4 *__restrict__ table) {
+// Sphere entries of all four levels: box centre of the finite member points, covering radius (inflated), stored in
+// the expanded-test form (see above); padding entries are never asked for.  A level-0 entry (TILE points) is built by a
+// group of 4 lanes, an entry of level l by 4 * 4^l lanes (up to a whole warp, which then strides over its 1024-point
+// span): every entry costs a few dozen instructions on its critical path instead of a serial walk over its members.
+__global__ void __launch_bounds__(128) sphere_table_kernel(const float *__restrict__ planes, int64_t M, int64_t Mp, int tile,
+                                                           float4 *__restrict__ table) {
     const SphereLayout L(M, tile);
     const int64_t b = blockIdx.y;
-    const int e = blockIdx.x * blockDim.x + threadIdx.x;
-    if (e >= L.entries()) return;
-    int64_t span = tile, first = e;
-    int real = L.n0;
-    if (e >= L.n0p + L.n1p + L.n2p) {
-        span = int64_t(tile) * 64;
-        first = e - L.n0p - L.n1p - L.n2p;
-        real = L.n3;
-    } else if (e >= L.n0p + L.n1p) {
-        span = int64_t(tile) * 16;
-        first = e - L.n0p - L.n1p;
-        real = L.n2;
-    } else if (e >= L.n0p) {
-        span = int64_t(tile) * 4;
-        first = e - L.n0p;
-        real = L.n1;
-    }
-    float4 *out = table + b * L.float4s(tile) + 2 * int64_t(e);
-    if (first >= real) {  // padding: NaN limit, every comparison is false
-        out[0] = make_float4(0.f, 0.f, 0.f, 0.f);
-        out[1] = make_float4(__int_as_float(0x7fc00000), 0.f, 0.f, 0.f);
+    const int lane = threadIdx.x & 31;
+    // work item = (entry, lanes per entry); items are laid out level by level so that a warp never mixes widths
+    const int64_t warp = int64_t(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int64_t w0 = ceil_div_dev(L.n0p, 8), w1 = ceil_div_dev(L.n1p, 2);   // 4 lanes / 16 lanes per entry
+    int e, width, sub;
+    int64_t span;
+    int real;
+    if (warp < w0) {
+        width = 4; e = int(warp * 8 + (lane >> 2)); sub = lane & 3; span = tile; real = L.n0;
+        if (e >= L.n0p) return;
+    } else if (warp < w0 + w1) {
+        width = 16; const int k = int((warp - w0) * 2 + (lane >> 4)); sub = lane & 15; span = int64_t(tile) * 4; real = L.n1;
+        if (k >= L.n1p) return;
+        e = L.n0p + k;
+    } else if (warp < w0 + w1 + L.n2p) {
+        width = 32; const int k = int(warp - w0 - w1); sub = lane; span = int64_t(tile) * 16; real = L.n2;
+        e = L.n0p + L.n1p + k;
+    } else if (warp < w0 + w1 + L.n2p + L.n3p) {
+        width = 32; const int k = int(warp - w0 - w1 - L.n2p); sub = lane; span = int64_t(tile) * 64; real = L.n3;
+        e = L.n0p + L.n1p + L.n2p + k;
+    } else {
         return;
     }
-    const int64_t j0 = first * span;
+    const int first = e - (e >= L.n0p + L.n1p + L.n2p ? L.n0p + L.n1p + L.n2p : (e >= L.n0p + L.n1p ? L.n0p + L.n1p : (e >= L.n0p ? L.n0p : 0)));
+    const unsigned gmask = width == 32 ? 0xffffffffu : (((1u << width) - 1u) << (lane & ~(width - 1)));
+    float4 *out = table + b * L.float4s(tile) + 2 * int64_t(e);
+    if (first >= real) {  // padding: NaN limit, every comparison is false
+        if (sub == 0) {
+            out[0] = make_float4(0.f, 0.f, 0.f, 0.f);
+            out[1] = make_float4(__int_as_float(0x7fc00000), 0.f, 0.f, 0.f);
+        }
+        return;
+    }
+    const int64_t j0 = int64_t(first) * span;
     const int64_t j1 = (j0 + span < M) ? j0 + span : M;
     const float *P = planes + b * 3 * Mp;
     float lo[3] = {CUDART_INF_F, CUDART_INF_F, CUDART_INF_F}, hi[3] = {-CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F};
-    for (int64_t j = j0; j < j1; ++j) {
+    for (int64_t j = j0 + sub; j < j1; j += width) {
         const float x = P[j], y = P[Mp + j], z = P[2 * Mp + j];
         if (fabsf(x) < CUDART_INF_F && fabsf(y) < CUDART_INF_F && fabsf(z) < CUDART_INF_F) {  // finite points only
             lo[0] = fminf(lo[0], x); hi[0] = fmaxf(hi[0], x);
@@ -998,20 +1012,31 @@ __global__ void sphere_table_kernel(const float *__restrict__ planes, int64_t M,
             lo[2] = fminf(lo[2], z); hi[2] = fmaxf(hi[2], z);
         }
     }
+    for (int o = width >> 1; o > 0; o >>= 1) {
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            lo[a] = fminf(lo[a], __shfl_xor_sync(gmask, lo[a], o));
+            hi[a] = fmaxf(hi[a], __shfl_xor_sync(gmask, hi[a], o));
+        }
+    }
     if (lo[0] > hi[0]) {  // no finite member: nothing in here can win; asked for only by queries without any bound
-        out[0] = make_float4(0.f, 0.f, 0.f, -2e-30f);
-        out[1] = make_float4(-CUDART_INF_F, 0.f, 0.f, 0.f);
+        if (sub == 0) {
+            out[0] = make_float4(0.f, 0.f, 0.f, -2e-30f);
+            out[1] = make_float4(-CUDART_INF_F, 0.f, 0.f, 0.f);
+        }
         return;
     }
     const float cx = 0.5f * lo[0] + 0.5f * hi[0], cy = 0.5f * lo[1] + 0.5f * hi[1], cz = 0.5f * lo[2] + 0.5f * hi[2];
     float r2 = 0.f;
-    for (int64_t j = j0; j < j1; ++j) {
+    for (int64_t j = j0 + sub; j < j1; j += width) {
         const float x = P[j], y = P[Mp + j], z = P[2 * Mp + j];
         if (fabsf(x) < CUDART_INF_F && fabsf(y) < CUDART_INF_F && fabsf(z) < CUDART_INF_F) {
             const float dx = x - cx, dy = y - cy, dz = z - cz;
             r2 = fmaxf(r2, dx * dx + dy * dy + dz * dz);
         }
     }
+    for (int o = width >> 1; o > 0; o >>= 1) r2 = fmaxf(r2, __shfl_xor_sync(gmask, r2, o));
+    if (sub != 0) return;
     const float r = sqrtf(r2) * 1.00001f + 1e-30f;
     const float c2 = cx * cx + cy * cy + cz * cz, rr = r * r;
     if (!(c2 + rr < 1e30f)) {  // the expanded test would overflow: always asked for (lim = +inf), full slack
@@ -1374,7 +1399,8 @@ int fpv_nn_sphere_table(const float *planes, int64_t batches, int64_t M, int til
     const int64_t Mp = ceil_div(M, 64) * 64;
     const SphereLayout L(M, tile);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    dim3 grid((unsigned)ceil_div(L.entries(), 128), (unsigned)batches);
+    const int64_t warps = ceil_div(L.n0p, 8) + ceil_div(L.n1p, 2) + L.n2p + L.n3p;
+    dim3 grid((unsigned)ceil_div(warps, 4), (unsigned)batches);
     sphere_table_kernel<<<grid, 128, 0, st>>>(planes, M, Mp, tile, reinterpret_cast<float4 *>(table));
     FPV_LAUNCH_CHECK("sphere_table_kernel");
     dim3 grid2((unsigned)ceil_div(int64_t(L.n0p) * tile / 4, 128), (unsigned)batches);
