@@ -85,6 +85,8 @@ SIGNATURES = {
     "fpv_p2p_min_unpack": (c_int, [c_void_p, c_int, c_int64, c_int64, c_void_p, c_int, c_int64, c_int64, c_void_p, c_int,
                                    c_void_p, c_void_p, c_int, c_void_p, c_void_p]),
     "fpv_p2p_push": (c_int, [c_void_p, c_int64, POINTER(c_void_p), c_int, c_void_p, c_int64, c_void_p]),
+    "fpv_p2p_gather": (c_int, [c_void_p, c_int, c_int64, c_int64, c_void_p, c_int, POINTER(c_int64), POINTER(c_int64), c_void_p,
+                               c_void_p]),
     "fpv_p2p_sum": (c_int, [c_void_p, c_int, c_int64, c_int64, c_void_p, c_int, c_int64, c_void_p, c_void_p]),
     "fpv_morton_keys": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p]),
     "fpv_nn_gather_pack": (c_int, [c_void_p, c_void_p, c_int, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_void_p]),

@@ -125,6 +125,23 @@ __global__ void __launch_bounds__(256) p2p_sum_kernel(const float *__restrict__ 
     out[i] = acc;
 }
 
+struct GatherParams {
+    int64_t offset[FPV_MAX_PEERS + 1];  // where rank r's piece goes in `out` (elements)
+    int64_t count[FPV_MAX_PEERS + 1];   // its length
+    int world;
+};
+
+// out[offset[r] + i] = slot r [i]: the pieces the ranks pushed (an all-gather), read from the local mailbox half
+__global__ void __launch_bounds__(256) p2p_gather_kernel(const float *__restrict__ slots, int64_t slot_stride,
+                                                         int64_t half_stride, const unsigned *parity, const GatherParams g,
+                                                         float *__restrict__ out) {
+    const int r = blockIdx.y;
+    const float *s = slots + ((parity && (*parity & 1u)) ? half_stride : 0) + int64_t(r) * slot_stride;
+    float *o = out + g.offset[r];
+    for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < g.count[r]; i += int64_t(gridDim.x) * blockDim.x)
+        o[i] = s[i];
+}
+
 }  // namespace fpv
 
 using namespace fpv;
@@ -222,6 +239,32 @@ int fpv_p2p_push(const float *src, int64_t n, float *const *dst_host, int n_dst,
     p.half_stride = half_stride;
     p2p_push_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(src, n, p);
     FPV_LAUNCH_CHECK("p2p_push_kernel");
+    return FPV_OK;
+}
+
+/* All-gather read-out: out[offset_host[r] .. + count_host[r]) = the piece rank r pushed into slot r of the local mailbox. */
+int fpv_p2p_gather(const float *slots, int world, int64_t slot_stride, int64_t half_stride, uint32_t *parity, int flip,
+                   const int64_t *offset_host, const int64_t *count_host, float *out, fpv_stream_t stream) {
+    FPV_CHECK_ARG(slots && out && offset_host && count_host && world >= 1 && world <= FPV_MAX_PEERS + 1,
+                  "fpv_p2p_gather: bad arguments");
+    GatherParams g;
+    int64_t mx = 1;
+    for (int r = 0; r < FPV_MAX_PEERS + 1; ++r) {
+        g.offset[r] = r < world ? offset_host[r] : 0;
+        g.count[r] = r < world ? count_host[r] : 0;
+        if (g.count[r] > mx) mx = g.count[r];
+    }
+    g.world = world;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    int64_t bx = ceil_div(mx, 256 * 4);
+    if (bx > 1024) bx = 1024;
+    dim3 grid((unsigned)bx, (unsigned)world);
+    p2p_gather_kernel<<<grid, 256, 0, st>>>(slots, slot_stride, half_stride, parity, g, out);
+    FPV_LAUNCH_CHECK("p2p_gather_kernel");
+    if (parity && flip) {
+        p2p_flip_kernel<<<1, 1, 0, st>>>(parity);
+        FPV_LAUNCH_CHECK("p2p_flip_kernel");
+    }
     return FPV_OK;
 }
 

@@ -100,11 +100,14 @@ class FitProblem:
                  rank: int = 0, world_size: int = 1, group=None, idx_dtype=torch.int64, presort_scene: bool = True,
                  front_end: bool = False, dct_frames: int = DCT_FRAMES, mode: str = "global", fused: bool = True,
                  comm: str = "p2p", options: Optional[chamfer.SearchOptions] = None, clips: int = 1,
-                 scene_order: str = "morton"):
+                 scene_order: str = "morton", shard_frames: bool = True):
         """clips > 1: T is the TOTAL number of frames of `clips` independent clips of T/clips frames batched into one
         step (BASELINE.json configs[4]); the temporal residuals never couple frames of different clips.
         fused: scene -> body reduced inside the search kernel (chamfer.scene_to_body_sum) instead of materialising
-        [T,M] distances and indices.  comm: "p2p" (peer-memory mailbox) or "nccl" for the sharded key / gradient exchange."""
+        [T,M] distances and indices.  comm: "p2p" (peer-memory mailbox) or "nccl" for the sharded key / gradient exchange.
+        shard_frames (sharded runs over the mailbox): the per-frame part of the step -- front-end, body model, world
+        placement and their backward -- runs on T / world frames per rank; the vertices are all-gathered through the
+        mailbox (backward: reduce-scatter of the vertex gradient), so only the searches' fixed costs stay replicated."""
         if mode not in ("global", "local"):
             raise RuntimeError("FitProblem: mode must be 'global' (cal_loss) or 'local' (cal_loss2)")
         if T % clips != 0:
@@ -118,7 +121,11 @@ class FitProblem:
         self.search_state = chamfer.SearchState()          # seeds, frozen body order: per problem, never global
         constants = make_body_constants(seed)
         self.constants = constants
-        self.model = SMPLXB200(constants, batch_size=T).to(self.device)
+        self.shard_frames = bool(shard_frames and world_size > 1 and comm == "p2p" and mode == "global"
+                                 and self.device.type == "cuda")
+        self.frame_ranges = [sharded.shard_range(T, world_size, r) for r in range(world_size)]
+        self.f0, self.f1 = self.frame_ranges[rank] if self.shard_frames else (0, T)
+        self.model = SMPLXB200(constants, batch_size=self.f1 - self.f0).to(self.device)
         parts = [make_clip_params(self.Tc, seed + 1000 * c) for c in range(clips)]
         clip = {k: (torch.cat([p[k] for p in parts]) if parts[0][k].dim() > 0 else parts[0][k]) for k in parts[0]}
         self.front_end = front_end
@@ -170,6 +177,9 @@ class FitProblem:
         self.comm = None
         if world_size > 1 and comm == "p2p" and self.device.type == "cuda":
             nfloats = self.host_params.numel() + 1 + 16 * T + 64 + (self.host_c_dct.numel() if self.dct_batches else 0)
+            if self.shard_frames:   # the all-gather / reduce-scatter pieces: vertices + 23 joints of the widest frame range
+                nv = constants["v_template"].shape[0]
+                nfloats = max(nfloats, max(e - b for b, e in self.frame_ranges) * (nv + 23) * 3)
             self.comm = p2p.Mailbox(self.device, group, key_capacity=T * constants["v_template"].shape[0], float_capacity=nfloats)
         self._adam = None
         self.upload()
@@ -226,8 +236,12 @@ class FitProblem:
         return torch.stack(vals).mean()
 
     def _body(self):
-        """Front-end + body model + world placement: (vertices [T,V,3], joints [T,23,3], extra losses)."""
-        p = self.params
+        """Front-end + body model + world placement: (vertices [T,V,3], joints [T,23,3], extra losses).  With
+        shard_frames every rank runs its own frame range and the results are all-gathered through the mailbox."""
+        f0, f1 = self.f0, self.f1
+        Tr = f1 - f0
+        p = self.params[f0:f1] if self.shard_frames else self.params
+        cam_ext = self.camera_ext[f0:f1] if self.shard_frames else self.camera_ext
         sl = lambda r: p[:, r[0]:r[1]]
         inv_world = 1.0 / self.world
         extra_losses = {}
@@ -237,17 +251,25 @@ class FitProblem:
             z = bp.pop("body_pose_vp")
             cam_transl = bp.pop("camera_translation")
             if self.mode == "global":
-                extra_losses["vposer"] = torch.mean(z ** 2) * inv_world
-            b2w = residuals.body2world(cam_transl, self.scale, self.camera_ext)
-            out = self.model(return_verts=True, body_pose=self.vposer.decode(z, output_type="aa").view(self.T, -1), **bp)
+                # mean over ALL frames: a rank that holds only its own rows contributes its share of the sum
+                extra_losses["vposer"] = (torch.sum(z ** 2) / float(self.T * z.shape[1])) if self.shard_frames \
+                    else torch.mean(z ** 2) * inv_world
+            b2w = residuals.body2world(cam_transl, self.scale, cam_ext)
+            out = self.model(return_verts=True, body_pose=self.vposer.decode(z, output_type="aa").view(Tr, -1), **bp)
         else:
-            b2w = residuals.body2world(sl(P_CAM), self.scale, self.camera_ext)
+            b2w = residuals.body2world(sl(P_CAM), self.scale, cam_ext)
             out = self.model(return_verts=True, body_pose=sl(P_POSE), transl=sl(P_TRANSL),
                              global_orient=sl(P_ORIENT), betas=sl(P_BETAS),
                              left_hand_pose=sl(P_LH), right_hand_pose=sl(P_RH))
         verts = residuals.verts_transform(out.vertices * self.scale, b2w)
         # joints are transformed UNSCALED, as in the reference (only the vertices are multiplied by scale, :284-285 vs :296-297)
         joints = residuals.verts_transform(out.joints[:, 0:23, :].contiguous(), b2w)
+        if self.shard_frames:
+            V = verts.shape[1]
+            rows = torch.cat([verts.reshape(Tr, V * 3), joints.reshape(Tr, 69)], dim=1)
+            full = p2p.all_gather_rows(rows, self.comm, self.frame_ranges)
+            verts = full[:, :V * 3].reshape(self.T, V, 3)
+            joints = full[:, V * 3:].reshape(self.T, 23, 3)
         return verts, joints, extra_losses
 
     def forward(self) -> Dict[str, torch.Tensor]:

@@ -131,6 +131,47 @@ class Mailbox:
                                      _lib.stream_ptr()), "fpv_p2p_sum")
         return out
 
+    def all_gather(self, piece: torch.Tensor, offsets, counts, out: torch.Tensor) -> torch.Tensor:
+        """out[offsets[r] : offsets[r] + counts[r]] = rank r's `piece` (flat float32), for every r.  Every rank pushes
+        its piece into slot `rank` of every mailbox, one barrier, one read-out kernel."""
+        L = _lib.lib()
+        n = int(counts[self.rank])
+        if max(counts) > self.float_cap or piece.numel() != n:
+            raise RuntimeError("p2p.Mailbox.all_gather: piece size / capacity mismatch")
+        src = piece.contiguous().float()
+        dst = (ctypes.c_void_p * self.world)(*[ctypes.c_void_p(self.float_slot(r, self.rank)) for r in range(self.world)])
+        off = (ctypes.c_int64 * self.world)(*[int(o) for o in offsets])
+        cnt = (ctypes.c_int64 * self.world)(*[int(c) for c in counts])
+        with torch.cuda.device(self.device):
+            _lib.check(L.fpv_p2p_push(_lib.ptr(src), n, dst, self.world, ctypes.c_void_p(self.parity_floats),
+                                      self.floats_half, _lib.stream_ptr()), "fpv_p2p_push")
+            self.barrier()
+            _lib.check(L.fpv_p2p_gather(ctypes.c_void_p(self.base + self.floats_off), self.world, self.float_cap,
+                                        self.floats_half, ctypes.c_void_p(self.parity_floats), 1, off, cnt, _lib.ptr(out),
+                                        _lib.stream_ptr()), "fpv_p2p_gather")
+        return out
+
+    def reduce_scatter(self, full: torch.Tensor, offsets, counts) -> torch.Tensor:
+        """sum over the ranks of full[offsets[rank] : + counts[rank]] (flat float32), in rank order: every rank pushes
+        each owner's slice of its `full` into slot `rank` of that owner's mailbox, one barrier, one sum kernel."""
+        L = _lib.lib()
+        if max(counts) > self.float_cap:
+            raise RuntimeError("p2p.Mailbox.reduce_scatter: slice exceeds the capacity")
+        src = full.contiguous().float().reshape(-1)
+        n = int(counts[self.rank])
+        out = torch.empty(n, dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.device):
+            for q in range(self.world):
+                dst = (ctypes.c_void_p * 1)(ctypes.c_void_p(self.float_slot(q, self.rank)))
+                piece = src[int(offsets[q]):int(offsets[q]) + int(counts[q])]
+                _lib.check(L.fpv_p2p_push(_lib.ptr(piece), int(counts[q]), dst, 1, ctypes.c_void_p(self.parity_floats),
+                                          self.floats_half, _lib.stream_ptr()), "fpv_p2p_push")
+            self.barrier()
+            _lib.check(L.fpv_p2p_sum(ctypes.c_void_p(self.base + self.floats_off), self.world, self.float_cap,
+                                     self.floats_half, ctypes.c_void_p(self.parity_floats), 1, n, _lib.ptr(out),
+                                     _lib.stream_ptr()), "fpv_p2p_sum")
+        return out
+
     def check(self) -> None:
         """Host-side: raise if a barrier ever timed out (a peer died or fell out of step).  Synchronises."""
         torch.cuda.synchronize(self.device)
@@ -155,6 +196,31 @@ class Mailbox:
                     L.fpv_p2p_close(ctypes.c_void_p(q))
                 L.fpv_p2p_free(ctypes.c_void_p(self.base))
             self._opened, self.base = [], 0
+
+
+class _AllGatherRows(torch.autograd.Function):
+    """rows [Tr, F] of this rank -> [T, F] of every rank (row ranges per rank); backward = reduce-scatter of the
+    gradient: every rank holds a partial gradient for ALL rows, the owner of a row range gets the sum."""
+
+    @staticmethod
+    def forward(ctx, rows, box, row_ranges):
+        F = rows.shape[1]
+        offsets = [b * F for b, _ in row_ranges]
+        counts = [(e - b) * F for b, e in row_ranges]
+        out = torch.empty(row_ranges[-1][1], F, dtype=torch.float32, device=rows.device)
+        box.all_gather(rows.reshape(-1), offsets, counts, out)
+        ctx.box, ctx.offsets, ctx.counts, ctx.shape = box, offsets, counts, tuple(rows.shape)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        return ctx.box.reduce_scatter(g, ctx.offsets, ctx.counts).view(ctx.shape), None, None
+
+
+def all_gather_rows(rows: torch.Tensor, box: "Mailbox", row_ranges) -> torch.Tensor:
+    """Differentiable all-gather of per-rank row blocks through the mailbox (forward: push + barrier + read-out;
+    backward: reduce-scatter in rank order)."""
+    return _AllGatherRows.apply(rows, box, row_ranges)
 
 
 def _as_tensor(addr: int, n: int, dtype, device) -> torch.Tensor:

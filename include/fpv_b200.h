@@ -346,6 +346,8 @@ int fpv_p2p_min_unpack(const uint64_t *slots, int world, int64_t slot_stride, in
                        int idx_bytes, uint64_t *keys_out, fpv_stream_t stream);
 int fpv_p2p_push(const float *src, int64_t n, float *const *dst_host, int n_dst, const uint32_t *parity,
                  int64_t half_stride, fpv_stream_t stream);
+int fpv_p2p_gather(const float *slots, int world, int64_t slot_stride, int64_t half_stride, uint32_t *parity, int flip,
+                   const int64_t *offset_host, const int64_t *count_host, float *out, fpv_stream_t stream);
 int fpv_p2p_sum(const float *slots, int world, int64_t slot_stride, int64_t half_stride, uint32_t *parity, int flip,
                 int64_t n, float *out, fpv_stream_t stream);
 
