@@ -60,7 +60,8 @@ def contact_vertex_ids(constants: Dict[str, torch.Tensor]) -> torch.Tensor:
     return torch.nonzero(leg[dom]).squeeze(1)
 
 
-SHARD_BLOCK = 2048
+SHARD_BLOCK = 2048        # Morton-ordered scene: points per dealt block
+SHARD_BLOCK_KD = 128      # k-d ordered scene: one query group (= two 64-point cells) per dealt block
 ADAM = dict(lr=0.005, beta1=0.9, beta2=0.999, eps=1e-8)     # optim.Adam(..., lr=self.init_lr_h) :188, init_lr_h = 0.005 :671
 
 
@@ -83,6 +84,22 @@ def _kd_sorted(points: torch.Tensor) -> torch.Tensor:
     return out[torch.argsort(cell * (1 << 30) + fine, stable=True)].contiguous()
 
 
+def _deal_blocks(M: int, world: int, blk: int) -> torch.Tensor:
+    """Permutation of arange(M) that deals blocks of `blk` consecutive indices round-robin to `world` ranks and lays the
+    ranks' shares out one after the other, each EXACTLY sharded.shard_range(M, world, r) long: whole blocks stay whole
+    and aligned inside every share (a share that ends up a few points long hands its tail to the short ones)."""
+    blocks = torch.arange(M).split(blk)
+    share = [torch.cat(blocks[r::world]) if len(blocks) > r else torch.zeros(0, dtype=torch.int64) for r in range(world)]
+    sizes = [e - b for b, e in (sharded.shard_range(M, world, r) for r in range(world))]
+    pool = torch.cat([share[r][sizes[r]:] for r in range(world)])
+    out = []
+    for r in range(world):
+        need = sizes[r] - min(sizes[r], share[r].numel())
+        out.append(torch.cat([share[r][:sizes[r]], pool[:need]]))
+        pool = pool[need:]
+    return torch.cat(out)
+
+
 def leg_vertex_ids(constants: Dict[str, torch.Tensor]):
     """Synthetic stand-ins for body_segments/L_Leg.json and R_Leg.json (:401-409): (left ids, right ids)."""
     dom = constants["lbs_weights"].argmax(dim=1)
@@ -100,7 +117,7 @@ class FitProblem:
                  rank: int = 0, world_size: int = 1, group=None, idx_dtype=torch.int64, presort_scene: bool = True,
                  front_end: bool = False, dct_frames: int = DCT_FRAMES, mode: str = "global", fused: bool = True,
                  comm: str = "p2p", options: Optional[chamfer.SearchOptions] = None, clips: int = 1,
-                 scene_order: str = "morton", shard_frames: bool = True):
+                 scene_order: str = "kd", shard_frames: bool = True):
         """clips > 1: T is the TOTAL number of frames of `clips` independent clips of T/clips frames batched into one
         step (BASELINE.json configs[4]); the temporal residuals never couple frames of different clips.
         fused: scene -> body reduced inside the search kernel (chamfer.scene_to_body_sum) instead of materialising
@@ -158,21 +175,21 @@ class FitProblem:
         self.begin, self.end = sharded.shard_range(M, world_size, rank)
         if presort_scene and mode == "global":
             # One-time host-side data preparation: the losses do not depend on the order of the scene points (every
-            # term is a min / mean over them), so the scene is stored along the Morton curve.  With several ranks the
-            # sorted points are dealt round-robin in blocks of SHARD_BLOCK (blocks keep 128 consecutive queries spatially
-            # compact), so every rank's shard covers the WHOLE room
-            # (a spatially contiguous shard leaves the ranks far from the body with far-field-only work for the
-            # body->scene search and unbalances the scene->body search: 58 vs 30 ms/step at 2 GPUs).  Each shard is
-            # then ordered on its own grid, which is the order spatial.cached_scene would sort it into (its
-            # permutation becomes the identity and the per-step gathers that undo it disappear).
-            order = _kd_sorted if scene_order == "kd" else _morton_sorted
+            # term is a min / mean over them), so the scene is stored in a spatial order (k-d partition or Morton curve).
+            # With several ranks the ordered points are dealt round-robin in blocks, so every rank's shard covers the
+            # WHOLE room at full local density (a spatially contiguous shard leaves the ranks far from the body with
+            # far-field-only work and unbalances the scene->body search: 58 vs 30 ms/step at 2 GPUs in round 1; dealing
+            # single points thins every query group out).  k-d order: blocks of 128 points -- one query group of the
+            # sphere search, two 64-point cells of the box search -- kept as they are: ~7,800 / world groups per rank
+            # balance the heavy-tailed per-group cost statistically (blocks of 2048 left 15 % between two ranks).
+            # Morton order: blocks of 2048, each shard then re-sorted on its own grid.
+            kd = scene_order == "kd"
+            order = _kd_sorted if kd else _morton_sorted
             whole = order(self.host_scene)
             if world_size > 1:
-                nblk = (M + SHARD_BLOCK - 1) // SHARD_BLOCK
-                blocks = torch.arange(M).split(SHARD_BLOCK)
-                whole = whole[torch.cat([blocks[i] for r in range(world_size) for i in range(r, nblk, world_size)])]
+                whole = whole[_deal_blocks(M, world_size, SHARD_BLOCK_KD if kd else SHARD_BLOCK)]
             parts = [whole[slice(*sharded.shard_range(M, world_size, r))] for r in range(world_size)]
-            self.host_scene = torch.cat([order(p) for p in parts]).contiguous()
+            self.host_scene = torch.cat(parts if kd else [order(p) for p in parts]).contiguous()
         self.scene_presorted = bool(presort_scene and mode == "global" and scene_order == "kd")
         self.comm = None
         if world_size > 1 and comm == "p2p" and self.device.type == "cuda":

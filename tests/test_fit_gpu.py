@@ -89,7 +89,7 @@ def test_fit_step_matches_oracle(fpv, cuda_dev):
 def test_fit_step_cuda_graph_replay_matches_eager(fpv, cuda_dev):
     """f1: the whole step captured as one CUDA graph reproduces the eager step bit for bit (the kernels are
     deterministic), and follows in-place parameter updates between replays."""
-    prob = fpv.FitProblem(T=5, M=12000, device=cuda_dev, seed=1237)
+    prob = fpv.FitProblem(T=5, M=12000, device=cuda_dev, seed=1237, scene_order="morton")
     loss_e = prob.step().clone()
     grads_e = [t.grad.clone() for t in prob.leaves()]
     prob.capture()
