@@ -183,3 +183,35 @@ def test_local_mode_step_matches_cal_loss2(fpv, cuda_dev):
     a = prob.step_graph().item()
     b = prob.step_graph().item()
     assert np.isfinite(a) and np.isfinite(b) and b != a                          # the captured update moves the body
+
+
+def test_batched_clips_equal_independent_clips(fpv, cuda_dev):
+    """BASELINE.json configs[4] (independent clips batched into one step): with equal-length clips every loss term is a
+    mean over frames, so the batched step must equal the average of the single-clip steps -- loss and per-frame
+    gradients -- and no temporal residual may couple frames of different clips."""
+    C, Tc, M = 3, 6, 8000
+    big = fpv.FitProblem(T=C * Tc, M=M, device=cuda_dev, seed=1242, front_end=True, dct_frames=3, clips=C)
+    assert big.dct_batches == C * (Tc // 3)
+    loss = big.step()
+    per = big.dct_batches // C
+    singles, total = [], 0.0
+    for c in range(C):
+        one = fpv.FitProblem(T=Tc, M=M, device=cuda_dev, seed=1242, front_end=True, dct_frames=3)
+        with torch.no_grad():
+            sl = slice(c * Tc, (c + 1) * Tc)
+            one.params.copy_(big.params[sl]); one.data.copy_(big.data[sl]); one.camera_ext.copy_(big.camera_ext[sl])
+            one.scale.copy_(big.scale); one.c_dct.copy_(big.c_dct[c * per:(c + 1) * per])
+        assert torch.equal(one.scene, big.scene)
+        total += one.step().item() / C
+        singles.append(one)
+    assert loss.item() == pytest.approx(total, rel=1e-5)
+    for c, one in enumerate(singles):
+        sl = slice(c * Tc, (c + 1) * Tc)
+        ref = one.params.grad / C
+        err = (big.params.grad[sl] - ref).abs().max().item()
+        assert err <= 1e-5 * ref.abs().max().item() + 1e-9, (c, err)
+        refc = one.camera_ext.grad / C
+        assert (big.camera_ext.grad[sl] - refc).abs().max().item() <= 1e-5 * refc.abs().max().item() + 1e-9
+    big.capture(update=True)
+    a = big.step_graph().item()
+    assert np.isfinite(a)
