@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """BASELINE.json configs[3]: chamfer NN microbench -- 10k-3M body-vertex queries x 100k-20M scene points at 1/2/4/8 GPUs.
 
-    python tools/nn_microbench.py [--q 10000,100000,1000000,3000000] [--m 100000,1000000,5000000,20000000] [--reps 5]
+    python tools/nn_microbench.py [--queries 10000,100000,1000000,3000000] [--points 100000,1000000,5000000,20000000] [--reps 5]
     python -m torch.distributed.run --nproc-per-node N --master-addr 127.0.0.1 tools/nn_microbench.py ...
 
 Queries are the world-space vertices of T = Q / 10,475 frames of the synthetic clip; the scene is sharded over the ranks
@@ -28,8 +28,8 @@ V = 10475
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--q", default="10000,100000,1000000,3000000")
-    ap.add_argument("--m", default="100000,1000000,5000000,20000000")
+    ap.add_argument("--queries", default="10000,100000,1000000,3000000")
+    ap.add_argument("--points", default="100000,1000000,5000000,20000000")
     ap.add_argument("--reps", type=int, default=5)
     ap.add_argument("--scene", default="uniform")
     args = ap.parse_args()
@@ -64,8 +64,8 @@ def main():
             ms = float(t.item())
         return ms
 
-    for M in [int(x) for x in args.m.split(",")]:
-        for Q in [int(x) for x in args.q.split(",")]:
+    for M in [int(x) for x in args.points.split(",")]:
+        for Q in [int(x) for x in args.queries.split(",")]:
             T = max(1, round(Q / V))
             prob = fpv.FitProblem(T=T, M=M, device=dev, seed=1235, rank=rank, world_size=world, scene_kind=args.scene,
                                   idx_dtype=torch.int32)
