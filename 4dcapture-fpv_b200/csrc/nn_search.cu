@@ -477,10 +477,8 @@ __device__ __forceinline__ int fix_exponent(const unsigned *bound, int nb_bits) 
 
 // For every (b,i): j = idx[b,i]; c = 2 g (x_i - y_j).  to_y: acc[b*acc_bstride + 3j..] -= c ; else
 // acc[b*acc_bstride + 3i..] += c (used when the target cloud is shared across batches).
-// A warp walks rows of 32 consecutive queries (coalesced loads) and merges runs of consecutive lanes with the same
-// target by a segmented scan before touching memory: when the queries arrive in spatial order (the Morton-sorted
-// scene of the spatial path) neighbours share their nearest body vertex and most atomics disappear.  Integer adds
-// are associative, so the merge order cannot change the result.
+// A warp walks rows of 32 consecutive queries (coalesced loads) and merges the lanes that hit the same target before
+// touching memory.  Integer adds are associative, so the merge order cannot change the result.
 constexpr int BWD_ROWS = 8;  // rows of 32 consecutive elements per warp
 
 template <typename IdxT>
@@ -515,32 +513,19 @@ __global__ void __launch_bounds__(256) bwd_accum_kernel(const float *__restrict_
                 v[k] = __float2ll_rn(__fmul_rn(c, scale));
             }
         }
-        // runs of equal targets over consecutive lanes: segmented inclusive scan, the last lane of a run owns its sum
-        const long long tp = __shfl_up_sync(0xffffffffu, t, 1);
-        const unsigned heads = __ballot_sync(0xffffffffu, lane == 0 || tp != t);
-        if (heads == 1u) {
-            // the whole row hits one target (the far field): three 21-bit limbs through the integer warp-reduce unit,
-            // v = lo + mid 2^21 + hi 2^42 with hi signed -- exact, like the scan
+        // lanes that hit the same target, consecutive or not, form one group (match.any); every group is summed through
+        // the integer warp-reduce unit -- three 21-bit limbs per component, v = lo + mid 2^21 + hi 2^42 with hi signed,
+        // exact for <= 32 addends -- and one lane per group touches memory.  When the queries arrive in spatial order
+        // (the sorted scene of the spatial path) neighbours share their nearest body vertex and most atomics disappear.
+        const unsigned grp = __match_any_sync(0xffffffffu, t);
 #pragma unroll
-            for (int k = 0; k < 3; ++k) {
-                const int lo = int(v[k] & 0x1FFFFF), mid = int((v[k] >> 21) & 0x1FFFFF), hi = int(v[k] >> 42);
-                const long long slo = __reduce_add_sync(0xffffffffu, lo), smid = __reduce_add_sync(0xffffffffu, mid);
-                const long long shi = __reduce_add_sync(0xffffffffu, hi);
-                v[k] = slo + (smid << 21) + (shi << 42);
-            }
-        } else {
-            const int start = 31 - __clz(heads & (0xffffffffu >> (31 - lane)));
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-#pragma unroll
-                for (int k = 0; k < 3; ++k) {
-                    const long long u = __shfl_up_sync(0xffffffffu, v[k], o);
-                    if (lane - o >= start) v[k] += u;
-                }
-            }
+        for (int k = 0; k < 3; ++k) {
+            const int lo = int(v[k] & 0x1FFFFF), mid = int((v[k] >> 21) & 0x1FFFFF), hi = int(v[k] >> 42);
+            const long long slo = __reduce_add_sync(grp, lo), smid = __reduce_add_sync(grp, mid);
+            const long long shi = __reduce_add_sync(grp, hi);
+            v[k] = slo + (smid << 21) + (shi << 42);
         }
-        const bool tail = lane == 31 || ((heads >> (lane + 1)) & 1u);
-        if (tail && t >= 0) {
+        if (t >= 0 && lane == __ffs(grp) - 1) {
 #pragma unroll
             for (int k = 0; k < 3; ++k)
                 if (v[k] != 0) atomicAdd(base + 3 * t + k, static_cast<unsigned long long>(v[k]));

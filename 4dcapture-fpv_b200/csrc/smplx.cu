@@ -303,6 +303,7 @@ __global__ void __launch_bounds__(128) jointgrad_kernel(const fpv_smplx_model_t 
     __shared__ int ex_id[MAX_EXTRA];
     __shared__ float ex_g[MAX_EXTRA][3];
     __shared__ float scratch[32];
+    __shared__ float red[8][12];
     const int64_t t = blockIdx.y;
     const int j = blockIdx.x;
     const int V = m.num_verts;
@@ -333,10 +334,19 @@ __global__ void __launch_bounds__(128) jointgrad_kernel(const fpv_smplx_model_t 
                 acc[4 * r + 3] += wg;
             }
         }
+        // all twelve sums in ONE block reduction (fixed shuffle tree per warp, warps added in order: deterministic)
+        // instead of twelve with two barriers each
 #pragma unroll
-        for (int k = 0; k < 12; ++k) {
-            const float s = block_sum(acc[k], scratch);
-            if (threadIdx.x == 0) gA[(t * NJ + j) * 12 + k] = s;
+        for (int k = 0; k < 12; ++k) acc[k] = warp_sum(acc[k]);
+        if ((threadIdx.x & 31) == 0) {
+#pragma unroll
+            for (int k = 0; k < 12; ++k) red[threadIdx.x >> 5][k] = acc[k];
+        }
+        __syncthreads();
+        if (threadIdx.x < 12) {
+            float s = 0.f;
+            for (int w = 0; w < int(blockDim.x >> 5); ++w) s += red[w][threadIdx.x];
+            gA[(t * NJ + j) * 12 + threadIdx.x] = s;
         }
     } else {
         for (int v = threadIdx.x; v < V; v += blockDim.x) {
