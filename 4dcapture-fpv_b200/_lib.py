@@ -71,7 +71,6 @@ SIGNATURES = {
     "fpv_nn_sphere_fused": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p,
                                     c_int, c_int64, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t,
                                     c_void_p]),
-    "fpv_nn_sphere_fused_variant": (c_int, [c_int]),
     "fpv_scene2body_grad": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int64, c_int64, c_void_p, c_int, c_void_p]),
     "fpv_adam_tick": (c_int, [c_void_p, c_void_p]),
     "fpv_adam_update": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_float, c_float, c_float, c_float,

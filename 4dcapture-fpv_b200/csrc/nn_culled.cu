@@ -519,10 +519,10 @@ struct SphereParams {
     void *idx;
     int idx_bytes;
     unsigned long long *tiles_searched;
-    // fused-loss mode (template FUSED): nothing of size [batches][N] is written except the seeds.  Per batch the kernel
-    // accumulates the winners' distances (per-warp partial sums in double, reduced in fixed order afterwards) and, per
-    // winning candidate, the number of queries it won and the fixed-point sum of their coordinates -- everything the
-    // backward of  sum_j d(x_j, y_win(j))  needs:  d/dy_i = 2 (n_i y_i - S_i).  Integer atomics: order-independent.
+    // fused-loss mode (MODE 2): nothing of size [batches][N] is written except the winners (into the seed buffer).  Per
+    // batch the kernel accumulates the winners' distances (per-warp partial sums in double, reduced in fixed order
+    // afterwards); s2b_accum_kernel then builds, per winning candidate, the number of queries it won and the fixed-point
+    // sum of their coordinates -- everything the backward of  sum_j d(x_j, y_win(j))  needs:  d/dy_i = 2 (n_i y_i - S_i).
     double *sum_partial;          // [batches][groups]
     int64_t groups;               // query groups (warps) per batch
     unsigned long long *acc;      // [batches][M][4]: S_x, S_y, S_z (x * 2^fix_shift, two's complement), count
@@ -616,63 +616,13 @@ __device__ __forceinline__ bool sphere_search_tile(const float4 *__restrict__ xp
     return improved;
 }
 
-// FUSED epilogue for one row of 32 consecutive queries (one per lane): add every query's fixed-point coordinates and a
-// count to the accumulator of the candidate it picked.  Runs of equal winners over consecutive lanes are merged by a
-// segmented scan before touching memory; a row that picked one winner (the far field) costs four atomics in total.
-// Kept out of line so that its registers do not weigh on the traversal.
-__device__ __noinline__ void fused_row_accumulate(unsigned long long *accb, bool valid, int winner, float x, float y,
-                                                  float z, float fix_scale, const long long *rowsum, int lane) {
-    const int t = valid ? winner : (-1 - lane);  // an invalid lane is its own empty run
-    const int tp = __shfl_up_sync(0xffffffffu, t, 1);
-    const unsigned heads = __ballot_sync(0xffffffffu, lane == 0 || tp != t);
-    if (heads == 1u && t >= 0) {
-        if (lane == 0) {
-            atomicAdd(accb + 4 * int64_t(t) + 0, static_cast<unsigned long long>(rowsum[0]));
-            atomicAdd(accb + 4 * int64_t(t) + 1, static_cast<unsigned long long>(rowsum[1]));
-            atomicAdd(accb + 4 * int64_t(t) + 2, static_cast<unsigned long long>(rowsum[2]));
-            atomicAdd(accb + 4 * int64_t(t) + 3, 32ull);
-        }
-        return;
-    }
-    long long v0 = 0, v1 = 0, v2 = 0;
-    int cnt = 0;
-    if (valid) {
-        v0 = __float2ll_rn(__fmul_rn(x, fix_scale));
-        v1 = __float2ll_rn(__fmul_rn(y, fix_scale));
-        v2 = __float2ll_rn(__fmul_rn(z, fix_scale));
-        cnt = 1;
-    }
-    const int start = 31 - __clz(heads & (0xffffffffu >> (31 - lane)));
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        const long long u0 = __shfl_up_sync(0xffffffffu, v0, o), u1 = __shfl_up_sync(0xffffffffu, v1, o);
-        const long long u2 = __shfl_up_sync(0xffffffffu, v2, o);
-        const int uc = __shfl_up_sync(0xffffffffu, cnt, o);
-        if (lane - o >= start) {
-            v0 += u0;
-            v1 += u1;
-            v2 += u2;
-            cnt += uc;
-        }
-    }
-    const bool tail = lane == 31 || ((heads >> (lane + 1)) & 1u);
-    if (tail && t >= 0) {
-        atomicAdd(accb + 4 * int64_t(t) + 0, static_cast<unsigned long long>(v0));
-        atomicAdd(accb + 4 * int64_t(t) + 1, static_cast<unsigned long long>(v1));
-        atomicAdd(accb + 4 * int64_t(t) + 2, static_cast<unsigned long long>(v2));
-        atomicAdd(accb + 4 * int64_t(t) + 3, static_cast<unsigned long long>(cnt));
-    }
-}
-
-// MODE 0: distances + indices out.  MODE 1: fused accumulate in the kernel (FUSED).  MODE 2: only the winners (into the
-// in/out seed buffer, -1 for a query without a finite winner) and the per-warp distance sums; a separate streaming
-// kernel (s2b_accum_kernel) then builds the accumulators from the winners.
+// MODE 0: distances + indices out.  MODE 2: only the winners (into the in/out seed buffer, -1 for a query without a
+// finite winner) and the per-warp distance sums; a separate streaming kernel (s2b_accum_kernel) then builds the
+// accumulators of the fused loss from the winners (accumulating inside this kernel was measured: +5.3 ms).
 template <int TILE, int MINB, int MODE>
 __global__ void __launch_bounds__(CU_WARPS * 32, MINB) nn_sphere_kernel(const SphereParams p) {
-    constexpr bool FUSED = MODE == 1;
     constexpr int ST = TILE < 32 ? 32 : TILE;
     __shared__ __align__(16) float stile[CU_WARPS][3][ST];  // canonical fallback path only
-    __shared__ long long rowsum[FUSED ? CU_WARPS : 1][CU_QPT][3];  // FUSED: fixed-point coordinate sums of the warp's 4 rows
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int64_t group = int64_t(blockIdx.x) * CU_WARPS + warp;
     const int64_t q0 = group * CU_GROUP;
@@ -700,23 +650,6 @@ __global__ void __launch_bounds__(CU_WARPS * 32, MINB) nn_sphere_kernel(const Sp
                 big |= x2 > 1e30f;
             }
             canonical = __ballot_sync(0xffffffffu, big) != 0;
-            if (FUSED) {
-                // the queries are static across the frames of this CTA: the sum of a whole row of 32 consecutive
-                // queries is a constant, used whenever the row's queries all pick the same winner (the far field)
-#pragma unroll
-                for (int k = 0; k < CU_QPT; ++k) {
-                    const float c3[3] = {qx[k], qy[k], qz[k]};
-#pragma unroll
-                    for (int a = 0; a < 3; ++a) {
-                        const long long v = __float2ll_rn(__fmul_rn(c3[a], p.fix_scale));
-                        const int lo = int(v & 0x1FFFFF), mid = int((v >> 21) & 0x1FFFFF), hi = int(v >> 42);
-                        const long long slo = __reduce_add_sync(0xffffffffu, lo), smid = __reduce_add_sync(0xffffffffu, mid);
-                        const long long shi = __reduce_add_sync(0xffffffffu, hi);
-                        if (lane == 0) rowsum[warp][k][a] = slo + (smid << 21) + (shi << 42);
-                    }
-                }
-                __syncwarp();
-            }
         }
         const float *planes = p.planes + int64_t(b) * p.plane_bstride;
         const float4 *tab = p.table + int64_t(b) * p.table_bstride;
@@ -900,23 +833,6 @@ __global__ void __launch_bounds__(CU_WARPS * 32, MINB) nn_sphere_kernel(const Sp
                     dsum += double(best[k]);
                     p.seed[int64_t(b) * p.N + qi] = best[k] < CUDART_INF_F ? bidx[k] : -1;
                 }
-            }
-            dsum = warp_sum(dsum);  // fixed shuffle tree: deterministic
-            if (lane == 0) p.sum_partial[int64_t(b) * p.groups + group] = dsum;
-        } else if (FUSED) {
-            unsigned long long *accb = p.acc + int64_t(b) * p.M * 4;
-            double dsum = 0.0;
-#pragma unroll
-            for (int k = 0; k < CU_QPT; ++k) {
-                const int64_t qi = q0 + k * 32 + lane;
-                const bool inb = qi < p.N;
-                if (inb) {
-                    dsum += double(best[k]);
-                    if (p.seed != nullptr) p.seed[int64_t(b) * p.N + qi] = bidx[k];
-                }
-                // a query without a finite winner contributes no gradient
-                fused_row_accumulate(accb, inb && best[k] < CUDART_INF_F, bidx[k], qx[k], qy[k], qz[k], p.fix_scale,
-                                     &rowsum[warp][k][0], lane);
             }
             dsum = warp_sum(dsum);  // fixed shuffle tree: deterministic
             if (lane == 0) p.sum_partial[int64_t(b) * p.groups + group] = dsum;
@@ -1410,7 +1326,6 @@ int fpv_nn_sphere_table(const float *planes, int64_t batches, int64_t M, int til
 }
 
 static int g_sphere_ctas_per_sm = 512;
-static int g_fused_variant = 2;  // 1: accumulate inside the search kernel; 2: winners only + a separate streaming accumulate
 
 /* Frame chunking of the temporally seeded sphere search: the grid is sized to about ctas_per_sm CTAs per SM
  * (more CTAs = better load balance over the heavy-tailed per-group cost, but every chunk pays one unseeded frame). */
@@ -1480,12 +1395,7 @@ static int sphere_search_impl(const float *queries, int q_shared, int64_t batche
         profile_begin(nm, st, 12.0 * double(q_shared ? N : batches * N) + 12.0 * double(M) * double(batches) + out_bytes,
                       double(batches * N) * double(M));
     }
-    if (fused && g_fused_variant == 1) {
-        if (tile == 16)
-            nn_sphere_kernel<16, 8, 1><<<grid, CU_WARPS * 32, 0, st>>>(p);
-        else
-            nn_sphere_kernel<32, 8, 1><<<grid, CU_WARPS * 32, 0, st>>>(p);
-    } else if (fused) {
+    if (fused) {
         if (tile == 16)
             nn_sphere_kernel<16, 8, 2><<<grid, CU_WARPS * 32, 0, st>>>(p);
         else
@@ -1565,7 +1475,7 @@ int fpv_nn_sphere_fused(const float *queries, int64_t batches, int64_t N, const 
     int rc = sphere_search_impl(queries, 1, batches, N, planes, table, orig_idx, pos_of, pos_shared, seed_inout, seed_valid, M, tile,
                                 0, nullptr, nullptr, 4, tiles_searched, partial, acc, fix_shift, st);
     if (rc) return rc;
-    if (g_fused_variant != 1) {
+    {
         dim3 grid((unsigned)ceil_div(N, 256 * S2B_ROWS), (unsigned)batches);
         if (profile_on()) {
             char nm[48];
@@ -1581,13 +1491,6 @@ int fpv_nn_sphere_fused(const float *queries, int64_t batches, int64_t N, const 
     }
     sphere_sum_kernel<<<(unsigned)batches, 256, 0, st>>>(partial, groups, sum_d);
     FPV_LAUNCH_CHECK("sphere_sum_kernel");
-    return FPV_OK;
-}
-
-/* Tuning hook: 1 = accumulate inside the search kernel, 2 (default) = winners only + a separate streaming accumulate. */
-int fpv_nn_sphere_fused_variant(int variant) {
-    FPV_CHECK_ARG(variant == 1 || variant == 2, "fpv_nn_sphere_fused_variant: 1 or 2");
-    g_fused_variant = variant;
     return FPV_OK;
 }
 

@@ -167,7 +167,6 @@ int fpv_nn_sphere_fused(const float *queries, int64_t batches, int64_t N, const 
                         int seed_valid, int64_t M, int tile, int fix_shift, float *sum_d, unsigned long long *acc,
                         unsigned long long *tiles_searched, void *workspace, size_t workspace_bytes,
                         fpv_stream_t stream);
-int fpv_nn_sphere_fused_variant(int variant); /* tuning: 1 = accumulate inside the search kernel, 2 = separate pass */
 int fpv_scene2body_grad(const float *cand, const unsigned long long *acc, int fix_shift, const float *g,
                         int64_t batches, int64_t M, float *grad, int accumulate, fpv_stream_t stream);
 
