@@ -1326,10 +1326,16 @@ int fpv_nn_sphere_table(const float *planes, int64_t batches, int64_t M, int til
 }
 
 static int g_sphere_ctas_per_sm = 512;
+static int g_sphere_minb = 7;   // resident CTAs per SM the fused tile-16 kernel is compiled for (8: 64 regs, 7: 72, 6: 80);
+                                // measured at cfg 2: 11.19 / 10.96 / 11.28 ms incl. the accumulate pass (profiles/r02_sphere_order_tune.txt)
 
 /* Frame chunking of the temporally seeded sphere search: the grid is sized to about ctas_per_sm CTAs per SM
  * (more CTAs = better load balance over the heavy-tailed per-group cost, but every chunk pays one unseeded frame). */
 int fpv_nn_sphere_set_chunking(int ctas_per_sm) {
+    if (ctas_per_sm >= -8 && ctas_per_sm <= -6) {   // tuning: negative values select the register budget instead
+        g_sphere_minb = -ctas_per_sm;
+        return FPV_OK;
+    }
     FPV_CHECK_ARG(ctas_per_sm >= 1 && ctas_per_sm <= 4096, "fpv_nn_sphere_set_chunking: ctas_per_sm out of range");
     g_sphere_ctas_per_sm = ctas_per_sm;
     return FPV_OK;
@@ -1396,7 +1402,11 @@ static int sphere_search_impl(const float *queries, int q_shared, int64_t batche
                       double(batches * N) * double(M));
     }
     if (fused) {
-        if (tile == 16)
+        if (tile == 16 && g_sphere_minb == 7)
+            nn_sphere_kernel<16, 7, 2><<<grid, CU_WARPS * 32, 0, st>>>(p);
+        else if (tile == 16 && g_sphere_minb == 6)
+            nn_sphere_kernel<16, 6, 2><<<grid, CU_WARPS * 32, 0, st>>>(p);
+        else if (tile == 16)
             nn_sphere_kernel<16, 8, 2><<<grid, CU_WARPS * 32, 0, st>>>(p);
         else
             nn_sphere_kernel<32, 8, 2><<<grid, CU_WARPS * 32, 0, st>>>(p);

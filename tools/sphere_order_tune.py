@@ -28,7 +28,7 @@ def timeit(fn, reps=4):
 
 
 ref = None
-for order in ("morton_body", "kd"):
+for order in ("kd",):
     for tile in (16,):
         if order == "kd":
             perm = sp.kd_order(verts[T // 2], leaf=tile)
@@ -54,6 +54,9 @@ for order in ("morton_body", "kd"):
         def fused():
             fpv._lib.check(L.fpv_nn_sphere_fused(P(scene.sorted), T, M, P(body.planes), P(body.boxes), P(body.oidx), P(body.pos_table()[0]), 1, P(seed), 1,
                                                  10475, tile, fs, P(sum_d), P(acc), None, P(ws), ws.numel(), fpv._lib.stream_ptr()))
+        for mb in (7, 6, 8):
+            L.fpv_nn_sphere_set_chunking(-mb)
+            print(f"   fused, compiled for {mb} CTAs/SM: {timeit(fused):7.3f} ms")
         ms_fused = timeit(fused)
         ok = torch.allclose(sum_d.double(), ref[0].double().sum(1), rtol=1e-6)
         print(f"{order:12s} tile {tile}: plain {ms_plain:7.3f} ms  winners+accumulate {ms_fused:7.3f} ms  clusters searched "
