@@ -45,6 +45,7 @@ class SearchOptions:
                   "tc"      tensor-core filter over all vertices (nn_tc.cu)
       carry_seeds start both searches from the previous call's winners (hints; never change a result)
       body_shared_order  clip=True batches: one ordering for all frames, computed once and kept in the SearchState
+      overlap     run the (short) body -> scene branch of a fused step on a second stream, next to the scene -> body search
       body_order  that ordering: "kd" (balanced k-d partition aligned with the sphere hierarchy, built once on the host:
                   clusters less than half as wide as along a Morton curve) or "morton" """
     engine: str = "auto"
@@ -54,6 +55,7 @@ class SearchOptions:
     body_shared_order: bool = True
     body_order: str = "kd"
     spatial_min_points: int = 4096
+    overlap: bool = True
 
     def __post_init__(self):
         if self.engine not in ("auto", "brute", "spatial"):
@@ -74,12 +76,14 @@ class SearchState:
       seeds      (direction, T, N) -> int32 winners of the last search (in/out buffers of the kernels)
       body_perm  (N, device) -> frozen Morton ordering of a clip's body (the clusters are fixed vertex sets, their
                  spheres are rebuilt from the actual positions every call)
-      stats      device counters of the last call (tiles / clusters searched)"""
+      stats      device counters of the last call (tiles / clusters searched)
+      streams    the second stream on which a fused step runs its body -> scene branch"""
 
     def __init__(self):
         self.seeds: Dict[tuple, torch.Tensor] = {}
         self.body_perm: Dict[tuple, torch.Tensor] = {}
         self.stats: Dict[str, torch.Tensor] = {}
+        self.streams: Dict[int, torch.cuda.Stream] = {}     # side stream of the overlapped body -> scene branch, per device
 
     def seed_buffer(self, direction: str, T: int, n: int, device, enabled: bool) -> Tuple[Optional[torch.Tensor], bool]:
         """(buffer, valid): the in/out seed buffer of one search direction; valid = it holds a previous call's winners."""
@@ -143,18 +147,61 @@ def _body_cloud(a_c: torch.Tensor, scene: spatial.SortedCloud, opts: SearchOptio
     return cloud
 
 
-def _search_a2b(a_c, b_c, scene, body, idx_dtype, idx_base, opts, state):
-    """body vertex -> scene point: the scene is static; its Morton tiles + boxes are built once and the box-culled search
-    with a per-query box test visits well under 1 % of it.  Returns (d [T,N], i [T,N]) in the ORIGINAL vertex order."""
-    T, N, _ = a_c.shape
-    dev = a_c.device
-    stats = torch.zeros(1, dtype=torch.int64, device=dev)
+class _SideBranch:
+    """Runs the body -> scene branch of a step on a second stream so that it overlaps the (much longer) scene -> body
+    search: `with branch:` forks from the current stream and switches to the side stream; `branch.join()` makes the
+    current stream wait for it.  Everything the branch writes is allocated BEFORE the fork, on the caller's stream (the
+    caching allocator then needs no cross-stream bookkeeping); the fork / join are plain event waits, which a CUDA
+    graph capture records as parallel branches."""
+
+    def __init__(self, state: "SearchState", device, enabled: bool = True):
+        self.cur = torch.cuda.current_stream(device)
+        self.side = None
+        if enabled:
+            self.side = state.streams.get(device.index)
+            if self.side is None:
+                self.side = state.streams[device.index] = torch.cuda.Stream(device)
+        self._ctx = None
+
+    def __enter__(self):
+        if self.side is not None:
+            self.side.wait_stream(self.cur)
+            self._ctx = torch.cuda.stream(self.side)
+            self._ctx.__enter__()
+        return self
+
+    def __exit__(self, *exc):
+        if self._ctx is not None:
+            self._ctx.__exit__(*exc)
+            self._ctx = None
+        return False
+
+    def join(self):
+        if self.side is not None:
+            self.cur.wait_stream(self.side)
+
+
+def _a2b_alloc(T, N, idx_dtype, dev, opts, state, want_keys: bool = True):
+    """Everything the body -> scene branch writes, allocated on the caller's stream:
+    (keys or None, d, i, stats, seed buffer, seed_valid)."""
+    keys = torch.empty(T * N, dtype=torch.int64, device=dev) if want_keys else None
     # winners of the previous call, per sorted query position (the order of the body is frozen for a clip; otherwise a
     # misplaced seed is still a nearby scene point)
     seed, seed_valid = state.seed_buffer("a2b", T, N, dev, opts.carry_seeds)
-    keys = spatial.culled_search_keys(body.sorted, T, scene, idx_base=idx_base, stats=stats, cand_orig=b_c, seed=seed,
-                                      seed_valid=seed_valid)
-    d, i = spatial.min_unpack(keys, 1, T * N, N, body.perm_row(), idx_dtype)
+    return (keys, torch.empty(T * N, dtype=torch.float32, device=dev), torch.empty(T * N, dtype=idx_dtype, device=dev),
+            torch.zeros(1, dtype=torch.int64, device=dev), seed, seed_valid)
+
+
+def _search_a2b(a_c, b_c, scene, body, idx_dtype, idx_base, opts, state, bufs=None):
+    """body vertex -> scene point: the scene is static; its tiles + boxes are built once and the box-culled search
+    with a per-query box test visits well under 1 % of it.  Returns (d [T,N], i [T,N]) in the ORIGINAL vertex order.
+    bufs: outputs pre-allocated by _a2b_alloc (required when called inside a _SideBranch)."""
+    T, N, _ = a_c.shape
+    dev = a_c.device
+    keys, d, i, stats, seed, seed_valid = bufs if bufs is not None else _a2b_alloc(T, N, idx_dtype, dev, opts, state)
+    spatial.culled_search_keys(body.sorted, T, scene, idx_base=idx_base, stats=stats, cand_orig=b_c, seed=seed,
+                               seed_valid=seed_valid, out=keys)
+    spatial.min_unpack(keys, 1, T * N, N, body.perm_row(), out=(d, i))
     state.stats["tiles_searched"] = stats
     return d.view(T, N), i.view(T, N)
 
@@ -483,8 +530,13 @@ class _FusedTermsFn(torch.autograd.Function):
         body = _body_cloud(a_c, scene, opts, state, clip, spheres=True)
         M = scene.M
         d_a2b = i_a2b = None
+        branch = None
         if want_a2b:
-            d_a2b, i_a2b = _search_a2b(a_c, b_c, scene, body, idx_dtype, 0, opts, state)
+            # the body -> scene branch overlaps the scene -> body search on a second stream
+            bufs = _a2b_alloc(T, N, idx_dtype, dev, opts, state)          # (allocated on this stream, before the fork)
+            branch = _SideBranch(state, dev, opts.overlap)
+            with branch:
+                d_a2b, i_a2b = _search_a2b(a_c, b_c, scene, body, idx_dtype, 0, opts, state, bufs)
         seed, seed_valid = state.seed_buffer("b2a", T, M, dev, True)     # the seeds are this op's only [T,M] array
         stats = torch.zeros(2, dtype=torch.int64, device=dev)
         sum_d = torch.empty(T, dtype=torch.float32, device=dev)
@@ -498,6 +550,8 @@ class _FusedTermsFn(torch.autograd.Function):
                                              body.sphere_tile, fix_shift, _lib.ptr(sum_d), _lib.ptr(acc), _lib.ptr(stats),
                                              _lib.ptr(ws), ws.numel(), _lib.stream_ptr()), "fpv_nn_sphere_fused")
         state.stats["tiles_searched_b2a"] = stats
+        if branch is not None:
+            branch.join()
         ctx.save_for_backward(a_c, b_c, acc, i_a2b)
         ctx.fix_shift = fix_shift
         ctx.idx_bytes = 8 if idx_dtype == torch.int64 else 4

@@ -104,14 +104,15 @@ class Mailbox:
                                          ctypes.c_void_p(self.base + _OFF_ERROR), self.timeout_s, _lib.stream_ptr()),
                        "fpv_p2p_barrier")
 
-    def combine_keys(self, n: int, row: int, perm_row, idx_dtype=torch.int32):
+    def combine_keys(self, n: int, row: int, perm_row, idx_dtype=torch.int32, out=None):
         """barrier, then min over the slots of the local mailbox -> (dist [n], idx [n]) un-permuted row by row."""
         from . import spatial
         if n > self.key_cap:
             raise RuntimeError(f"p2p.Mailbox: {n} keys exceed the capacity {self.key_cap}")
         self.barrier()
         return spatial.min_unpack(self.base + self.keys_off, self.world, n, row, perm_row, idx_dtype, device=self.device,
-                                  slot_stride=self.key_cap, half_stride=self.keys_half, parity=self.parity_keys, flip=True)
+                                  slot_stride=self.key_cap, half_stride=self.keys_half, parity=self.parity_keys, flip=True,
+                                  out=out)
 
     def allreduce_sum(self, flat: torch.Tensor) -> torch.Tensor:
         """Sum of a small float32 vector over the ranks, in rank order (same bits on every rank).  Returns a new tensor."""

@@ -75,6 +75,7 @@ class _ShardedChamferFn(torch.autograd.Function):
         ctx.fused = bool(fused)
         ctx.fix_shift = 0
         acc = None
+        branch = None
         if search is not None:  # injected search (CPU oracle in the gloo tests): same combine logic, no CUDA
             if fused:
                 raise RuntimeError("the fused scene->body form needs the CUDA path")
@@ -94,20 +95,25 @@ class _ShardedChamferFn(torch.autograd.Function):
                 if state is None:
                     state = chamfer._default_state(scene, T, N)
                 body = chamfer._body_cloud(a_c, scene, opts, state, clip, spheres=True)
-                stats = torch.zeros(1, dtype=torch.int64, device=dev)
-                seed, seed_valid = state.seed_buffer("a2b", T, N, dev, opts.carry_seeds)
-                if comm is not None and ws > 1:
-                    # keys go from the search epilogue into slot `rank` of every mailbox; barrier; local min
-                    spatial.culled_search_keys(body.sorted, T, scene, idx_base=idx_base, stats=stats, cand_orig=b_c,
-                                               seed=seed, seed_valid=seed_valid, keys=comm.key_slot(comm.rank, comm.rank),
-                                               push=comm.push_targets(), push_parity=comm.parity_keys,
-                                               push_half=comm.keys_half)
-                    d_a2b, i_a2b = comm.combine_keys(T * N, N, body.perm_row(), torch.int64)
-                else:
-                    keys = spatial.culled_search_keys(body.sorted, T, scene, idx_base=idx_base, stats=stats, cand_orig=b_c,
-                                                      seed=seed, seed_valid=seed_valid)
-                    combine_keys(keys, group)
-                    d_a2b, i_a2b = spatial.min_unpack(keys, 1, T * N, N, body.perm_row(), torch.int64)
+                # body -> scene branch (search with the key epilogue, exchange, combine) on a second stream: it overlaps
+                # the scene -> body search, and so does the wait for the slowest rank at its barrier
+                use_box = comm is not None and ws > 1
+                keys, d_a2b, i_a2b, stats, seed, seed_valid = chamfer._a2b_alloc(T, N, torch.int64, dev, opts, state,
+                                                                                 want_keys=not use_box)
+                branch = chamfer._SideBranch(state, dev, opts.overlap and (use_box or ws == 1))
+                with branch:
+                    if use_box:
+                        # keys go from the search epilogue into slot `rank` of every mailbox; barrier; local min
+                        spatial.culled_search_keys(body.sorted, T, scene, idx_base=idx_base, stats=stats, cand_orig=b_c,
+                                                   seed=seed, seed_valid=seed_valid, keys=comm.key_slot(comm.rank, comm.rank),
+                                                   push=comm.push_targets(), push_parity=comm.parity_keys,
+                                                   push_half=comm.keys_half)
+                        comm.combine_keys(T * N, N, body.perm_row(), out=(d_a2b, i_a2b))
+                    else:
+                        spatial.culled_search_keys(body.sorted, T, scene, idx_base=idx_base, stats=stats, cand_orig=b_c,
+                                                   seed=seed, seed_valid=seed_valid, out=keys)
+                        combine_keys(keys, group)
+                        spatial.min_unpack(keys, 1, T * N, N, body.perm_row(), out=(d_a2b, i_a2b))
                 d_a2b, i_a2b = d_a2b.view(T, N), i_a2b.view(T, N)
                 state.stats["tiles_searched"] = stats
                 if fused:
@@ -141,6 +147,8 @@ class _ShardedChamferFn(torch.autograd.Function):
                 d_b2a, i_b2a = chamfer._nn_search_raw(b_c, True, T, Ms, planes_a, T, N, torch.int64)
                 combine_keys(keys, group)
                 d_a2b, i_a2b = chamfer.unpack_keys(keys, torch.int64)
+        if branch is not None:
+            branch.join()
         ctx.save_for_backward(a_c, b_c, i_b2a, i_a2b, acc)
         ctx.idx_base, ctx.world, ctx.search = idx_base, ws, search
         ctx.mark_non_differentiable(*[t for t in (i_b2a, i_a2b) if t is not None])

@@ -237,7 +237,7 @@ def culled_search(queries_grouped: torch.Tensor, q_shared: bool, batches: int, c
 def culled_search_keys(queries_grouped: torch.Tensor, batches: int, cloud: SortedCloud, idx_base: int = 0,
                        stats: torch.Tensor = None, cand_orig: torch.Tensor = None, seed: torch.Tensor = None,
                        seed_valid: bool = False, keys: torch.Tensor = None, push=None, push_parity=None,
-                       push_half: int = 0) -> torch.Tensor:
+                       push_half: int = 0, out: torch.Tensor = None) -> torch.Tensor:
     """Box-culled search of [batches,N,3] grouped queries against ONE sorted cloud, with the packed-key epilogue:
     returns int64 keys [batches*N] = float_bits(d) << 32 | (idx_base + original index), in the QUERY order given.
     keys (optional): the destination, e.g. this rank's slot of a p2p mailbox (a raw device address as int); push: raw
@@ -246,9 +246,9 @@ def culled_search_keys(queries_grouped: torch.Tensor, batches: int, cloud: Sorte
     q = queries_grouped.contiguous()
     N = q.shape[1]
     dev = q.device
-    out = None
     if keys is None:
-        out = torch.empty(batches * N, dtype=torch.int64, device=dev)
+        if out is None:
+            out = torch.empty(batches * N, dtype=torch.int64, device=dev)
         keys_ptr = _lib.ptr(out)
     else:
         keys_ptr = ctypes.c_void_p(int(keys))
@@ -266,9 +266,10 @@ def culled_search_keys(queries_grouped: torch.Tensor, batches: int, cloud: Sorte
 
 
 def min_unpack(slots, world: int, n: int, row: int, perm_row, idx_dtype=torch.int32, device=None, slot_stride: int = 0,
-               half_stride: int = 0, parity=None, flip: bool = False):
+               half_stride: int = 0, parity=None, flip: bool = False, out=None):
     """Element-wise minimum over `world` key slots, unpacked to (dist [n], idx [n]) and un-permuted row by row.
-    slots: an int64 tensor (world == 1: plain keys) or a raw device address (a p2p mailbox)."""
+    slots: an int64 tensor (world == 1: plain keys) or a raw device address (a p2p mailbox).  out: optional
+    pre-allocated (dist, idx) -- callers that launch on a side stream allocate on their own stream first."""
     L = _lib.lib()
     if isinstance(slots, torch.Tensor):
         device = slots.device
@@ -276,8 +277,12 @@ def min_unpack(slots, world: int, n: int, row: int, perm_row, idx_dtype=torch.in
     else:
         slots_ptr = ctypes.c_void_p(int(slots))
     perm, batched = perm_row if perm_row is not None else (None, False)
-    dist = torch.empty(n, dtype=torch.float32, device=device)
-    idx = torch.empty(n, dtype=idx_dtype, device=device)
+    if out is not None:
+        dist, idx = out
+        idx_dtype = idx.dtype
+    else:
+        dist = torch.empty(n, dtype=torch.float32, device=device)
+        idx = torch.empty(n, dtype=idx_dtype, device=device)
     with torch.cuda.device(device):
         _lib.check(L.fpv_p2p_min_unpack(slots_ptr, world, int(slot_stride), int(half_stride),
                                         ctypes.c_void_p(int(parity)) if parity else None, int(flip), n, row,
