@@ -35,7 +35,15 @@ def load_smplx_npz(path: str, num_betas: int = 10, num_expression_coeffs: int = 
     """Read a real SMPL-X model file into the canonical constant layout ([3P] smplx.body_models.SMPLX.__init__)."""
     d = np.load(path, allow_pickle=True)
     shapedirs = np.asarray(d["shapedirs"], np.float64)
-    sd = np.concatenate([shapedirs[:, :, :num_betas], shapedirs[:, :, 300:300 + num_expression_coeffs]], -1)
+    # expression directions: columns 300.. of the 400-column SMPL-X v1.1 files; SMPL-X v1.0 files carry only 20 columns
+    # (10 shape + 10 expression) and the smplx package then reads the expression part from column 10 on
+    expr_start = 300 if shapedirs.shape[-1] >= 300 + num_expression_coeffs else 10
+    n_expr = min(num_expression_coeffs, shapedirs.shape[-1] - expr_start)
+    if n_expr <= 0:
+        raise RuntimeError(f"load_smplx_npz: shapedirs has {shapedirs.shape[-1]} columns, no expression directions found")
+    sd = np.concatenate([shapedirs[:, :, :num_betas], shapedirs[:, :, expr_start:expr_start + n_expr]], -1)
+    if sd.shape[-1] < num_betas + num_expression_coeffs:     # pad missing expression directions with zeros
+        sd = np.concatenate([sd, np.zeros(sd.shape[:2] + (num_betas + num_expression_coeffs - sd.shape[-1],))], -1)
     posedirs = np.asarray(d["posedirs"], np.float64)
     posedirs = posedirs.reshape(-1, posedirs.shape[-1]).T                      # [486, 3V]
     parents = np.asarray(d["kintree_table"])[0].astype(np.int64)

@@ -101,3 +101,33 @@ def test_formats_match_reference_functions():
         assert np.array_equal(io.qvec2rotmat(q), R)
     frame = {k[len("frame_"):]: d[k] for k in d.files if k.startswith("frame_")}
     assert np.array_equal(io.body_params_parse(frame), d["row"])
+
+
+def test_load_smplx_npz_v10_and_v11_layouts(tmp_path):
+    """body_model.load_smplx_npz reads both shapedirs layouts of the real model files: 400 columns (v1.1: expression
+    directions from column 300) and 20 columns (v1.0: 10 shape + 10 expression, what the smplx package falls back to)."""
+    import numpy as np
+    import torch
+    from conftest import load_pkg
+    fpv = load_pkg()
+    V = 64
+    c = fpv.synthetic.make_body_constants(5, V)
+    rng = np.random.default_rng(0)
+    base = dict(v_template=c["v_template"].numpy(), posedirs=c["posedirs"].numpy().T.reshape(V, 3, 486),
+                J_regressor=c["J_regressor"].numpy(), weights=c["lbs_weights"].numpy(),
+                kintree_table=np.stack([np.array([2 ** 32 - 1] + c["parents"].tolist()[1:]), np.arange(55)]).astype(np.int64),
+                hands_componentsl=rng.standard_normal((45, 45)), hands_componentsr=rng.standard_normal((45, 45)),
+                hands_meanl=rng.standard_normal(45), hands_meanr=rng.standard_normal(45))
+    sd400 = rng.standard_normal((V, 3, 400))
+    sd20 = np.concatenate([sd400[:, :, :10], sd400[:, :, 300:310]], -1)
+    out = {}
+    for tag, sd in (("v11", sd400), ("v10", sd20)):
+        path = tmp_path / f"SMPLX_{tag}.npz"
+        np.savez(path, shapedirs=sd, **base)
+        k = fpv.load_smplx_npz(str(path))
+        assert k["shapedirs"].shape == (V, 3, 20) and k["posedirs"].shape == (486, 3 * V)
+        assert k["lh_components"].shape == (12, 45) and int(k["parents"][0]) == -1
+        out[tag] = k
+        fpv.create(str(path), batch_size=2)          # the module accepts the constants (CPU construction only)
+    assert torch.equal(out["v10"]["shapedirs"], out["v11"]["shapedirs"])
+    np.testing.assert_allclose(out["v11"]["shapedirs"][:, :, 10:].numpy(), sd400[:, :, 300:310].astype(np.float32))
