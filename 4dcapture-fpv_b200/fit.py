@@ -125,8 +125,14 @@ class FitProblem:
         shard_frames (sharded runs over the mailbox): the per-frame part of the step -- front-end, body model, world
         placement and their backward -- runs on T / world frames per rank; the vertices are all-gathered through the
         mailbox (backward: reduce-scatter of the vertex gradient), so only the searches' fixed costs stay replicated."""
-        if mode not in ("global", "local"):
-            raise RuntimeError("FitProblem: mode must be 'global' (cal_loss) or 'local' (cal_loss2)")
+        if mode not in ("global", "local", "reference"):
+            raise RuntimeError("FitProblem: mode must be 'global' (cal_loss, both chamfer directions), 'local' (cal_loss2) "
+                               "or 'reference' (the literal call sequence of cal_loss)")
+        self.literal = mode == "reference"
+        if self.literal:
+            if world_size != 1 or clips != 1:
+                raise RuntimeError("FitProblem: mode 'reference' is single-rank, single-clip (like the reference)")
+            mode = "global"
         if T % clips != 0:
             raise RuntimeError("FitProblem: T must be a multiple of clips")
         self.T, self.M, self.device = T, M, torch.device(device)
@@ -289,9 +295,34 @@ class FitProblem:
             joints = full[:, V * 3:].reshape(self.T, 23, 3)
         return verts, joints, extra_losses
 
+    def forward_reference(self) -> Dict[str, torch.Tensor]:
+        """The reference's LITERAL call sequence (FittingOP.cal_loss, global_optimization.py:249-312, and the first-stage
+        loss of fitting(mode='global'), :570): the scene as the materialised .repeat(T,1,1) copy of :176, the contact
+        term through ext.chamferDist()(contact_verts.contiguous(), s_verts_batch.contiguous()) with its second value
+        discarded (:290-294), every term of cal_loss computed, loss = 0.1 contact + smoothing + rec."""
+        p = self.params
+        verts, joints, extra = self._body()
+        if not hasattr(self, "s_verts_batch"):
+            self.s_verts_batch = self.scene.repeat(self.T, 1, 1)                                   # :175-176
+        body_verts_contact_batch = verts[:, self.contact_ids, :]                                   # :290
+        contact_dist, _ = chamfer.chamferDist()(body_verts_contact_batch.contiguous(), self.s_verts_batch.contiguous())
+        losses = {
+            "rec": torch.mean(torch.abs(self.data - p)),                                           # :259
+            "vposer": extra.get("vposer", p.new_zeros(())),                                        # :262-263
+            "smoothing": residuals.second_diff_l1(p),                                              # :266-267
+            "contact": residuals.contact_robust_loss(contact_dist),                                # :295
+            "world_smoothing": residuals.first_diff_l1(joints),                                    # :304
+        }
+        if self.front_end and self.dct_batches:
+            losses["dct"] = self._dct(joints)                                                      # :310
+        losses["total"] = 0.1 * losses["contact"] + losses["smoothing"] + losses["rec"]           # :570
+        return losses
+
     def forward(self) -> Dict[str, torch.Tensor]:
         if self.mode == "local":
             return self.forward_local()
+        if self.literal:
+            return self.forward_reference()
         p, W = self.params, LOSS_WEIGHTS
         inv_world = 1.0 / self.world
         verts, joints, extra_losses = self._body()

@@ -319,6 +319,25 @@ def run_b200(args):
                       "ms_per_step": ms_local / K, "steps_per_s": K / (ms_local * 1e-3),
                       "algorithmic_bytes_per_step": bytes_local,
                       "achieved_GBps": bytes_local / (ms_local / K * 1e-3) / 1e9}
+    # ---- the reference's literal call sequence (dist1 only on the contact vertices, .repeat(T,1,1) scene) ----
+    literal_info = None
+    if world == 1 and not args.no_local and args.clips == 1:
+        rp = pkg.FitProblem(T=args.T, M=args.M, device=dev, seed=1235, front_end=not args.no_front_end, mode="reference",
+                            scene_kind=args.scene, scene_order=args.scene_order)
+        for _ in range(W):
+            rp.step(update=True)
+        try:
+            rp.capture(update=True)
+            ms_lit, _ = timed(rp.step_graph, K)
+            launch = "cuda graph replay"
+        except Exception:
+            ms_lit, _ = timed(lambda: rp.step(update=True), K)
+            launch = "eager"
+        literal_info = {"step": "FittingOP.cal_loss as written (global_optimization.py:249-312): ext.chamferDist()(contact_verts, "
+                                "s_verts_batch.repeat(T,1,1)) with dist2 discarded, loss = 0.1 contact + smoothing + rec (:570), "
+                                "backward, Adam", "launch": launch, "contact_vertices": int(rp.contact_ids.numel()),
+                        "ms_per_step": ms_lit / K, "steps_per_s": K / (ms_lit * 1e-3)}
+        del rp
     if rank != 0:
         prob.close()
         if world > 1:
@@ -383,6 +402,7 @@ def run_b200(args):
                                      "eager_drifting_adam": ms_drift / K,
                                      "graph_drifting_adam": graph_info.get("ms_per_step") if graph_info else None},
         "local_mode": local_info,
+        "reference_literal_step": literal_info,
     }
     if graph_info and "steps_per_s" in graph_info:
         # headline = the captured drifting step; keep the eager measurements alongside

@@ -215,3 +215,29 @@ def test_batched_clips_equal_independent_clips(fpv, cuda_dev):
     big.capture(update=True)
     a = big.step_graph().item()
     assert np.isfinite(a)
+
+
+def test_reference_literal_call_sequence(fpv, cuda_dev):
+    """mode='reference': cal_loss as written -- repeated scene (:176), chamferDist on the contact vertices with dist2
+    discarded (:290-294), loss of :570 -- against the float64 assembly; the repeated scene must take the indexed path."""
+    prob = fpv.FitProblem(T=5, M=9000, device=cuda_dev, seed=1243, front_end=True, dct_frames=2, mode="reference")
+    loss = prob.step()
+    assert prob.s_verts_batch.shape == (5, 9000, 3) and prob.s_verts_batch.stride(0) == 27000     # a real copy
+    p = prob.params.detach().cpu().double().requires_grad_(True)
+    scale = prob.scale.detach().cpu().double().requires_grad_(True)
+    cam = prob.camera_ext.detach().cpu().double()
+    r75 = po.convert_to_3D_rot(p)
+    wd = {k: getattr(prob.vposer, k).detach().cpu().double() for k in ("w1", "b1", "w2", "b2", "w3", "b3")}
+    b2w = ro.body2world(r75[:, 72:75], scale, cam)
+    v, _ = so.smplx_forward(prob.constants, betas=r75[:, 6:16], global_orient=r75[:, 3:6],
+                            body_pose=po.vposer_decode_aa(wd, r75[:, 16:48]).view(5, -1), transl=r75[:, 0:3],
+                            left_hand_pose=r75[:, 48:60], right_hand_pose=r75[:, 60:72], dtype=torch.float64)
+    verts = ro.verts_transform(v * scale, b2w)
+    cv = verts[:, prob.contact_ids.cpu()]
+    scene = prob.host_scene.double()
+    _, _, _, i_a2b = co.dist_chamfer(cv.detach().float().numpy(), prob.host_scene.numpy())
+    d = ((cv - scene[torch.tensor(i_a2b)]) ** 2).sum(-1)
+    total = 0.1 * ro.contact_robust_loss(d) + ro.second_diff_l1(p) + torch.mean(torch.abs(prob.data.cpu().double() - p))
+    total.backward()
+    assert loss.item() == pytest.approx(total.item(), rel=1e-5)
+    _check_grads([(prob.params.grad, p.grad, "params"), (prob.scale.grad, scale.grad, "scale")])
