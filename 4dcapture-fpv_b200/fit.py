@@ -142,6 +142,7 @@ class FitProblem:
         self.mode, self.fused = mode, bool(fused)
         self.options = options or chamfer.DEFAULT_OPTIONS
         self.search_state = chamfer.SearchState()          # seeds, frozen body order: per problem, never global
+        self.report_terms = False                          # forward() also returns the individual (scaled) loss terms
         constants = make_body_constants(seed)
         self.constants = constants
         self.shard_frames = bool(shard_frames and world_size > 1 and comm == "p2p" and mode == "global"
@@ -149,6 +150,9 @@ class FitProblem:
         self.frame_ranges = [sharded.shard_range(T, world_size, r) for r in range(world_size)]
         self.f0, self.f1 = self.frame_ranges[rank] if self.shard_frames else (0, T)
         self.model = SMPLXB200(constants, batch_size=self.f1 - self.f0).to(self.device)
+        # the module's own default parameters (jaw / eye poses, expression: zeros the loop never optimises, :154-168) get no
+        # gradient: otherwise every backward splits and accumulates four more slices into buffers nobody reads
+        self.model.requires_grad_(False)
         parts = [make_clip_params(self.Tc, seed + 1000 * c) for c in range(clips)]
         clip = {k: (torch.cat([p[k] for p in parts]) if parts[0][k].dim() > 0 else parts[0][k]) for k in parts[0]}
         self.front_end = front_end
@@ -336,18 +340,29 @@ class FitProblem:
         else:
             s_b2a, d_a2b, _, _ = chamfer.distChamfer(verts, self.scene, idx_dtype=self.idx_dtype, clip=True,
                                                      options=self.options, state=self.search_state)
-        losses = {
-            "rec": torch.mean(torch.abs(self.data - p)) * inv_world,
-            "smoothing": self._per_clip(residuals.second_diff_l1, p) * inv_world,
-            "contact": residuals.contact_robust_loss(d_a2b.index_select(1, self.contact_ids)) * inv_world,
-            "scene2body": s_b2a.sum() / float(self.T * self.M),
-            "world_smoothing": self._per_clip(residuals.first_diff_l1, joints) * inv_world,
-            "vert_smoothing": self._per_clip(residuals.second_diff_l1, verts) * inv_world,
+        # raw terms; each is scaled so that the sum over ranks of the local totals is the global loss: replicated terms by
+        # 1/world, the shard-local scene -> body sum by the GLOBAL point count, the frame-sharded VPoser term already is
+        # a share.  The weighted total is ONE stack . weights product (it replaced ~25 scalar multiply / add launches
+        # and as many in the backward).
+        terms = {
+            "rec": (torch.mean(torch.abs(self.data - p)), inv_world),
+            "smoothing": (self._per_clip(residuals.second_diff_l1, p), inv_world),
+            "contact": (residuals.contact_robust_loss(d_a2b.index_select(1, self.contact_ids)), inv_world),
+            "scene2body": (s_b2a.sum(), 1.0 / float(self.T * self.M)),
+            "world_smoothing": (self._per_clip(residuals.first_diff_l1, joints), inv_world),
+            "vert_smoothing": (self._per_clip(residuals.second_diff_l1, verts), inv_world),
         }
         if self.front_end and self.dct_batches:
-            extra_losses["dct"] = self._dct(joints) * inv_world      # :310
-        losses.update(extra_losses)
-        losses["total"] = sum(W[k] * v for k, v in losses.items())
+            terms["dct"] = (self._dct(joints), inv_world)      # :310
+        for k, v in extra_losses.items():
+            terms[k] = (v, 1.0)                                  # (already scaled in _body)
+        keys = tuple(terms)
+        if getattr(self, "_loss_keys", None) != keys:
+            self._loss_keys = keys
+            self._loss_w = torch.tensor([W[k] * terms[k][1] for k in keys], dtype=torch.float32, device=self.device)
+        stacked = torch.stack([terms[k][0].reshape(()) for k in keys])
+        losses = {k: stacked[i].detach() * terms[k][1] for i, k in enumerate(keys)} if self.report_terms else {}
+        losses["total"] = torch.dot(stacked, self._loss_w)
         return losses
 
     def _dct(self, joints):
