@@ -117,11 +117,13 @@ class FitProblem:
                  rank: int = 0, world_size: int = 1, group=None, idx_dtype=torch.int64, presort_scene: bool = True,
                  front_end: bool = False, dct_frames: int = DCT_FRAMES, mode: str = "global", fused: bool = True,
                  comm: str = "p2p", options: Optional[chamfer.SearchOptions] = None, clips: int = 1,
-                 scene_order: str = "kd", shard_frames: bool = True):
+                 scene_order: str = "kd", shard_frames: bool = True, scene_points: Optional[torch.Tensor] = None):
         """clips > 1: T is the TOTAL number of frames of `clips` independent clips of T/clips frames batched into one
         step (BASELINE.json configs[4]); the temporal residuals never couple frames of different clips.
         fused: scene -> body reduced inside the search kernel (chamfer.scene_to_body_sum) instead of materialising
         [T,M] distances and indices.  comm: "p2p" (peer-memory mailbox) or "nccl" for the sharded key / gradient exchange.
+        scene_points: a ready host scene [M,3] in its final stored order (what a previous FitProblem built as
+        .host_scene for the same M, order and world size) -- skips generation, ordering and dealing.
         shard_frames (sharded runs over the mailbox): the per-frame part of the step -- front-end, body model, world
         placement and their backward -- runs on T / world frames per rank; the vertices are all-gathered through the
         mailbox (backward: reduce-scatter of the vertex gradient), so only the searches' fixed costs stay replicated."""
@@ -173,7 +175,12 @@ class FitProblem:
                 self.host_c_dct = torch.randn(self.dct_batches, 23, 3, self.dct_mtx.shape[1], generator=g)   # :186
         else:
             self.host_params = pack_params(clip)                       # [T,106] observed data (CPU)
-        self.host_scene = make_scene(M, scene_kind, seed) if mode == "global" else torch.zeros(0, 3)
+        if scene_points is not None:
+            if tuple(scene_points.shape) != (M, 3):
+                raise RuntimeError("FitProblem: scene_points must be [M,3]")
+            self.host_scene, presort_scene_now = scene_points, False
+        else:
+            self.host_scene, presort_scene_now = (make_scene(M, scene_kind, seed) if mode == "global" else torch.zeros(0, 3)), True
         self.host_camera_ext = clip["camera_ext"].clone()
         self.host_scale = clip["scale"].clone().reshape(1)
         self.contact_ids = contact_vertex_ids(constants).to(self.device)
@@ -183,7 +190,7 @@ class FitProblem:
         gw = torch.Generator().manual_seed(seed + 5)
         self.host_contact_weight = torch.clamp(0.5 + 0.6 * torch.sin(torch.arange(T) * 0.21 + torch.rand(1, generator=gw) * 6.28), 0, 1)
         self.begin, self.end = sharded.shard_range(M, world_size, rank)
-        if presort_scene and mode == "global":
+        if presort_scene and presort_scene_now and mode == "global":
             # One-time host-side data preparation: the losses do not depend on the order of the scene points (every
             # term is a min / mean over them), so the scene is stored in a spatial order (k-d partition or Morton curve).
             # With several ranks the ordered points are dealt round-robin in blocks, so every rank's shard covers the

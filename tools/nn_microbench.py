@@ -65,10 +65,12 @@ def main():
         return ms
 
     for M in [int(x) for x in args.points.split(",")]:
+        stored = None                                                  # the ordered / dealt host scene, built once per M
         for Q in [int(x) for x in args.queries.split(",")]:
             T = max(1, round(Q / V))
             prob = fpv.FitProblem(T=T, M=M, device=dev, seed=1235, rank=rank, world_size=world, scene_kind=args.scene,
-                                  idx_dtype=torch.int32)
+                                  idx_dtype=torch.int32, scene_points=stored)
+            stored = prob.host_scene
             with torch.no_grad():
                 verts, _, _ = prob._body()
             g = torch.Generator(device=dev).manual_seed(7)

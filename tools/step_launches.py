@@ -13,7 +13,7 @@ ap.add_argument("--scene-order", default="kd")
 args = ap.parse_args()
 fpv = importlib.import_module("4dcapture-fpv_b200")
 dev = torch.device("cuda:0")
-prob = fpv.FitProblem(T=args.T, M=args.M if args.mode == "global" else 0, device=dev, seed=1235, front_end=True, mode=args.mode,
+prob = fpv.FitProblem(T=args.T, M=0 if args.mode == "local" else args.M, device=dev, seed=1235, front_end=True, mode=args.mode,
                       idx_dtype=torch.int32, scene_order=args.scene_order)
 for _ in range(4):
     prob.step(update=True)
