@@ -1,0 +1,42 @@
+"""Sweeps the slice count of the pipelined fused scene->body search (search of slice k+1 overlapping the accumulate pass of
+slice k) at config-2 shapes; run on the GPU box.  Prints ms per call (median of reps) and checks the results are bitwise equal."""
+import importlib, os, sys
+import torch
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+fpv = importlib.import_module("4dcapture-fpv_b200")
+L = fpv._lib.lib()
+dev = torch.device("cuda:0")
+T = int(sys.argv[1]) if len(sys.argv) > 1 else 300
+M = int(sys.argv[2]) if len(sys.argv) > 2 else 1_000_000
+splits = [int(x) for x in sys.argv[3].split(",")] if len(sys.argv) > 3 else [1, 2, 3, 4, 6, 8, 12, 16]
+prob = fpv.FitProblem(T=T, M=M, device=dev, seed=1235)
+with torch.no_grad():
+    verts, _, _ = prob._body()
+state = fpv.SearchState()
+g = torch.Generator(device=dev).manual_seed(3)
+moved = [verts + 0.002 * k * torch.randn(verts.shape, device=dev, generator=g) for k in range(4)]
+
+
+def run(v):
+    v = v.clone().requires_grad_(True)
+    s = fpv.scene_to_body_sum(v, prob.scene, state=state)
+    s.sum().backward()
+    return s.detach().clone(), v.grad.clone()
+
+
+ref = None
+for k in splits:
+    L.fpv_nn_sphere_set_chunking(-100 - k) if k > 1 else L.fpv_nn_sphere_set_chunking(-101)
+    run(moved[0]); run(moved[1])
+    torch.cuda.synchronize()
+    ms = []
+    for r in range(6):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        v = moved[r % 4]
+        e0.record(); out = run(v); e1.record(); torch.cuda.synchronize()
+        ms.append(e0.elapsed_time(e1))
+    out = run(moved[3])
+    if ref is None:
+        ref = out
+    same = torch.equal(out[0], ref[0]) and torch.equal(out[1], ref[1])
+    print(f"slices={k:3d}: fwd+bwd {sorted(ms)[len(ms)//2]:8.3f} ms  (min {min(ms):.3f})  same={same}", flush=True)
