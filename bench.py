@@ -135,7 +135,7 @@ def cpu_reference_step(T: int, M: int, budget_s: float = 12.0, seed: int = 1235)
     return 1.0 / t_full, cores, sample, t_ch + t_smplx + t_probe
 
 
-def ncu_traffic(kernel_name, args, world):
+def ncu_traffic(kernel_name, args, world, section=None):
     """DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture (profiles/), or None when
     the capture does not describe this workload."""
     for fn in ("r02_dram_traffic.json", "r01_dram_traffic.json"):
@@ -147,6 +147,8 @@ def ncu_traffic(kernel_name, args, world):
         w = rec.get("workload", {})
         if (w.get("frames"), w.get("scene_points"), w.get("n_gpus"), w.get("scene")) != (args.T, args.M, world, args.scene):
             continue
+        if section:
+            rec = rec.get(section, {})
         for key, val in rec.items():
             if isinstance(val, (int, float)) and kernel_name.startswith(key):
                 return float(val)
@@ -361,6 +363,15 @@ def run_b200(args):
                                      "the per-frame sums and the per-vertex accumulators); the carried seed buffer is NOT counted",
                 "note": "exact search through a bounding-sphere hierarchy: the binding resource is FP32 issue on the per-query "
                         "sphere tests and the surviving clusters, not HBM (profiles/r02_nn_sphere_ncu.md)"}
+    winst = ncu_traffic(dom[0], args, world, section="warp_instructions")
+    if winst:
+        # what actually binds the kernel: warp instructions per launch (ncu count of the committed capture; the search is
+        # deterministic, so the count belongs to the workload) over the LIVE launch time, against 4 schedulers x SMs x clock
+        sm_mhz = float((clocks or {}).get("sm_mhz") or 1965.0)
+        peak_issue = 4.0 * torch.cuda.get_device_properties(dev).multi_processor_count * sm_mhz * 1e6
+        roofline["issue"] = {"warp_instructions_per_launch": winst, "achieved_Ginst_per_s": winst / (dms * 1e-3) / 1e9,
+                             "peak_Ginst_per_s": peak_issue / 1e9, "frac": winst / (dms * 1e-3) / peak_issue,
+                             "source": "instruction count: ncu smsp__inst_executed.sum (profiles/r02_nn_sphere_ncu.md); time: live"}
     extra = {}
     st = prob.search_state.stats.get("tiles_searched_b2a")
     if st is not None and dom[0].startswith("nn_sphere"):
