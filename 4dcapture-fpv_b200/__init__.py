@@ -27,7 +27,7 @@ from .chamfer import (NN_loss, SearchOptions, SearchState, body_to_scene, chamfe
 from .fit import FitProblem, LOSS_WEIGHTS  # noqa: F401
 from .residuals import (body2world, contact_robust_loss, first_diff_l1, second_diff_l1,  # noqa: F401
                         verts_transform)
-from .prior import (VPoserDecoderB200, aa_to_rot6d, body_params_encapsulate_batch, cal_dctloss,  # noqa: F401
+from .prior import (VPoserDecoderB200, aa_to_rot6d, body_params_encapsulate_batch, cal_dctloss, front_end_split,  # noqa: F401
                     convert_to_3D_rot, convert_to_6D_rot, dct_basis, make_vposer_weights, rot6d_to_aa)
 from .sharded import allreduce_grads, combine_keys, distChamferSharded, shard_range  # noqa: F401
 from . import io_formats, p2p, sharded, spatial, synthetic  # noqa: F401

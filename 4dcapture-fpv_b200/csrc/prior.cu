@@ -225,74 +225,150 @@ __global__ void aa_to_rot6d_kernel(const float *__restrict__ aa, int64_t n, floa
 }
 
 // ---------------------------------------------------------------------------------------------
-// VPoser decoder: one CTA per frame, one thread per hidden unit; weights are read in the layout that makes
-// the accesses of a warp contiguous (transposed copies forward, nn.Linear's own [out][in] backward).
+// VPoser decoder: one CTA per FR consecutive frames, one thread per hidden unit; weights are read in the layout that
+// makes the accesses of a warp contiguous (transposed copies forward, nn.Linear's own [out][in] backward).  The kernel is
+// bound by the L2 reads of the 1.3 MB of weights per CTA: a weight fetched once serves FR frames (FR accumulators per
+// thread, each frame's own k-ascending FMA chain: the result of a frame does not depend on FR).
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ float lrelu(float x) { return x > 0.f ? x : 0.2f * x; }
 
-__global__ void vposer_fwd_kernel(const fpv_vposer_model m, const float *__restrict__ z, float *__restrict__ aa,
-                                  float *__restrict__ saved) {
-    extern __shared__ float sm[];
-    const int H = m.hidden, Z = m.latent, O = 6 * m.joints;
-    float *sz = sm, *h1 = sz + Z, *h2 = h1 + H, *y = h2 + H;
-    const int64_t t = blockIdx.x;
-    const int o = threadIdx.x;
-    if (o < Z) sz[o] = z[t * Z + o];
-    __syncthreads();
-    if (o < H) {
-        float acc = m.b1[o];
-        for (int k = 0; k < Z; ++k) acc = fmaf(m.w1t[int64_t(k) * H + o], sz[k], acc);
-        h1[o] = lrelu(acc);
+// acc[f] += sum_{k0 <= k < k1} w[k * ld + o] * s[f * S + k]  (k ascending; 16 independent weight loads in flight per
+// thread: the loops are bound by the L2 latency of the weight fetches, not by bandwidth or arithmetic)
+template <int FR>
+__device__ __forceinline__ void vp_dot(const float *__restrict__ w, int ld, int o, int k0, int k1, const float *s, int S,
+                                       float (&acc)[FR]) {
+#pragma unroll 16
+    for (int k = k0; k < k1; ++k) {
+        const float wv = __ldg(w + int64_t(k) * ld + o);
+#pragma unroll
+        for (int f = 0; f < FR; ++f) acc[f] = fmaf(wv, s[f * S + k], acc[f]);
     }
-    __syncthreads();
-    if (o < H) {
-        float acc = m.b2[o];
-        for (int k = 0; k < H; ++k) acc = fmaf(m.w2t[int64_t(k) * H + o], h1[k], acc);
-        h2[o] = lrelu(acc);
-    }
-    __syncthreads();
-    if (o < O) {
-        float acc = m.b3[o];
-        for (int k = 0; k < H; ++k) acc = fmaf(m.w3t[int64_t(k) * O + o], h2[k], acc);
-        y[o] = acc;
-    }
-    __syncthreads();
-    if (o < m.joints) rot6d_to_aa_f(y + 6 * o, aa + (t * m.joints + o) * 3);
-    // saved for the backward: post-activations (leaky ReLU keeps the sign) and the 6D output
-    float *sv = saved + t * int64_t(2 * H + O);
-    if (o < H) {
-        sv[o] = h1[o];
-        sv[H + o] = h2[o];
-    }
-    if (o < O) sv[2 * H + o] = y[o];
 }
 
-__global__ void vposer_bwd_kernel(const fpv_vposer_model m, const float *__restrict__ saved,
-                                  const float *__restrict__ g_aa, float *__restrict__ g_z) {
+// A layer with few outputs (NO << blockDim) would leave most of the CTA idle behind a K-long serial loop: the thread
+// groups split K instead, partial sums meet in shared memory and are added in group order (fixed: deterministic).
+// Returns through out[f * S_out + o] for o < NO.  `part` holds blockDim * FR floats.  Ends with a barrier.
+template <int FR>
+__device__ __forceinline__ void vp_layer_split(const float *__restrict__ w, const float *__restrict__ bias, int NO, int K,
+                                               const float *s, int S, float *part, float *out, int S_out) {
+    const int o = threadIdx.x, nthr = blockDim.x;
+    const int NOP = (NO + 31) & ~31;
+    const int G = nthr / NOP > 0 ? nthr / NOP : 1;
+    const int g = o / NOP, oo = o - g * NOP;
+    if (g < G && oo < NO) {
+        const int chunk = (K + G - 1) / G;
+        const int k0 = g * chunk, k1 = k0 + chunk < K ? k0 + chunk : K;
+        float acc[FR];
+#pragma unroll
+        for (int f = 0; f < FR; ++f) acc[f] = (g == 0 && bias) ? bias[oo] : 0.f;
+        vp_dot<FR>(w, NO, oo, k0, k1, s, S, acc);
+#pragma unroll
+        for (int f = 0; f < FR; ++f) part[f * nthr + o] = acc[f];
+    }
+    __syncthreads();
+    if (o < NO) {
+#pragma unroll
+        for (int f = 0; f < FR; ++f) {
+            float v = part[f * nthr + o];
+            for (int gg = 1; gg < G; ++gg) v += part[f * nthr + gg * NOP + o];
+            out[f * S_out + o] = v;
+        }
+    }
+    __syncthreads();
+}
+
+template <int FR>
+__global__ void vposer_fwd_kernel(const fpv_vposer_model m, const float *__restrict__ z, float *__restrict__ aa,
+                                  float *__restrict__ saved, int64_t T) {
     extern __shared__ float sm[];
     const int H = m.hidden, Z = m.latent, O = 6 * m.joints;
-    float *gy = sm, *g2 = gy + O, *g1 = g2 + H;
-    const int64_t t = blockIdx.x;
+    const int S = Z + 2 * H + O;  // per frame: sz[Z], h1[H], h2[H], y[O]
+    float *part = sm + FR * S;    // blockDim * FR partial sums of the split output layer
+    const int64_t t0 = int64_t(blockIdx.x) * FR;
+    const int nf = int(T - t0 < FR ? T - t0 : FR);
     const int o = threadIdx.x;
-    const float *sv = saved + t * int64_t(2 * H + O);
-    if (o < m.joints) rot6d_to_aa_vjp(sv + 2 * H + 6 * o, g_aa + (t * m.joints + o) * 3, gy + 6 * o);
+    for (int i = o; i < FR * Z; i += blockDim.x) {
+        const int f = i / Z, k = i - f * Z;
+        sm[f * S + k] = f < nf ? z[(t0 + f) * Z + k] : 0.f;
+    }
     __syncthreads();
+    float acc[FR];
     if (o < H) {
-        float acc = 0.f;
-        for (int k = 0; k < O; ++k) acc = fmaf(m.w3[int64_t(k) * H + o], gy[k], acc);
-        g2[o] = sv[H + o] > 0.f ? acc : 0.2f * acc;
+#pragma unroll
+        for (int f = 0; f < FR; ++f) acc[f] = m.b1[o];
+        vp_dot<FR>(m.w1t, H, o, 0, Z, sm, S, acc);
+#pragma unroll
+        for (int f = 0; f < FR; ++f) sm[f * S + Z + o] = lrelu(acc[f]);
     }
     __syncthreads();
     if (o < H) {
-        float acc = 0.f;
-        for (int k = 0; k < H; ++k) acc = fmaf(m.w2[int64_t(k) * H + o], g2[k], acc);
-        g1[o] = sv[o] > 0.f ? acc : 0.2f * acc;
+#pragma unroll
+        for (int f = 0; f < FR; ++f) acc[f] = m.b2[o];
+        vp_dot<FR>(m.w2t, H, o, 0, H, sm + Z, S, acc);
+#pragma unroll
+        for (int f = 0; f < FR; ++f) sm[f * S + Z + H + o] = lrelu(acc[f]);
     }
     __syncthreads();
-    if (o < Z) {
-        float acc = 0.f;
-        for (int k = 0; k < H; ++k) acc = fmaf(m.w1[int64_t(k) * Z + o], g1[k], acc);
-        g_z[t * Z + o] = acc;
+    vp_layer_split<FR>(m.w3t, m.b3, O, H, sm + Z + H, S, part, sm + Z + 2 * H, S);
+    for (int i = o; i < nf * m.joints; i += blockDim.x) {
+        const int f = i / m.joints, j = i - f * m.joints;
+        rot6d_to_aa_f(sm + f * S + Z + 2 * H + 6 * j, aa + ((t0 + f) * m.joints + j) * 3);
+    }
+    // saved for the backward: post-activations (leaky ReLU keeps the sign) and the 6D output
+    for (int f = 0; f < nf; ++f) {
+        float *sv = saved + (t0 + f) * int64_t(2 * H + O);
+        const float *fr = sm + f * S + Z;
+        if (o < H) {
+            sv[o] = fr[o];
+            sv[H + o] = fr[H + o];
+        }
+        if (o < O) sv[2 * H + o] = fr[2 * H + o];
+    }
+}
+
+template <int FR>
+__global__ void vposer_bwd_kernel(const fpv_vposer_model m, const float *__restrict__ saved,
+                                  const float *__restrict__ g_aa, float *__restrict__ g_z, int64_t T) {
+    extern __shared__ float sm[];
+    const int H = m.hidden, Z = m.latent, O = 6 * m.joints;
+    const int S = O + 2 * H + Z;  // per frame: gy[O], g2[H], g1[H], gz[Z]
+    float *part = sm + FR * S;
+    const int64_t t0 = int64_t(blockIdx.x) * FR;
+    const int nf = int(T - t0 < FR ? T - t0 : FR);
+    const int o = threadIdx.x;
+    const int64_t svs = int64_t(2 * H + O);
+    for (int i = o; i < FR * m.joints; i += blockDim.x) {
+        const int f = i / m.joints, j = i - f * m.joints;
+        if (f < nf) {
+            rot6d_to_aa_vjp(saved + (t0 + f) * svs + 2 * H + 6 * j, g_aa + ((t0 + f) * m.joints + j) * 3, sm + f * S + 6 * j);
+        } else {
+            for (int c = 0; c < 6; ++c) sm[f * S + 6 * j + c] = 0.f;
+        }
+    }
+    __syncthreads();
+    float acc[FR];
+    if (o < H) {
+#pragma unroll
+        for (int f = 0; f < FR; ++f) acc[f] = 0.f;
+        vp_dot<FR>(m.w3, H, o, 0, O, sm, S, acc);
+#pragma unroll
+        for (int f = 0; f < FR; ++f)
+            sm[f * S + O + o] = (f < nf && saved[(t0 + f) * svs + H + o] > 0.f) ? acc[f] : 0.2f * acc[f];
+    }
+    __syncthreads();
+    if (o < H) {
+#pragma unroll
+        for (int f = 0; f < FR; ++f) acc[f] = 0.f;
+        vp_dot<FR>(m.w2, H, o, 0, H, sm + O, S, acc);
+#pragma unroll
+        for (int f = 0; f < FR; ++f)
+            sm[f * S + O + H + o] = (f < nf && saved[(t0 + f) * svs + o] > 0.f) ? acc[f] : 0.2f * acc[f];
+    }
+    __syncthreads();
+    vp_layer_split<FR>(m.w1, nullptr, Z, H, sm + O + H, S, part, sm + O + 2 * H, S);
+    for (int i = o; i < nf * Z; i += blockDim.x) {
+        const int f = i / Z, k = i - f * Z;
+        g_z[(t0 + f) * Z + k] = sm[f * S + O + 2 * H + k];
     }
 }
 
@@ -345,22 +421,35 @@ __global__ void dct_bwd_x_kernel(const float *__restrict__ x, const float *__res
     }
 }
 
-// one thread per coefficient: fixed-order sum over the F frames of its window
-__global__ void dct_bwd_coef_kernel(const float *__restrict__ x, const float *__restrict__ basis,
-                                    const float *__restrict__ coef, int64_t NB, int64_t F, int64_t C, int64_t K,
-                                    const float *__restrict__ g_out, float *__restrict__ grad_coef) {
-    const int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
-    if (i >= NB * C * K) return;
-    const int64_t k = i % K, c = (i / K) % C, nb = i / (K * C);
+// one warp per (window, channel): the lanes take the F frames of the window (residual and its weight once per frame, not
+// once per coefficient), then every coefficient is one fixed-tree warp sum over the frames (deterministic)
+__global__ void __launch_bounds__(128) dct_bwd_coef_kernel(const float *__restrict__ x, const float *__restrict__ basis,
+                                                           const float *__restrict__ coef, int64_t NB, int64_t F, int64_t C,
+                                                           int64_t K, const float *__restrict__ g_out,
+                                                           float *__restrict__ grad_coef) {
+    const int lane = threadIdx.x & 31;
+    const int64_t i = int64_t(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);  // (nb, c)
+    if (i >= NB * C) return;
+    const int64_t c = i % C, nb = i / C;
     const float gs = g_out[0] / float(NB * C);
-    float acc = 0.f;
-    for (int64_t f = 0; f < F; ++f) {
-        const int64_t e = (nb * F + f) * C + c;
-        const float r = dct_residual(x, basis, coef, F, C, K, e);
-        const float q = fmaf(r, r, 1.0f);
-        acc = fmaf(-2.0f * r / (q * q), basis[f * K + k], acc);
+    for (int64_t k0 = 0; k0 < K; k0 += 32) {  // coefficients in chunks of 32: lane k keeps chunk coefficient k
+        float mine = 0.f;
+        for (int64_t f0 = 0; f0 < F; f0 += 32) {
+            const int64_t f = f0 + lane;
+            float w = 0.f;
+            if (f < F) {
+                const float r = dct_residual(x, basis, coef, F, C, K, (nb * F + f) * C + c);
+                const float q = fmaf(r, r, 1.0f);
+                w = -2.0f * r / (q * q);
+            }
+            const int64_t kn = (K - k0 < 32) ? K - k0 : 32;
+            for (int64_t k = 0; k < kn; ++k) {
+                const float s = __shfl_sync(0xffffffffu, warp_sum(f < F ? w * basis[f * K + k0 + k] : 0.f), 0);  // total in lane 0
+                if (lane == k) mine += s;
+            }
+        }
+        if (k0 + lane < K) grad_coef[i * K + k0 + lane] = gs * mine;
     }
-    grad_coef[i] = gs * acc;
 }
 
 }  // namespace fpv
@@ -390,6 +479,14 @@ int fpv_aa_to_rot6d(const float *aa, int64_t n, float *out6, fpv_stream_t stream
     return FPV_OK;
 }
 
+// frames per CTA: as many as keep about one CTA per SM (the weights are re-read from L2 once per CTA)
+static int vposer_frames_per_cta(int64_t T, size_t smem_per_frame) {
+    const int64_t sms = sm_count();
+    int fr = T >= 4 * sms ? 4 : (T >= 2 * sms - 8 ? 2 : 1);
+    while (fr > 1 && fr * smem_per_frame > 48 * 1024) fr >>= 1;  // stay inside the default dynamic shared-memory limit
+    return fr;
+}
+
 static int vposer_check(const fpv_vposer_model *m, const char *who) {
     FPV_CHECK_ARG(m && m->w1 && m->w2 && m->w3 && m->w1t && m->w2t && m->w3t && m->b1 && m->b2 && m->b3,
                   "%s: null weight pointer", who);
@@ -409,8 +506,16 @@ int fpv_vposer_decode_fwd(const fpv_vposer_model *m, const float *z, int64_t T, 
     if (int rc = vposer_check(m, "fpv_vposer_decode_fwd")) return rc;
     FPV_CHECK_ARG(z && aa && saved && T > 0, "fpv_vposer_decode_fwd: empty input");
     const int threads = int(align_up(size_t(m->hidden), 32));
-    const size_t smem = size_t(m->latent + 2 * m->hidden + 6 * m->joints) * sizeof(float);
-    vposer_fwd_kernel<<<(unsigned)T, threads, smem, static_cast<cudaStream_t>(stream)>>>(*m, z, aa, saved);
+    // per frame: activations + one partial sum per thread for the split output layer
+    const size_t smem = size_t(m->latent + 2 * m->hidden + 6 * m->joints + threads) * sizeof(float);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int fr = vposer_frames_per_cta(T, smem);
+    if (fr == 4)
+        vposer_fwd_kernel<4><<<(unsigned)ceil_div(T, 4), threads, 4 * smem, st>>>(*m, z, aa, saved, T);
+    else if (fr == 2)
+        vposer_fwd_kernel<2><<<(unsigned)ceil_div(T, 2), threads, 2 * smem, st>>>(*m, z, aa, saved, T);
+    else
+        vposer_fwd_kernel<1><<<(unsigned)T, threads, smem, st>>>(*m, z, aa, saved, T);
     FPV_LAUNCH_CHECK("vposer_fwd_kernel");
     return FPV_OK;
 }
@@ -420,8 +525,15 @@ int fpv_vposer_decode_bwd(const fpv_vposer_model *m, const float *saved, const f
     if (int rc = vposer_check(m, "fpv_vposer_decode_bwd")) return rc;
     FPV_CHECK_ARG(saved && g_aa && g_z && T > 0, "fpv_vposer_decode_bwd: empty input");
     const int threads = int(align_up(size_t(m->hidden), 32));
-    const size_t smem = size_t(2 * m->hidden + 6 * m->joints) * sizeof(float);
-    vposer_bwd_kernel<<<(unsigned)T, threads, smem, static_cast<cudaStream_t>(stream)>>>(*m, saved, g_aa, g_z);
+    const size_t smem = size_t(m->latent + 2 * m->hidden + 6 * m->joints + threads) * sizeof(float);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int fr = vposer_frames_per_cta(T, smem);
+    if (fr == 4)
+        vposer_bwd_kernel<4><<<(unsigned)ceil_div(T, 4), threads, 4 * smem, st>>>(*m, saved, g_aa, g_z, T);
+    else if (fr == 2)
+        vposer_bwd_kernel<2><<<(unsigned)ceil_div(T, 2), threads, 2 * smem, st>>>(*m, saved, g_aa, g_z, T);
+    else
+        vposer_bwd_kernel<1><<<(unsigned)T, threads, smem, st>>>(*m, saved, g_aa, g_z, T);
     FPV_LAUNCH_CHECK("vposer_bwd_kernel");
     return FPV_OK;
 }
@@ -461,7 +573,7 @@ int fpv_dct_prior_bwd(const float *x, const float *basis, const float *coef, int
         FPV_LAUNCH_CHECK("dct_bwd_x_kernel");
     }
     if (grad_coef) {
-        dct_bwd_coef_kernel<<<(unsigned)ceil_div(NB * C * K, 128), 128, 0, st>>>(x, basis, coef, NB, F, C, K, g_out, grad_coef);
+        dct_bwd_coef_kernel<<<(unsigned)ceil_div(NB * C, 4), 128, 0, st>>>(x, basis, coef, NB, F, C, K, g_out, grad_coef);
         FPV_LAUNCH_CHECK("dct_bwd_coef_kernel");
     }
     return FPV_OK;

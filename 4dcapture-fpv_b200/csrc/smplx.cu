@@ -239,9 +239,21 @@ __global__ void extras_fwd_kernel(const fpv_smplx_model_t m, const float *__rest
         joints[(t * joints_stride + NJ + e) * 3 + c] = verts[(t * m.num_verts + v) * 3 + c];
 }
 
-// effective vertex gradient: g_vertices + the gradient of the extra joints picked from this vertex
+// effective vertex gradient: g_vertices + the gradient of the extra joints picked from this vertex.  `mask` is a CTA-shared
+// bitmap of the vertices that carry an extra joint (ex_mask_build): only those walk the list of extras -- one bit test for
+// the other 10,4xx vertices instead of E comparisons each (the list walk was 2/3 of jointgrad_kernel's instructions).
+constexpr int EX_MASK_WORDS = 512;  // covers 16,384 vertices; vertices beyond it always walk the list
+__device__ __forceinline__ void ex_mask_build(unsigned *mask, const int *ex_id, int E) {
+    for (int k = threadIdx.x; k < EX_MASK_WORDS; k += blockDim.x) mask[k] = 0u;
+    __syncthreads();
+    for (int e = threadIdx.x; e < E; e += blockDim.x) {
+        const int v = ex_id[e];
+        if (v >= 0 && (v >> 5) < EX_MASK_WORDS) atomicOr(&mask[v >> 5], 1u << (v & 31));
+    }
+    __syncthreads();
+}
 __device__ __forceinline__ void eff_grad(const float *__restrict__ g_verts, int64_t t, int V, int v, int E,
-                                         const int *ex_id, const float (*ex_g)[3], float *g) {
+                                         const int *ex_id, const float (*ex_g)[3], const unsigned *mask, float *g) {
     if (g_verts) {
         const float *s = g_verts + (t * V + v) * 3;
         g[0] = s[0];
@@ -250,11 +262,13 @@ __device__ __forceinline__ void eff_grad(const float *__restrict__ g_verts, int6
     } else {
         g[0] = g[1] = g[2] = 0.f;
     }
-    for (int e = 0; e < E; ++e) {
-        if (ex_id[e] == v) {
-            g[0] += ex_g[e][0];
-            g[1] += ex_g[e][1];
-            g[2] += ex_g[e][2];
+    if (E > 0 && ((v >> 5) >= EX_MASK_WORDS || ((mask[v >> 5] >> (v & 31)) & 1u))) {
+        for (int e = 0; e < E; ++e) {
+            if (ex_id[e] == v) {
+                g[0] += ex_g[e][0];
+                g[1] += ex_g[e][1];
+                g[2] += ex_g[e][2];
+            }
         }
     }
 }
@@ -270,6 +284,7 @@ __global__ void __launch_bounds__(SKIN_THREADS) skin_bwd_kernel(const fpv_smplx_
     __shared__ float A[NJ][12];
     __shared__ int ex_id[MAX_EXTRA];
     __shared__ float ex_g[MAX_EXTRA][3];
+    __shared__ unsigned ex_mask[EX_MASK_WORDS];
     const int64_t t = blockIdx.y;
     const int V = m.num_verts;
     const int E = g_joints ? m.num_extra : 0;
@@ -279,10 +294,11 @@ __global__ void __launch_bounds__(SKIN_THREADS) skin_bwd_kernel(const fpv_smplx_
         for (int c = 0; c < 3; ++c) ex_g[e][c] = g_joints[(t * joints_stride + NJ + e) * 3 + c];
     }
     __syncthreads();
+    ex_mask_build(ex_mask, ex_id, E);
     const int v = blockIdx.x * SKIN_THREADS + threadIdx.x;
     if (v >= V) return;
     float g[3];
-    eff_grad(g_verts, t, V, v, E, ex_id, ex_g, g);
+    eff_grad(g_verts, t, V, v, E, ex_id, ex_g, ex_mask, g);
     float Tm[12];
     blend_transform(A, m.ell_joint, m.ell_weight, m.ell_width, V, v, Tm);
 #pragma unroll
@@ -304,6 +320,7 @@ __global__ void __launch_bounds__(128) jointgrad_kernel(const fpv_smplx_model_t 
     __shared__ float ex_g[MAX_EXTRA][3];
     __shared__ float scratch[32];
     __shared__ float red[8][12];
+    __shared__ unsigned ex_mask[EX_MASK_WORDS];
     const int64_t t = blockIdx.y;
     const int j = blockIdx.x;
     const int V = m.num_verts;
@@ -313,6 +330,7 @@ __global__ void __launch_bounds__(128) jointgrad_kernel(const fpv_smplx_model_t 
         for (int c = 0; c < 3; ++c) ex_g[e][c] = g_joints[(t * joints_stride + NJ + e) * 3 + c];
     }
     __syncthreads();
+    ex_mask_build(ex_mask, ex_id, E);
     float acc[12];
 #pragma unroll
     for (int k = 0; k < 12; ++k) acc[k] = 0.f;
@@ -322,7 +340,7 @@ __global__ void __launch_bounds__(128) jointgrad_kernel(const fpv_smplx_model_t 
             const int v = m.csr_vert[e];
             const float w = m.csr_weight[e];
             float g[3];
-            eff_grad(g_verts, t, V, v, E, ex_id, ex_g, g);
+            eff_grad(g_verts, t, V, v, E, ex_id, ex_g, ex_mask, g);
             const float *vp = vposed + t * ldp + 3 * v;
             const float x = vp[0], y = vp[1], z = vp[2];
 #pragma unroll
@@ -351,7 +369,7 @@ __global__ void __launch_bounds__(128) jointgrad_kernel(const fpv_smplx_model_t 
     } else {
         for (int v = threadIdx.x; v < V; v += blockDim.x) {
             float g[3];
-            eff_grad(g_verts, t, V, v, E, ex_id, ex_g, g);
+            eff_grad(g_verts, t, V, v, E, ex_id, ex_g, ex_mask, g);
             acc[0] += g[0];
             acc[1] += g[1];
             acc[2] += g[2];

@@ -261,6 +261,13 @@ class FitProblem:
         extra = [self.c_dct] if (self.front_end and self.dct_batches) else []
         return [self.params, self.scale, self.camera_ext] + extra
 
+    def _refresh_leaves(self) -> None:
+        self.params = self.params.detach().requires_grad_(True)
+        self.scale = self.scale.detach().requires_grad_(True)
+        self.camera_ext = self.camera_ext.detach().requires_grad_(True)
+        if self.front_end and self.dct_batches:
+            self.c_dct = self.c_dct.detach().requires_grad_(True)
+
     # ---- temporal residuals, clip-aware: frames of different clips are never differenced ----
     def _per_clip(self, fn, x, *rest):
         if self.clips == 1:
@@ -281,7 +288,7 @@ class FitProblem:
         extra_losses = {}
         if self.front_end:
             # global_optimization.py:261-283: 6D row -> axis-angle row -> VPoser decode -> body model
-            bp = prior.body_params_encapsulate_batch(prior.convert_to_3D_rot(p))
+            bp = prior.front_end_split(p)
             z = bp.pop("body_pose_vp")
             cam_transl = bp.pop("camera_translation")
             if self.mode == "global":
@@ -455,6 +462,14 @@ class FitProblem:
         side = torch.cuda.Stream(self.device)
         side.wait_stream(torch.cuda.current_stream(self.device))
         with torch.cuda.stream(side):
+            # Fresh leaf tensors on the same storage.  A leaf's AccumulateGrad node keeps the stream it was CREATED on and
+            # is reused for as long as anything holds it -- the autograd worker thread still holds the last node of a
+            # backward for a moment after backward() returns, so the node of an eager step on the default stream can be
+            # handed from step to step.  During capture the engine would then enqueue a wait on the legacy stream:
+            # cudaErrorStreamCaptureImplicit (round 1: seen under compute-sanitizer, where that window is wide).  New
+            # leaves get their node in the first warm-up step below, on the capture stream.  (Holders of the old tensor
+            # objects still see the values -- same storage -- but not the .grad.)
+            self._refresh_leaves()
             for _ in range(max(1, warmup)):
                 self.step(update=update)
         torch.cuda.current_stream(self.device).wait_stream(side)

@@ -5,6 +5,7 @@ SMPL-X forward and the temporal residual of the `dct` mode, with the reference's
     convert_to_6D_rot(x)      global_optimization.py:96-104    [T,75] -> [T,78]
     VPoserDecoderB200.decode  [3P] human_body_prior v1 VPoser.decode(z, output_type='aa'), call site :270-271
     body_params_encapsulate_batch   column split of the 75-D row (cvae.py:189-208, call site :268)
+    front_end_split(x)        the two above composed as one autograd node (what FitProblem runs)
     cal_dctloss(joints, dct_mtx, c_dct)   FittingOP.cal_dctloss, :232-246
     dct_basis(F, K)           orthonormal DCT-II basis (the reference loads ../Data/DCT_Basis/60.mat, absent)
 
@@ -85,6 +86,54 @@ def body_params_encapsulate_batch(x_body_rec: torch.Tensor) -> Dict[str, torch.T
     return {"transl": x_body_rec[:, :3], "global_orient": x_body_rec[:, 3:6], "betas": x_body_rec[:, 6:16],
             "body_pose_vp": x_body_rec[:, 16:48], "left_hand_pose": x_body_rec[:, 48:60],
             "right_hand_pose": x_body_rec[:, 60:72], "camera_translation": x_body_rec[:, 72:75]}
+
+
+_ROW78 = (3, 6, 10, 32, 12, 12, 3)   # transl | 6D global orientation | betas | VPoser latent | hands | camera translation
+_ROW78_KEYS = ("transl", "global_orient", "betas", "body_pose_vp", "left_hand_pose", "right_hand_pose", "camera_translation")
+
+
+class _FrontEndSplitFn(torch.autograd.Function):
+    """body_params_encapsulate_batch(convert_to_3D_rot(x)) as ONE autograd node: the column blocks of the 78-D row as
+    contiguous tensors, the orientation block decoded to axis-angle.  The backward is the 6D codec's VJP and one
+    concatenation -- the chain of slice / cat nodes it replaces costs a zero-fill, a copy and an add per block."""
+
+    @staticmethod
+    def forward(ctx, x):
+        xc = _f32c(x, "front_end_split")
+        blocks = [b.contiguous() for b in xc.split(_ROW78, dim=1)]
+        n = xc.shape[0]
+        aa = torch.empty(n, 3, dtype=torch.float32, device=xc.device)
+        with torch.cuda.device(xc.device):
+            _lib.check(_lib.lib().fpv_rot6d_to_aa_fwd(_lib.ptr(blocks[1]), n, _lib.ptr(aa), _lib.stream_ptr()),
+                       "fpv_rot6d_to_aa_fwd")
+        ctx.save_for_backward(blocks[1])
+        blocks[1] = aa
+        return tuple(blocks)
+
+    @staticmethod
+    def backward(ctx, *grads):
+        (x6,) = ctx.saved_tensors
+        n = x6.shape[0]
+        cols = []
+        for k, (g, w) in enumerate(zip(grads, _ROW78)):
+            if k == 1:
+                g6 = torch.zeros_like(x6) if g is None else torch.empty_like(x6)
+                if g is not None:
+                    gc = g.contiguous().float()
+                    with torch.cuda.device(x6.device):
+                        _lib.check(_lib.lib().fpv_rot6d_to_aa_bwd(_lib.ptr(x6), n, _lib.ptr(gc), _lib.ptr(g6), _lib.stream_ptr()),
+                                   "fpv_rot6d_to_aa_bwd")
+                cols.append(g6)
+            else:
+                cols.append(g if g is not None else x6.new_zeros(n, w))
+        return torch.cat(cols, dim=1)
+
+
+def front_end_split(x_batch: torch.Tensor) -> Dict[str, torch.Tensor]:
+    """== body_params_encapsulate_batch(convert_to_3D_rot(x_batch)) (global_optimization.py:261-268), fused."""
+    if x_batch.dim() != 2 or x_batch.shape[1] != sum(_ROW78):
+        raise RuntimeError(f"front_end_split: expected [T,{sum(_ROW78)}], got {tuple(x_batch.shape)}")
+    return dict(zip(_ROW78_KEYS, _FrontEndSplitFn.apply(x_batch)))
 
 
 # ---------------------------------------------------------------------------------------------

@@ -93,3 +93,45 @@ def test_dct_loss_matches_reference_golden(fpv, cuda_dev):
     np.testing.assert_allclose(fpv.dct_basis(60, 5).numpy(), d["basis"], atol=1e-7)
     with pytest.raises(RuntimeError):
         fpv.cal_dctloss(joints[:100], basis, c)
+
+
+def test_front_end_split_equals_the_composed_reference_calls(fpv, cuda_dev):
+    """front_end_split == body_params_encapsulate_batch(convert_to_3D_rot(x)) (global_optimization.py:261-268): same
+    values bit for bit, same gradient (the fused node only replaces the slice / cat bookkeeping)."""
+    g = torch.Generator(device="cpu").manual_seed(5)
+    x = torch.randn(37, 78, generator=g).to(cuda_dev)
+    x[:, 3:9] = fpv.convert_to_6D_rot(torch.cat([x[:, :3], 0.4 * x[:, 3:6], x[:, 9:]], 1))[:, 3:9]
+    w = {k: torch.randn(37, n, generator=g).to(cuda_dev)
+         for k, n in zip(("transl", "global_orient", "betas", "body_pose_vp", "left_hand_pose", "right_hand_pose",
+                          "camera_translation"), (3, 3, 10, 32, 12, 12, 3))}
+    xa = x.clone().requires_grad_(True)
+    xb = x.clone().requires_grad_(True)
+    fused = fpv.prior.front_end_split(xa)
+    ref = fpv.body_params_encapsulate_batch(fpv.convert_to_3D_rot(xb))
+    assert list(fused) == list(ref)
+    for k in ref:
+        assert torch.equal(fused[k], ref[k]), k
+    sum((fused[k] * w[k]).sum() for k in w if k != "betas").backward()     # one block without a gradient
+    sum((ref[k] * w[k]).sum() for k in w if k != "betas").backward()
+    assert torch.equal(xa.grad, xb.grad)
+    with pytest.raises(RuntimeError):
+        fpv.prior.front_end_split(x[:, :75])
+
+
+def test_vposer_decode_does_not_depend_on_frames_per_cta(fpv, cuda_dev):
+    """Long clips put 2 or 4 frames on one CTA (one weight fetch serves them all); a frame's result and gradient are
+    bit-identical to the one-frame-per-CTA launch that short batches get."""
+    dec = fpv.VPoserDecoderB200(fpv.make_vposer_weights(seed=7)).to(cuda_dev)
+    g = torch.Generator().manual_seed(4)
+    for T in (301, 1801 if torch.cuda.get_device_properties(cuda_dev).multi_processor_count <= 450 else 4001):
+        z = torch.randn(T, 32, generator=g).to(cuda_dev)
+        cot = torch.randn(T, 1, 21, 3, generator=g).to(cuda_dev)
+        zb = z.clone().requires_grad_(True)
+        big = dec.decode(zb, output_type="aa")
+        (big * cot).sum().backward()
+        for s in range(0, T, 100):                      # 100 frames: always one frame per CTA
+            zs = z[s:s + 100].clone().requires_grad_(True)
+            small = dec.decode(zs, output_type="aa")
+            (small * cot[s:s + 100]).sum().backward()
+            assert torch.equal(small, big[s:s + 100])
+            assert torch.equal(zs.grad, zb.grad[s:s + 100])
