@@ -1000,31 +1000,42 @@ __global__ void sphere_expand_kernel(const float *__restrict__ planes, int64_t M
 // on the order of arrival.
 constexpr int S2B_ROWS = 8;
 
-// rowsum[r][0..2] = sum over the 32 queries of row r of x * 2^k (fixed point): the static part of the fast path
-__global__ void __launch_bounds__(256) s2b_rowsum_kernel(const float *__restrict__ x, int64_t N, float fix_scale,
-                                                         long long *__restrict__ rowsum) {
+// Prepare pass (once per call; the query cloud is shared by every batch): xfix[j][0..2] = round(x_j * 2^k) as int64 --
+// the accumulate pass then splits limbs with two integer instructions per coordinate instead of converting per batch --
+// rowsum[r][0..2] = the sum over the 32 queries of row r (the static part of the one-winner fast path), and *wide != 0
+// when some |xfix| >= 2^41 (then the 32-lane sums need three 21-bit limbs, otherwise two).
+__global__ void __launch_bounds__(256) s2b_prepare_kernel(const float *__restrict__ x, int64_t N, float fix_scale,
+                                                          long long *__restrict__ xfix, long long *__restrict__ rowsum,
+                                                          unsigned *__restrict__ wide) {
     const int lane = threadIdx.x & 31;
     const int64_t row = int64_t(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (row * 32 >= N) return;
     const int64_t i = row * 32 + lane;
+    bool big = false;
 #pragma unroll
     for (int a = 0; a < 3; ++a) {
         const long long v = i < N ? __float2ll_rn(__fmul_rn(__ldg(x + 3 * i + a), fix_scale)) : 0;
+        if (i < N) xfix[3 * i + a] = v;
+        big |= (v >= (1ll << 41)) || (v <= -(1ll << 41));
         const int lo = int(v & 0x1FFFFF), mid = int((v >> 21) & 0x1FFFFF), hi = int(v >> 42);
         const long long slo = __reduce_add_sync(0xffffffffu, lo), smid = __reduce_add_sync(0xffffffffu, mid);
         const long long shi = __reduce_add_sync(0xffffffffu, hi);
         if (lane == 0) rowsum[row * 4 + a] = slo + (smid << 21) + (shi << 42);
     }
     if (lane == 0) rowsum[row * 4 + 3] = 0;
+    if (__any_sync(0xffffffffu, big) && lane == 0) atomicOr(wide, 1u);
 }
 
-__global__ void __launch_bounds__(256) s2b_accum_kernel(const float *__restrict__ x, int64_t N, const int *__restrict__ win,
-                                                        int64_t M, float fix_scale, const long long *__restrict__ rowsum,
+__global__ void __launch_bounds__(256) s2b_accum_kernel(const long long *__restrict__ xfix, int64_t N,
+                                                        const int *__restrict__ win, int64_t M,
+                                                        const long long *__restrict__ rowsum,
+                                                        const unsigned *__restrict__ wide_flag,
                                                         unsigned long long *__restrict__ acc) {
     const int64_t b = blockIdx.y;
     const int lane = threadIdx.x & 31;
     const int64_t row0 = (int64_t(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5)) * (32 * S2B_ROWS);
     if (row0 >= N) return;
+    const bool wide = __ldg(wide_flag) != 0u;  // uniform
     unsigned long long *accb = acc + b * M * 4;
     const int *wb = win + b * N;
     int w[S2B_ROWS];
@@ -1052,17 +1063,27 @@ __global__ void __launch_bounds__(256) s2b_accum_kernel(const float *__restrict_
         }
         long long v[3] = {0, 0, 0};
         if (valid) {
-            v[0] = __float2ll_rn(__fmul_rn(__ldg(x + 3 * i), fix_scale));
-            v[1] = __float2ll_rn(__fmul_rn(__ldg(x + 3 * i + 1), fix_scale));
-            v[2] = __float2ll_rn(__fmul_rn(__ldg(x + 3 * i + 2), fix_scale));
+            v[0] = __ldg(xfix + 3 * i);
+            v[1] = __ldg(xfix + 3 * i + 1);
+            v[2] = __ldg(xfix + 3 * i + 2);
         }
-        // group sums through the integer warp-reduce unit, three 21-bit limbs per coordinate (exact: <= 32 addends)
+        // group sums through the integer warp-reduce unit (exact: <= 32 addends per limb): a low limb of 21 bits and
+        // the signed rest when every |value| < 2^41, three limbs otherwise
+        if (!wide) {
 #pragma unroll
-        for (int k = 0; k < 3; ++k) {
-            const int lo = int(v[k] & 0x1FFFFF), mid = int((v[k] >> 21) & 0x1FFFFF), hi = int(v[k] >> 42);
-            const long long slo = __reduce_add_sync(grp, lo), smid = __reduce_add_sync(grp, mid);
-            const long long shi = __reduce_add_sync(grp, hi);
-            v[k] = slo + (smid << 21) + (shi << 42);
+            for (int k = 0; k < 3; ++k) {
+                const int lo = int(v[k] & 0x1FFFFF), rest = int(v[k] >> 21);
+                const long long slo = __reduce_add_sync(grp, lo), srest = __reduce_add_sync(grp, rest);
+                v[k] = slo + (srest << 21);
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                const int lo = int(v[k] & 0x1FFFFF), mid = int((v[k] >> 21) & 0x1FFFFF), hi = int(v[k] >> 42);
+                const long long slo = __reduce_add_sync(grp, lo), smid = __reduce_add_sync(grp, mid);
+                const long long shi = __reduce_add_sync(grp, hi);
+                v[k] = slo + (smid << 21) + (shi << 42);
+            }
         }
         if (valid && lane == __ffs(grp) - 1) {
             atomicAdd(accb + 4 * int64_t(t) + 0, static_cast<unsigned long long>(v[0]));
@@ -1449,7 +1470,8 @@ int fpv_nn_sphere_search(const float *queries, int q_shared, int64_t batches, in
 size_t fpv_nn_sphere_fused_workspace_bytes(int64_t batches, int64_t N) {
     if (batches <= 0 || N <= 0) return 0;
     return align_up(size_t(batches) * size_t(ceil_div(N, CU_GROUP)) * sizeof(double), 256) +
-           align_up(size_t(ceil_div(N, 32)) * 4 * sizeof(long long), 256) + 256;
+           align_up(size_t(ceil_div(N, 32)) * 4 * sizeof(long long), 256) + align_up(size_t(N) * 3 * sizeof(long long), 256) +
+           256 + 256;
 }
 
 int fpv_fix_shift_for(float max_abs_coordinate, int64_t count) {
@@ -1476,7 +1498,9 @@ int fpv_nn_sphere_fused(const float *queries, int64_t batches, int64_t N, const 
     const int64_t groups = ceil_div(N, CU_GROUP);
     double *partial = ar.take<double>(size_t(batches) * size_t(groups));
     long long *rowsum = ar.take<long long>(size_t(ceil_div(N, 32)) * 4);
-    if (!partial || !rowsum) {
+    long long *xfix = ar.take<long long>(size_t(N) * 3);
+    unsigned *wide = ar.take<unsigned>(1);
+    if (!partial || !rowsum || !xfix || !wide) {
         set_error("fpv_nn_sphere_fused: workspace too small (%zu bytes, need %zu)", workspace_bytes,
                   fpv_nn_sphere_fused_workspace_bytes(batches, N));
         return FPV_ERR_WORKSPACE;
@@ -1492,10 +1516,13 @@ int fpv_nn_sphere_fused(const float *queries, int64_t batches, int64_t N, const 
             snprintf(nm, sizeof(nm), "s2b_accum Q=%lld M=%lld", (long long)(batches * N), (long long)M);
             profile_begin(nm, st, 12.0 * double(N) + 4.0 * double(batches * N) + 32.0 * double(batches * M), double(batches * N));
         }
-        // (the row sums are static per query cloud; recomputing them costs one pass over 12 N bytes, ~2 us per million points)
-        s2b_rowsum_kernel<<<(unsigned)ceil_div(ceil_div(N, 32), 8), 256, 0, st>>>(queries, N, ldexpf(1.0f, fix_shift), rowsum);
+        // (the fixed-point copy and the row sums are static per query cloud; rebuilding them costs one pass of 36 N bytes,
+        // ~10 us per million points)
+        FPV_CUDA(cudaMemsetAsync(wide, 0, sizeof(unsigned), st));
+        s2b_prepare_kernel<<<(unsigned)ceil_div(ceil_div(N, 32), 8), 256, 0, st>>>(queries, N, ldexpf(1.0f, fix_shift), xfix, rowsum,
+                                                                                 wide);
         count_launch();
-        s2b_accum_kernel<<<grid, 256, 0, st>>>(queries, N, seed_inout, M, ldexpf(1.0f, fix_shift), rowsum, acc);
+        s2b_accum_kernel<<<grid, 256, 0, st>>>(xfix, N, seed_inout, M, rowsum, wide, acc);
         profile_end(st);
         FPV_LAUNCH_CHECK("s2b_accum_kernel");
     }

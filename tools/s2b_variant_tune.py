@@ -1,5 +1,7 @@
-"""Sweeps the slice count of the pipelined fused scene->body search (search of slice k+1 overlapping the accumulate pass of
-slice k) at config-2 shapes; run on the GPU box.  Prints ms per call (median of reps) and checks the results are bitwise equal."""
+"""Times the fused scene->body term (forward + backward) at config-2 shapes for a list of tuning codes of
+fpv_nn_sphere_set_chunking (run on the GPU box):  -20 / -21 = accumulate pass without / with sector-coalesced atomics,
+-6 / -7 / -8 = register budget of the search kernel.  (With profiles/r02_fused_pipeline.patch applied: -100 - k = k slices.)
+Prints ms per call (median of reps) and checks that every variant returns bitwise the same sums and gradients."""
 import importlib, os, sys
 import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -8,7 +10,7 @@ L = fpv._lib.lib()
 dev = torch.device("cuda:0")
 T = int(sys.argv[1]) if len(sys.argv) > 1 else 300
 M = int(sys.argv[2]) if len(sys.argv) > 2 else 1_000_000
-splits = [int(x) for x in sys.argv[3].split(",")] if len(sys.argv) > 3 else [1, 2, 3, 4, 6, 8, 12, 16]
+codes = [int(x) for x in sys.argv[3].split(",")] if len(sys.argv) > 3 else [-20, -21, -20, -21]
 prob = fpv.FitProblem(T=T, M=M, device=dev, seed=1235)
 with torch.no_grad():
     verts, _, _ = prob._body()
@@ -25,8 +27,8 @@ def run(v):
 
 
 ref = None
-for k in splits:
-    L.fpv_nn_sphere_set_chunking(-100 - k) if k > 1 else L.fpv_nn_sphere_set_chunking(-101)
+for k in codes:
+    assert L.fpv_nn_sphere_set_chunking(k) == 0, k
     run(moved[0]); run(moved[1])
     torch.cuda.synchronize()
     ms = []
@@ -39,4 +41,4 @@ for k in splits:
     if ref is None:
         ref = out
     same = torch.equal(out[0], ref[0]) and torch.equal(out[1], ref[1])
-    print(f"slices={k:3d}: fwd+bwd {sorted(ms)[len(ms)//2]:8.3f} ms  (min {min(ms):.3f})  same={same}", flush=True)
+    print(f"code={k:4d}: fwd+bwd {sorted(ms)[len(ms)//2]:8.3f} ms  (min {min(ms):.3f})  same={same}", flush=True)
