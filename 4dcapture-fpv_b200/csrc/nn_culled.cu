@@ -1006,11 +1006,12 @@ constexpr int S2B_ROWS = 8;
 // when some |xfix| >= 2^41 (then the 32-lane sums need three 21-bit limbs, otherwise two).
 __global__ void __launch_bounds__(256) s2b_prepare_kernel(const float *__restrict__ x, int64_t N, float fix_scale,
                                                           long long *__restrict__ xfix, long long *__restrict__ rowsum,
-                                                          unsigned *__restrict__ wide) {
-    const int lane = threadIdx.x & 31;
-    const int64_t row = int64_t(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (row * 32 >= N) return;
+                                                          long long *__restrict__ blocksum, unsigned *__restrict__ wide) {
+    __shared__ long long srow[8][3];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t row = int64_t(blockIdx.x) * 8 + warp;   // 8 rows per CTA = the 256 queries one accumulate warp walks
     const int64_t i = row * 32 + lane;
+    const bool live = row * 32 < N;
     bool big = false;
 #pragma unroll
     for (int a = 0; a < 3; ++a) {
@@ -1020,15 +1021,26 @@ __global__ void __launch_bounds__(256) s2b_prepare_kernel(const float *__restric
         const int lo = int(v & 0x1FFFFF), mid = int((v >> 21) & 0x1FFFFF), hi = int(v >> 42);
         const long long slo = __reduce_add_sync(0xffffffffu, lo), smid = __reduce_add_sync(0xffffffffu, mid);
         const long long shi = __reduce_add_sync(0xffffffffu, hi);
-        if (lane == 0) rowsum[row * 4 + a] = slo + (smid << 21) + (shi << 42);
+        const long long sum = slo + (smid << 21) + (shi << 42);
+        if (lane == 0) {
+            if (live) rowsum[row * 4 + a] = sum;
+            srow[warp][a] = sum;
+        }
     }
-    if (lane == 0) rowsum[row * 4 + 3] = 0;
+    if (lane == 0 && live) rowsum[row * 4 + 3] = 0;
     if (__any_sync(0xffffffffu, big) && lane == 0) atomicOr(wide, 1u);
+    __syncthreads();
+    if (threadIdx.x < 3) {   // blocksum[c][0..2]: the sum over the CTA's 256 queries (the all-rows-one-winner fast path)
+        long long sum = 0;
+        for (int w = 0; w < 8; ++w) sum += srow[w][threadIdx.x];
+        blocksum[int64_t(blockIdx.x) * 4 + threadIdx.x] = sum;
+    }
 }
 
 __global__ void __launch_bounds__(256) s2b_accum_kernel(const long long *__restrict__ xfix, int64_t N,
                                                         const int *__restrict__ win, int64_t M,
                                                         const long long *__restrict__ rowsum,
+                                                        const long long *__restrict__ blocksum,
                                                         const unsigned *__restrict__ wide_flag,
                                                         unsigned long long *__restrict__ acc) {
     const int64_t b = blockIdx.y;
@@ -1043,6 +1055,21 @@ __global__ void __launch_bounds__(256) s2b_accum_kernel(const long long *__restr
     for (int r = 0; r < S2B_ROWS; ++r) {   // all index loads of the warp's rows in flight before the first is used
         const int64_t i = row0 + r * 32 + lane;
         w[r] = i < N ? __ldg(wb + i) : -1;
+    }
+    {   // ONE winner for all 256 queries of the warp (deep far field): four atomics with the static block sums
+        const int t0 = __shfl_sync(0xffffffffu, w[0], 0);
+        bool same = true;
+#pragma unroll
+        for (int r = 0; r < S2B_ROWS; ++r) same &= w[r] == t0;
+        if (__all_sync(0xffffffffu, same) && t0 >= 0 && row0 + 32 * S2B_ROWS <= N) {
+            if (lane < 4) {
+                const unsigned long long add =
+                    lane < 3 ? static_cast<unsigned long long>(__ldg(blocksum + (row0 / (32 * S2B_ROWS)) * 4 + lane))
+                             : static_cast<unsigned long long>(32 * S2B_ROWS);
+                atomicAdd(accb + 4 * int64_t(t0) + lane, add);
+            }
+            return;
+        }
     }
 #pragma unroll
     for (int r = 0; r < S2B_ROWS; ++r) {
@@ -1471,7 +1498,7 @@ size_t fpv_nn_sphere_fused_workspace_bytes(int64_t batches, int64_t N) {
     if (batches <= 0 || N <= 0) return 0;
     return align_up(size_t(batches) * size_t(ceil_div(N, CU_GROUP)) * sizeof(double), 256) +
            align_up(size_t(ceil_div(N, 32)) * 4 * sizeof(long long), 256) + align_up(size_t(N) * 3 * sizeof(long long), 256) +
-           256 + 256;
+           align_up(size_t(ceil_div(N, 32 * S2B_ROWS)) * 4 * sizeof(long long), 256) + 256 + 256;
 }
 
 int fpv_fix_shift_for(float max_abs_coordinate, int64_t count) {
@@ -1499,8 +1526,9 @@ int fpv_nn_sphere_fused(const float *queries, int64_t batches, int64_t N, const 
     double *partial = ar.take<double>(size_t(batches) * size_t(groups));
     long long *rowsum = ar.take<long long>(size_t(ceil_div(N, 32)) * 4);
     long long *xfix = ar.take<long long>(size_t(N) * 3);
+    long long *blocksum = ar.take<long long>(size_t(ceil_div(N, 32 * S2B_ROWS)) * 4);
     unsigned *wide = ar.take<unsigned>(1);
-    if (!partial || !rowsum || !xfix || !wide) {
+    if (!partial || !rowsum || !xfix || !blocksum || !wide) {
         set_error("fpv_nn_sphere_fused: workspace too small (%zu bytes, need %zu)", workspace_bytes,
                   fpv_nn_sphere_fused_workspace_bytes(batches, N));
         return FPV_ERR_WORKSPACE;
@@ -1519,10 +1547,11 @@ int fpv_nn_sphere_fused(const float *queries, int64_t batches, int64_t N, const 
         // (the fixed-point copy and the row sums are static per query cloud; rebuilding them costs one pass of 36 N bytes,
         // ~10 us per million points)
         FPV_CUDA(cudaMemsetAsync(wide, 0, sizeof(unsigned), st));
-        s2b_prepare_kernel<<<(unsigned)ceil_div(ceil_div(N, 32), 8), 256, 0, st>>>(queries, N, ldexpf(1.0f, fix_shift), xfix, rowsum,
-                                                                                 wide);
+        static_assert(S2B_ROWS == 8, "s2b_prepare_kernel sums one accumulate warp's queries per CTA of 8 warps");
+        s2b_prepare_kernel<<<(unsigned)ceil_div(N, 32 * S2B_ROWS), 256, 0, st>>>(queries, N, ldexpf(1.0f, fix_shift), xfix, rowsum,
+                                                                               blocksum, wide);
         count_launch();
-        s2b_accum_kernel<<<grid, 256, 0, st>>>(xfix, N, seed_inout, M, rowsum, wide, acc);
+        s2b_accum_kernel<<<grid, 256, 0, st>>>(xfix, N, seed_inout, M, rowsum, blocksum, wide, acc);
         profile_end(st);
         FPV_LAUNCH_CHECK("s2b_accum_kernel");
     }
