@@ -146,6 +146,20 @@ def test_scene_to_body_sum_matches_full_outputs(fpv, cuda_dev, T, N, M, presorte
     np.testing.assert_allclose(grads[0], ga, rtol=1e-5, atol=1e-5 * np.abs(ga).max())
     for k in (1, 2):    # seeded, garbage-seeded: bitwise the same (integer accumulators, fixed-order sums)
         assert np.array_equal(sums[k], sums[0]) and np.array_equal(grads[k], grads[0])
+    # a coarser fixed point (every |value| < 2^41: the accumulate pass then reduces two limbs per coordinate instead of
+    # three -- the path a 1 M-point scene takes) gives the same gradient up to its 2^-33 relative resolution
+    sc = fpv.spatial.cached_scene(bt)
+    assert sc.M == M
+    shift = sc.fix_shift()
+    sc._fix_shift = shift - 8
+    try:
+        ta = torch.tensor(a, device=cuda_dev, requires_grad=True)
+        s = fpv.scene_to_body_sum(ta, bt, clip=True, state=state)
+        (s * torch.tensor(g, device=cuda_dev)).sum().backward()
+        assert np.array_equal(s.detach().cpu().numpy(), sums[0])
+        np.testing.assert_allclose(ta.grad.cpu().numpy(), grads[0], rtol=1e-6, atol=1e-7 * np.abs(ga).max())
+    finally:
+        sc._fix_shift = shift
     # the combined form returns the same sum plus the body->scene direction
     s2, d_a2b, i_a2b = fpv.fit_chamfer_terms(torch.tensor(a, device=cuda_dev), bt, state=fpv.SearchState())
     _, d2, _, i2 = co.dist_chamfer(a, b)
