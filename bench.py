@@ -371,7 +371,7 @@ def run_b200(args):
         peak_issue = 4.0 * torch.cuda.get_device_properties(dev).multi_processor_count * sm_mhz * 1e6
         roofline["issue"] = {"warp_instructions_per_launch": winst, "achieved_Ginst_per_s": winst / (dms * 1e-3) / 1e9,
                              "peak_Ginst_per_s": peak_issue / 1e9, "frac": winst / (dms * 1e-3) / peak_issue,
-                             "source": "instruction count: ncu smsp__inst_executed.sum (profiles/r02_nn_sphere_ncu.md); time: live"}
+                             "source": "instruction count: ncu smsp__inst_executed.sum of the committed capture of this build (profiles/r02_nn_sphere_ncu.md); time: live"}
     extra = {}
     st = prob.search_state.stats.get("tiles_searched_b2a")
     if st is not None and dom[0].startswith("nn_sphere"):
