@@ -246,3 +246,19 @@ def test_drifting_fit_at_benchmark_scene_size_stays_exact(fpv, cuda_dev):
     assert all(np.isfinite(losses)) and losses[-1] < losses[0]          # the optimiser is really descending
     moved = (prob.params.detach().cpu() - prob._host_init).abs().max().item()
     assert moved > 0.02                                                 # 6 Adam steps of lr 0.005: the body drifted
+
+
+def test_fused_terms_tolerate_retain_graph(fpv, cuda_dev):
+    """The reference loop calls loss.backward(retain_graph=True) (global_optimization.py:591): the backward of the fused
+    terms must not consume or change what the forward saved -- a second backward adds exactly the same gradient."""
+    rng = np.random.default_rng(17)
+    a, b = _clouds(rng, 3, 1200, 20000)
+    ta = torch.tensor(a, device=cuda_dev, requires_grad=True)
+    tb = torch.tensor(b, device=cuda_dev).unsqueeze(0)
+    s, d, _ = fpv.fit_chamfer_terms(ta, tb, state=fpv.SearchState())
+    loss = s.sum() / b.shape[0] + d.mean()
+    loss.backward(retain_graph=True)
+    g1 = ta.grad.clone()
+    loss.backward()
+    assert torch.equal(ta.grad, g1 + g1)
+    assert float(g1.abs().max()) > 0
