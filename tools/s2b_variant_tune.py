@@ -1,6 +1,7 @@
 """Times the fused scene->body term (forward + backward) at config-2 shapes for a list of tuning codes of
-fpv_nn_sphere_set_chunking (run on the GPU box):  -20 / -21 = accumulate pass without / with sector-coalesced atomics,
--6 / -7 / -8 = register budget of the search kernel.  (With profiles/r02_fused_pipeline.patch applied: -100 - k = k slices.)
+fpv_nn_sphere_set_chunking (run on the GPU box):  -6 / -7 / -8 = register budget of the search kernel (6 / 7 / 8 CTAs per
+SM).  Experimental builds add codes: with profiles/r02_fused_pipeline.patch applied, -100 - k = k slices of the pipelined
+search; the sector-coalesced accumulate pass of profiles/r02_step_kernels_ncu.md was measured with -20 / -21.
 Prints ms per call (median of reps) and checks that every variant returns bitwise the same sums and gradients."""
 import importlib, os, sys
 import torch
@@ -10,7 +11,7 @@ L = fpv._lib.lib()
 dev = torch.device("cuda:0")
 T = int(sys.argv[1]) if len(sys.argv) > 1 else 300
 M = int(sys.argv[2]) if len(sys.argv) > 2 else 1_000_000
-codes = [int(x) for x in sys.argv[3].split(",")] if len(sys.argv) > 3 else [-20, -21, -20, -21]
+codes = [int(x) for x in sys.argv[3].split(",")] if len(sys.argv) > 3 else [-7, -8, -6, -7]
 prob = fpv.FitProblem(T=T, M=M, device=dev, seed=1235)
 with torch.no_grad():
     verts, _, _ = prob._body()
